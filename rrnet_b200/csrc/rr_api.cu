@@ -1,0 +1,93 @@
+// C-ABI glue of librrnet_b200: version / error strings / launch counter and the one-call
+// eval path (decode -> stage-1 NMS -> RoIAlign+ReLU -> head -> generate_bbox), i.e.
+// RRNet.forward after forward_stage1 (models/rrnet.py:31-54) + RRNetOperator.generate_bbox
+// (operators/rrnet_operator.py:188-209) for the whole batch with no host synchronisation.
+#include "rr_common.cuh"
+
+namespace rr {
+
+std::atomic<uint64_t> g_launches{0};
+
+// implemented in the per-kernel translation units
+int decode_launch(const float*, const float*, const float*, int, int, int, int, int, int, float*, int64_t*,
+                  void*, cudaStream_t);
+size_t decode_ws_bytes(int B);
+int stage1_nms_launch(const float*, int, int, int, double, float*, float*, float*, int32_t*, void*, cudaStream_t);
+size_t stage1_nms_ws_bytes(int B, int K, int C);
+int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, float*, cudaStream_t);
+int head_forward_launch(const float*, const int32_t*, int, const float*, float*, cudaStream_t);
+int generate_bbox_launch(const float*, const float*, const float*, const float*, const int32_t*, int, float,
+                         float*, float*, cudaStream_t);
+
+struct EvalWs {
+    void* decode; void* nms; float* roi_feat; size_t bytes;
+};
+static EvalWs carve_eval(void* ws, int B, int K, int C, int feat_ch) {
+    Carver cv(ws);
+    EvalWs w;
+    w.decode = cv.take<char>(decode_ws_bytes(B));
+    w.nms = cv.take<char>(stage1_nms_ws_bytes(B, K, C));
+    w.roi_feat = cv.take<float>((size_t)B * K * feat_ch * RR_POOL * RR_POOL);
+    w.bytes = cv.off;
+    return w;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+RR_API int rr_version(void) { return 100; }
+
+RR_API uint64_t rr_launch_count(void) { return g_launches.load(); }
+
+RR_API const char* rr_error_string(int code) {
+    switch (code) {
+        case RR_OK: return "ok";
+        case RR_E_BADARG: return "rrnet_b200: bad argument (null pointer or non-positive size)";
+        case RR_E_WORKSPACE: return "rrnet_b200: workspace too small or not 256-byte aligned";
+        case RR_E_RANGE: return "rrnet_b200: size outside the supported range";
+        case RR_E_ALIGN: return "rrnet_b200: pointer not 16-byte aligned";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "rrnet_b200: unknown error";
+}
+
+RR_API size_t rr_eval_workspace_bytes(int B, int C, int H, int W, int K, int feat_ch) {
+    (void)H; (void)W;
+    if (B <= 0 || C <= 0 || K <= 0 || feat_ch <= 0) return 0;
+    return carve_eval(nullptr, B, K, C, feat_ch).bytes;
+}
+
+RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, const float* feat,
+                           int B, int C, int H, int W, int K, int feat_ch, int pool, double nms_thr,
+                           const float* head_folded, float scale,
+                           float* out_dets, int64_t* out_inds,
+                           float* out_bxyxy, float* out_scores, float* out_clses, int32_t* out_counts,
+                           float* out_reg, float* out_s1, float* out_s2, float* roi_feat,
+                           void* ws, size_t ws_bytes, void* stream) {
+    if (!hm || !wh || !off || !feat || !head_folded || !out_dets || !out_bxyxy || !out_scores || !out_clses ||
+        !out_counts || !out_reg || !out_s1 || !out_s2 || !ws)
+        return RR_E_BADARG;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
+    if (feat_ch != RR_HEAD_CH) return RR_E_RANGE;               // the head is 256-channel (fasterrcnn_detector.py:9)
+    if (pool != 0 && pool != 3) return RR_E_BADARG;
+    if (C > RR_MAX_CLASSES || K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;
+    if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
+    if (ws_bytes < carve_eval(nullptr, B, K, C, feat_ch).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    if (((uintptr_t)out_reg & 15) || ((uintptr_t)head_folded & 15)) return RR_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    EvalWs w = carve_eval(ws, B, K, C, feat_ch);
+    float* rf = roi_feat ? roi_feat : w.roi_feat;
+    const int n_cap = B * K;
+    int rc = decode_launch(hm, wh, off, B, C, H, W, K, pool, out_dets, out_inds, w.decode, st);
+    if (rc) return rc;
+    rc = stage1_nms_launch(out_dets, B, K, C, nms_thr, out_bxyxy, out_scores, out_clses, out_counts, w.nms, st);
+    if (rc) return rc;
+    const int32_t* n_dev = out_counts + B;
+    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, rf, st);
+    if (rc) return rc;
+    rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);
+    if (rc) return rc;
+    return generate_bbox_launch(out_bxyxy, out_reg, out_scores, out_clses, n_dev, n_cap, scale, out_s1, out_s2, st);
+}

@@ -1,0 +1,87 @@
+// Shared helpers for librrnet_b200 (sm_100a).  Internal header, not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "../../include/rrnet_b200.h"
+
+#define RR_API extern "C" __attribute__((visibility("default")))
+
+namespace rr {
+
+extern std::atomic<uint64_t> g_launches;   // defined in rr_api.cu
+
+// Count one kernel launch and fold its launch status into `rc` (first error wins).
+#define RR_LAUNCHED(rc)                                                    \
+    do {                                                                   \
+        ::rr::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+        cudaError_t _e = cudaPeekAtLastError();                            \
+        if (_e != cudaSuccess && (rc) == 0) (rc) = (int)_e;                \
+    } while (0)
+
+#define RR_CUDA(call, rc)                                                  \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess && (rc) == 0) (rc) = (int)_e;                \
+    } while (0)
+
+constexpr int kSMs = 148;   // B200
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Carves a caller-provided workspace into 256-byte aligned pieces.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off = align_up(off + count * sizeof(T));
+        return p;
+    }
+};
+
+// Monotone fp32 -> uint32 ordering key (larger float <=> larger key).
+__host__ __device__ __forceinline__ uint32_t f2key(float v) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(v);
+#else
+    uint32_t u;
+    memcpy(&u, &v, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float sigmoid_f32(float z) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z)));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (data is touched once per CTA)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace rr

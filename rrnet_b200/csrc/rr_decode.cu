@@ -1,0 +1,426 @@
+// Heat-map decode for sm_100a: per-image top-K over C*H*W logits, wh/offset gather, box assembly.
+//
+// Replaces RRNet.transform_bbox / _topk / _gather_feat / _transpose_and_gather_feat
+// (models/rrnet.py:83-138): sigmoid over the full map, two torch.topk calls (16-pass radix
+// select over 80 slices), two full NCHW->NHWC permute copies and five gathers become
+//
+//   1. decode_sample_kernel   one CTA per image reads ~16K pseudo-random samples and picks a
+//                             threshold key whose expected population count is ~3K;
+//   2. decode_collect_kernel  ONE streaming pass over the logits (128-bit loads, all SMs):
+//                             elements with key >= threshold are appended to a per-image
+//                             candidate list (shared-memory staging, one global atomic per CTA);
+//   3. decode_select_kernel   one CTA per image sorts the candidates (bitonic, shared memory),
+//                             takes the first K, gathers wh/offset with direct strided loads
+//                             (no permute copy) and writes [B,K,6] + inds.
+//
+// The ranking key is the LOGIT (monotone bit transform); sigmoid is evaluated for the K
+// survivors only.  Ties are ordered by ascending flat index.  The sample threshold is only a
+// speed-up: if the candidate count falls outside [K, CAP] (adversarial data, massive ties,
+// pool=3 on smooth maps) step 3 falls back to an exact in-CTA radix descent over the whole
+// image, so the result is exact for every input.
+//
+// HBM traffic: the logits once (B*C*H*W*4 bytes) + K*4 gathers + outputs.
+// Built with --fmad=false (box arithmetic must round like the reference's separate torch ops).
+#include "rr_common.cuh"
+
+#include <math_constants.h>
+
+namespace rr {
+
+constexpr int kCap = 16384;          // candidate capacity per image (== RR_MAX_TOPK)
+constexpr int kSampleThreads = 1024;
+constexpr int kSamplesPerThread = 16;
+constexpr int kCollectThreads = 256;
+constexpr int kStage = 1024;         // per-CTA staging entries in decode_collect_kernel
+constexpr int kSelectThreads = 1024;
+
+struct DecodeWs {
+    unsigned int* thr_key;            // [B]
+    unsigned int* count;              // [B]
+    unsigned long long* cand;         // [B][kCap]   (key << 32) | ~flat_index
+    size_t bytes;
+};
+static DecodeWs carve_decode(void* ws, int B) {
+    Carver cv(ws);
+    DecodeWs w;
+    w.thr_key = cv.take<unsigned int>(B);
+    w.count = cv.take<unsigned int>(B);
+    w.cand = cv.take<unsigned long long>((size_t)B * kCap);
+    w.bytes = cv.off;
+    return w;
+}
+
+// value used for ranking: the logit, or -inf when pool=3 and the element is not a 3x3 peak
+// (operators/centernet_operator.py:204-210: keep = (maxpool3x3(heat) == heat)).
+__device__ __forceinline__ float pooled_value(const float* __restrict__ img, int H, int W, int HW,
+                                              unsigned flat, float v) {
+    int c = flat / HW, ind = flat - c * HW;
+    int y = ind / W, x = ind - y * W;
+    const float* plane = img + (size_t)c * HW;
+    for (int dy = -1; dy <= 1; ++dy) {
+        int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int xx = x + dx;
+            if (xx < 0 || xx >= W) continue;
+            if (__ldg(plane + yy * W + xx) > v) return -CUDART_INF_F;
+        }
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. threshold estimate from a pseudo-random sample (one CTA per image)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSampleThreads)
+decode_sample_kernel(const float* __restrict__ hm, int H, int W, int N, int K, int pool,
+                     unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) count[b] = 0;
+    if (N <= kCap) {                   // everything fits in the candidate list: no threshold
+        if (tid == 0) thr_key[b] = 0u;
+        return;
+    }
+    const float* img = hm + (size_t)b * N;
+    const int HW = H * W;
+    const unsigned nlines = (unsigned)N / 32u;
+    unsigned keys[kSamplesPerThread];
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int it = 0; it < kSamplesPerThread; ++it) {
+        unsigned L = (unsigned)(warp * kSamplesPerThread + it);
+        unsigned line = (unsigned)(((unsigned long long)L * 2654435761ull + 12345ull) % nlines);
+        unsigned flat = line * 32u + (unsigned)lane;
+        float v = __ldg(img + flat);
+        if (pool == 3) v = pooled_value(img, H, W, HW, flat, v);
+        keys[it] = f2key(v);
+    }
+    // target population count T in [K, kCap]; sample rank r = T * S / N
+    const int S = kSampleThreads * kSamplesPerThread;
+    int target = max(3 * K, K + 2048);
+    target = min(target, (K + kCap) / 2);
+    int r = (int)(((long long)target * S + N - 1) / N);
+    r = max(r, 8);
+    // largest key t with #{sample keys >= t} >= r  (MSB-first descent, 32 block-wide counts)
+    unsigned t = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        unsigned trial = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int it = 0; it < kSamplesPerThread; ++it) c += (keys[it] >= trial);
+        // __syncthreads_count counts threads with non-zero predicate; we need the SUM
+        __shared__ int s_warp[kSampleThreads / 32];
+        int ws = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+        if (lane == 0) s_warp[warp] = ws;
+        __syncthreads();
+        int tot = (lane < kSampleThreads / 32) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        __syncthreads();
+        if (tot >= r) t = trial;
+    }
+    if (tid == 0) thr_key[b] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. streaming collect: grid (ctas_per_image, B)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_candidate(unsigned key, unsigned flat, unsigned long long* s_stage,
+                                               int* s_n, unsigned int* g_count,
+                                               unsigned long long* g_cand) {
+    unsigned long long e = ((unsigned long long)key << 32) | (unsigned long long)(~flat);
+    int slot = atomicAdd(s_n, 1);
+    if (slot < kStage) {
+        s_stage[slot] = e;
+    } else {                            // staging full (dense hits): go straight to global
+        unsigned pos = atomicAdd(g_count, 1u);
+        if (pos < (unsigned)kCap) g_cand[pos] = e;
+    }
+}
+
+__global__ void __launch_bounds__(kCollectThreads)
+decode_collect_kernel(const float* __restrict__ hm, int H, int W, int N, int pool,
+                      const unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count,
+                      unsigned long long* __restrict__ cand) {
+    __shared__ unsigned long long s_stage[kStage];
+    __shared__ int s_n;
+    __shared__ unsigned s_base;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float* img = hm + (size_t)b * N;
+    const unsigned thr = thr_key[b];
+    unsigned int* g_count = count + b;
+    unsigned long long* g_cand = cand + (size_t)b * kCap;
+    const int HW = H * W;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+
+    const bool vec_ok = ((N & 3) == 0) && ((((uintptr_t)img) & 15) == 0);
+    const int stride = gridDim.x * blockDim.x;
+    const int gtid = blockIdx.x * blockDim.x + tid;
+    if (vec_ok) {
+        const float4* p4 = reinterpret_cast<const float4*>(img);
+        const int n4 = N >> 2;
+        int i = gtid;
+        // 4 independent 128-bit loads in flight per thread
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(p4 + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned key = f2key(e[q]);
+                    if (key >= thr) {
+                        unsigned flat = (unsigned)(i + u * stride) * 4u + q;
+                        if (pool == 3) {
+                            key = f2key(pooled_value(img, H, W, HW, flat, e[q]));
+                            if (key < thr) continue;
+                        }
+                        push_candidate(key, flat, s_stage, &s_n, g_count, g_cand);
+                    }
+                }
+            }
+        }
+        for (; i < n4; i += stride) {
+            float4 v = ld_stream_f4(p4 + i);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned key = f2key(e[q]);
+                if (key >= thr) {
+                    unsigned flat = (unsigned)i * 4u + q;
+                    if (pool == 3) {
+                        key = f2key(pooled_value(img, H, W, HW, flat, e[q]));
+                        if (key < thr) continue;
+                    }
+                    push_candidate(key, flat, s_stage, &s_n, g_count, g_cand);
+                }
+            }
+        }
+    } else {
+        for (int i = gtid; i < N; i += stride) {
+            float e = __ldg(img + i);
+            unsigned key = f2key(e);
+            if (key >= thr) {
+                if (pool == 3) {
+                    key = f2key(pooled_value(img, H, W, HW, (unsigned)i, e));
+                    if (key < thr) continue;
+                }
+                push_candidate(key, (unsigned)i, s_stage, &s_n, g_count, g_cand);
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_n, kStage);
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(g_count, (unsigned)n);
+    __syncthreads();
+    const unsigned base = s_base;
+    for (int k = tid; k < n; k += blockDim.x) {
+        unsigned pos = base + k;
+        if (pos < (unsigned)kCap) g_cand[pos] = s_stage[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. select + sort + gather + box assembly (one CTA per image)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_sum_int(int v, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();                     // protect s_red from the previous use
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int tot = (lane < (int)(blockDim.x >> 5)) ? s_red[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    return tot;
+}
+
+// Exact selection over the whole image by one CTA: K-th largest key by MSB-first descent, then
+// an index-ordered collection (all keys > kth, and the lowest-index keys == kth).  Fills s_e[0..K).
+__device__ void exact_select(const float* __restrict__ img, int H, int W, int N, int K, int pool,
+                             unsigned long long* s_e, int* s_red) {
+    const int HW = H * W, tid = threadIdx.x, nthr = blockDim.x;
+    unsigned kth = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        unsigned trial = kth | (1u << bit);
+        int c = 0;
+        for (int i = tid; i < N; i += nthr) {
+            float v = __ldg(img + i);
+            unsigned key = f2key(v);
+            if (key >= trial && pool == 3) key = f2key(pooled_value(img, H, W, HW, (unsigned)i, v));
+            c += (key >= trial);
+        }
+        if (block_sum_int(c, s_red) >= K) kth = trial;
+    }
+    int c_gt = 0;
+    for (int i = tid; i < N; i += nthr) {
+        float v = __ldg(img + i);
+        unsigned key = f2key(v);
+        if (key > kth && pool == 3) key = f2key(pooled_value(img, H, W, HW, (unsigned)i, v));
+        c_gt += (key > kth);
+    }
+    const int n_gt = block_sum_int(c_gt, s_red);
+    const int need_eq = K - n_gt;        // >= 1 by definition of kth
+    __shared__ int s_fill, s_eq_seen;
+    if (tid == 0) { s_fill = 0; s_eq_seen = 0; }
+    __syncthreads();
+    // index-ordered sweep in chunks of nthr so that "first need_eq equal keys" is deterministic
+    for (int base = 0; base < N; base += nthr) {
+        int i = base + tid;
+        unsigned key = 0;
+        bool gt = false, eq = false;
+        if (i < N) {
+            float v = __ldg(img + i);
+            key = f2key(v);
+            if (key >= kth && pool == 3) key = f2key(pooled_value(img, H, W, HW, (unsigned)i, v));
+            gt = key > kth;
+            eq = key == kth;
+        }
+        // rank of this thread among the chunk's equal keys
+        unsigned m = __ballot_sync(0xffffffffu, eq);
+        const int lane = tid & 31, warp = tid >> 5;
+        int my = __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (lane == 0) s_red[warp] = __popc(m);
+        __syncthreads();
+        int before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += s_red[w2];
+        int chunk_eq = 0;
+        for (int w2 = 0; w2 < (nthr >> 5); ++w2) chunk_eq += s_red[w2];
+        const int seen = s_eq_seen;
+        if (gt || (eq && seen + before + my < need_eq)) {
+            int slot = atomicAdd(&s_fill, 1);
+            s_e[slot] = ((unsigned long long)key << 32) | (unsigned long long)(~(unsigned)i);
+        }
+        __syncthreads();
+        if (tid == 0) s_eq_seen = seen + chunk_eq;
+        __syncthreads();
+    }
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* s_e, int P) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nthr) {
+                int i = 2 * t - (t & (j - 1));          // lower index of the pair
+                int ixj = i + j;
+                bool desc = ((i & k) == 0);
+                unsigned long long a = s_e[i], c = s_e[ixj];
+                if (desc ? (a < c) : (a > c)) { s_e[i] = c; s_e[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
+                     const float* __restrict__ off, int C, int H, int W, int K, int pool,
+                     const unsigned int* __restrict__ count, const unsigned long long* __restrict__ cand,
+                     float* __restrict__ out_dets, long long* __restrict__ out_inds) {
+    extern __shared__ unsigned long long s_e[];          // [P], P = pow2 >= candidates
+    __shared__ int s_red[kSelectThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int HW = H * W, N = C * HW;
+    const float* img = hm + (size_t)b * N;
+    const unsigned cnt = count[b];
+    int n;
+    if (cnt >= (unsigned)K && cnt <= (unsigned)kCap) {
+        n = (int)cnt;
+        const unsigned long long* src = cand + (size_t)b * kCap;
+        for (int i = tid; i < n; i += blockDim.x) s_e[i] = src[i];
+    } else {
+        exact_select(img, H, W, N, K, pool, s_e, s_red);
+        n = K;
+    }
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += blockDim.x) s_e[i] = 0ull;   // below every real entry
+    __syncthreads();
+    bitonic_sort_desc(s_e, P);
+
+    const float* whb = wh + (size_t)b * 2 * HW;
+    const float* ofb = off + (size_t)b * 2 * HW;
+    for (int k = tid; k < K; k += blockDim.x) {
+        const unsigned long long e = s_e[k];
+        const unsigned key = (unsigned)(e >> 32);
+        const unsigned flat = ~(unsigned)(e & 0xffffffffull);
+        const int cls = flat / HW, ind = flat - cls * HW;
+        const int yi = ind / W, xi = ind - yi * W;                  // models/rrnet.py:99-100
+        const float logit = key2f(key);
+        const float score = (logit == -CUDART_INF_F) ? 0.0f : sigmoid_f32(logit);   // :119
+        const float xs = __fadd_rn((float)xi, __ldg(ofb + ind));         // :126
+        const float ys = __fadd_rn((float)yi, __ldg(ofb + HW + ind));    // :127
+        float w = __ldg(whb + ind), h = __ldg(whb + HW + ind);
+        w = (w < 0.0f) ? 0.0f : w;                                   // :128 clamp(min=0), NaN passes
+        h = (h < 0.0f) ? 0.0f : h;
+        const float px = __fsub_rn(xs, __fmul_rn(w, 0.5f));          // :133 (w/2 is exact)
+        const float py = __fsub_rn(ys, __fmul_rn(h, 0.5f));          // :134
+        float* o = out_dets + ((size_t)b * K + k) * 6;
+        o[0] = px; o[1] = py;
+        o[2] = __fadd_rn(w, px);                                     // :137 pred_w + pred_x
+        o[3] = __fadd_rn(h, py);
+        o[4] = score;
+        o[5] = (float)cls;
+        if (out_inds) out_inds[(size_t)b * K + k] = ind;
+    }
+}
+
+int decode_launch(const float* hm, const float* wh, const float* off, int B, int C, int H, int W,
+                  int K, int pool, float* out_dets, int64_t* out_inds, void* ws, cudaStream_t st) {
+    int rc = 0;
+    DecodeWs w = carve_decode(ws, B);
+    const int N = C * H * W;
+    decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
+    RR_LAUNCHED(rc);
+    // fill the machine: ~8 CTAs of 256 threads per SM in total, at least one per image
+    int per_img = max(1, (kSMs * 8 + B - 1) / B);
+    int max_useful = max(1, (N / 4 + kCollectThreads - 1) / kCollectThreads);
+    per_img = min(per_img, max_useful);
+    dim3 gc((unsigned)per_img, (unsigned)B);
+    decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
+    RR_LAUNCHED(rc);
+    static bool attr_set = false;
+    const size_t smem = (size_t)kCap * sizeof(unsigned long long);
+    if (!attr_set) {
+        RR_CUDA(cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
+        attr_set = true;
+    }
+    decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, w.count, w.cand,
+                                                         out_dets, (long long*)out_inds);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
+size_t decode_ws_bytes(int B) { return carve_decode(nullptr, B).bytes; }
+
+}  // namespace rr
+
+using namespace rr;
+
+RR_API size_t rr_decode_workspace_bytes(int B, int C, int H, int W, int K) {
+    (void)C; (void)H; (void)W; (void)K;
+    if (B <= 0) return 0;
+    return decode_ws_bytes(B);
+}
+
+RR_API int rr_decode_topk(const float* hm, const float* wh, const float* off,
+                          int B, int C, int H, int W, int K, int pool,
+                          float* out_dets, int64_t* out_inds,
+                          void* ws, size_t ws_bytes, void* stream) {
+    if (!hm || !wh || !off || !out_dets || !ws) return RR_E_BADARG;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
+    if (pool != 0 && pool != 3) return RR_E_BADARG;
+    if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
+    if (K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;   // torch.topk raises (:96)
+    if (ws_bytes < decode_ws_bytes(B) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    return decode_launch(hm, wh, off, B, C, H, W, K, pool, out_dets, out_inds, ws, (cudaStream_t)stream);
+}

@@ -1,0 +1,260 @@
+// Penalty-reduced focal loss on heat-map logits for sm_100a, forward and backward.
+//
+// Replaces focal_loss_for_hm (modules/loss/functional.py:25-51) together with the caller's
+// clamp(sigmoid(logits), 1e-4, 1-1e-4) (operators/rrnet_operator.py:55): about twelve
+// element-wise kernels, three reductions and ten 21 MB temporaries in the reference (and twice
+// that again in autograd's backward) become
+//   forward  : one streaming pass over logits+gt (2 x 4 B/element), deterministic two-level sum
+//   backward : one pass reading logits+gt and writing the gradient (3 x 4 B/element)
+//   fwd_bwd  : both in ONE cooperative launch; the second phase re-reads logits/gt from L2
+//              (config 3: 42 MB < 126 MB L2), so HBM sees 3 x 4 B/element in total.
+// Sums: fp32 per-thread partials over a few elements, then double precision across the block
+// and across blocks in a fixed order (last-block-done), so the loss is bit-reproducible.
+#include "rr_common.cuh"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace rr {
+
+constexpr int kFocalThreads = 256;
+constexpr float kLo = 1e-4f, kHi = 1.0f - 1e-4f;
+
+struct FocalWs {
+    double* partial;        // [grid][3]
+    unsigned int* ticket;   // [1]
+    size_t bytes;
+};
+static int focal_grid(long long n) {
+    long long want = (n / 4 + kFocalThreads * 4 - 1) / (kFocalThreads * 4);   // >= 4 float4 per thread
+    long long cap = (long long)kSMs * 8;
+    return (int)max(1LL, min(want, cap));
+}
+static FocalWs carve_focal(void* ws) {
+    Carver cv(ws);
+    FocalWs w;
+    w.partial = cv.take<double>((size_t)kSMs * 8 * 3);
+    w.ticket = cv.take<unsigned int>(1);
+    w.bytes = cv.off;
+    return w;
+}
+
+__device__ __forceinline__ void focal_term(float z, float g, float& pos, float& neg, int& npos) {
+    const float s = __frcp_rn(1.0f + expf(-z));
+    const float p = fminf(fmaxf(s, kLo), kHi);                    // rrnet_operator.py:55
+    if (g == 1.0f) {                                              // functional.py:33,40
+        const float q = 1.0f - p;
+        pos += logf(p) * (q * q);
+        npos += 1;
+    } else if (g < 1.0f) {                                        // :34,36,41
+        const float q = 1.0f - g;
+        const float w = (q * q) * (q * q);
+        neg += logf(1.0f - p) * (p * p) * w;
+    }
+}
+
+// d loss / d z for one element, already multiplied by `scale` (= upstream * -1/num_pos)
+__device__ __forceinline__ float focal_grad(float z, float g, float scale) {
+    const float s = __frcp_rn(1.0f + expf(-z));
+    if (s < kLo || s > kHi) return 0.0f;                          // clamp blocks the gradient
+    const float p = s, q = 1.0f - s;
+    float d = 0.0f;
+    if (g == 1.0f) {
+        d = q * q * q - 2.0f * p * (q * q) * logf(p);
+    } else if (g < 1.0f) {
+        const float r = 1.0f - g;
+        const float w = (r * r) * (r * r);
+        d = w * (2.0f * (p * p) * q * logf(q) - p * p * p);
+    }
+    return d * scale;
+}
+
+__device__ __forceinline__ void focal_accumulate(const float* __restrict__ logits, const float* __restrict__ gt,
+                                                 long long n, float& pos, float& neg, int& npos) {
+    const long long n4 = n >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(logits);
+    const float4* g4 = reinterpret_cast<const float4*>(gt);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {                    // two independent float4 pairs in flight
+        const float4 za = ld_stream_f4(z4 + i), ga = ld_stream_f4(g4 + i);
+        const float4 zb = ld_stream_f4(z4 + i + stride), gb = ld_stream_f4(g4 + i + stride);
+        focal_term(za.x, ga.x, pos, neg, npos); focal_term(za.y, ga.y, pos, neg, npos);
+        focal_term(za.z, ga.z, pos, neg, npos); focal_term(za.w, ga.w, pos, neg, npos);
+        focal_term(zb.x, gb.x, pos, neg, npos); focal_term(zb.y, gb.y, pos, neg, npos);
+        focal_term(zb.z, gb.z, pos, neg, npos); focal_term(zb.w, gb.w, pos, neg, npos);
+    }
+    for (; i < n4; i += stride) {
+        const float4 za = ld_stream_f4(z4 + i), ga = ld_stream_f4(g4 + i);
+        focal_term(za.x, ga.x, pos, neg, npos); focal_term(za.y, ga.y, pos, neg, npos);
+        focal_term(za.z, ga.z, pos, neg, npos); focal_term(za.w, ga.w, pos, neg, npos);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {               // tail (n not a multiple of 4)
+        const long long j = (n4 << 2) + threadIdx.x;
+        focal_term(logits[j], gt[j], pos, neg, npos);
+    }
+}
+
+// block-level double reduction of (pos, neg, npos) -> partial[blockIdx]; returns true in the
+// LAST block to finish (which then owns the final fixed-order sum).
+__device__ __forceinline__ bool focal_block_reduce(float pos, float neg, int npos, double* partial,
+                                                   unsigned int* ticket) {
+    __shared__ double s_p[kFocalThreads / 32], s_n[kFocalThreads / 32], s_c[kFocalThreads / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double dp = warp_sum((double)pos), dn = warp_sum((double)neg), dc = warp_sum((double)npos);
+    if (lane == 0) { s_p[warp] = dp; s_n[warp] = dn; s_c[warp] = dc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < kFocalThreads / 32; ++w) { a += s_p[w]; b += s_n[w]; c += s_c[w]; }
+        partial[blockIdx.x * 3 + 0] = a;
+        partial[blockIdx.x * 3 + 1] = b;
+        partial[blockIdx.x * 3 + 2] = c;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    return s_last;
+}
+
+__device__ __forceinline__ void focal_finish(const double* partial, float* stats) {
+    // one thread, fixed order -> bit-reproducible
+    double a = 0, b = 0, c = 0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+        a += __ldcg(partial + k * 3 + 0);
+        b += __ldcg(partial + k * 3 + 1);
+        c += __ldcg(partial + k * 3 + 2);
+    }
+    const double loss = (c == 0.0) ? -b : -(a + b) / c;            // functional.py:47-50
+    stats[0] = (float)loss; stats[1] = (float)a; stats[2] = (float)b; stats[3] = (float)c;
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_forward_kernel(const float* __restrict__ logits, const float* __restrict__ gt, long long n,
+                     double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                     float* __restrict__ stats) {
+    float pos = 0.f, neg = 0.f;
+    int npos = 0;
+    focal_accumulate(logits, gt, n, pos, neg, npos);
+    if (focal_block_reduce(pos, neg, npos, partial, ticket) && threadIdx.x == 0) {
+        __threadfence();
+        focal_finish(partial, stats);
+        *ticket = 0u;                                             // ready for the next launch
+    }
+}
+
+__device__ __forceinline__ void focal_write_grads(const float* __restrict__ logits, const float* __restrict__ gt,
+                                                  long long n, float scale, float* __restrict__ grad) {
+    const long long n4 = n >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(logits);
+    const float4* g4 = reinterpret_cast<const float4*>(gt);
+    float4* o4 = reinterpret_cast<float4*>(grad);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 z = __ldg(z4 + i), g = __ldg(g4 + i);
+        float4 o;
+        o.x = focal_grad(z.x, g.x, scale); o.y = focal_grad(z.y, g.y, scale);
+        o.z = focal_grad(z.z, g.z, scale); o.w = focal_grad(z.w, g.w, scale);
+        __stcs(o4 + i, o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long j = (n4 << 2) + threadIdx.x;
+        grad[j] = focal_grad(logits[j], gt[j], scale);
+    }
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_backward_kernel(const float* __restrict__ logits, const float* __restrict__ gt, long long n,
+                      const float* __restrict__ stats, float upstream, float* __restrict__ grad) {
+    const float npos = stats[3];
+    const float scale = upstream * ((npos == 0.f) ? -1.0f : -1.0f / npos);
+    focal_write_grads(logits, gt, n, scale, grad);
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ gt, long long n,
+                     float upstream, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                     float* __restrict__ stats, float* __restrict__ grad) {
+    float pos = 0.f, neg = 0.f;
+    int npos = 0;
+    focal_accumulate(logits, gt, n, pos, neg, npos);
+    if (focal_block_reduce(pos, neg, npos, partial, ticket) && threadIdx.x == 0) {
+        __threadfence();
+        focal_finish(partial, stats);
+        *ticket = 0u;
+        __threadfence();
+    }
+    cg::this_grid().sync();
+    const float np = __ldcg(stats + 3);
+    const float scale = upstream * ((np == 0.f) ? -1.0f : -1.0f / np);
+    focal_write_grads(logits, gt, n, scale, grad);
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+RR_API size_t rr_focal_workspace_bytes(int64_t n) {
+    (void)n;
+    return carve_focal(nullptr).bytes;
+}
+
+static int focal_check(const float* logits, const float* gt, int64_t n, const void* ws, size_t ws_bytes,
+                       bool need_ws) {
+    if (!logits || !gt || n <= 0) return RR_E_BADARG;
+    if (((uintptr_t)logits & 15) || ((uintptr_t)gt & 15)) return RR_E_ALIGN;
+    if (need_ws) {
+        if (!ws) return RR_E_BADARG;
+        if (ws_bytes < carve_focal(nullptr).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    }
+    return 0;
+}
+
+RR_API int rr_focal_forward(const float* logits, const float* gt, int64_t n, float* stats,
+                            void* ws, size_t ws_bytes, void* stream) {
+    int rc = focal_check(logits, gt, n, ws, ws_bytes, true);
+    if (rc) return rc;
+    if (!stats) return RR_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    FocalWs w = carve_focal(ws);
+    RR_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st), rc);
+    focal_forward_kernel<<<focal_grid(n), kFocalThreads, 0, st>>>(logits, gt, n, w.partial, w.ticket, stats);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
+RR_API int rr_focal_backward(const float* logits, const float* gt, int64_t n, const float* stats,
+                             float upstream, float* grad, void* stream) {
+    int rc = focal_check(logits, gt, n, nullptr, 0, false);
+    if (rc) return rc;
+    if (!stats || !grad) return RR_E_BADARG;
+    if ((uintptr_t)grad & 15) return RR_E_ALIGN;
+    focal_backward_kernel<<<focal_grid(n), kFocalThreads, 0, (cudaStream_t)stream>>>(logits, gt, n, stats, upstream, grad);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
+RR_API int rr_focal_fwd_bwd(const float* logits, const float* gt, int64_t n, float upstream,
+                            float* stats, float* grad, void* ws, size_t ws_bytes, void* stream) {
+    int rc = focal_check(logits, gt, n, ws, ws_bytes, true);
+    if (rc) return rc;
+    if (!stats || !grad) return RR_E_BADARG;
+    if ((uintptr_t)grad & 15) return RR_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    FocalWs w = carve_focal(ws);
+    RR_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st), rc);
+    // cooperative launch: every CTA must be co-resident
+    int dev = 0, sms = kSMs, per_sm = 0;
+    RR_CUDA(cudaGetDevice(&dev), rc);
+    RR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), rc);
+    RR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, focal_fwd_bwd_kernel, kFocalThreads, 0), rc);
+    if (rc) return rc;
+    int grid = min(focal_grid(n), max(1, per_sm * sms));
+    long long n_ll = n;
+    void* args[] = {(void*)&logits, (void*)&gt, (void*)&n_ll, (void*)&upstream, (void*)&w.partial,
+                    (void*)&w.ticket, (void*)&stats, (void*)&grad};
+    RR_CUDA(cudaLaunchCooperativeKernel((void*)focal_fwd_bwd_kernel, dim3(grid), dim3(kFocalThreads), args, 0, st), rc);
+    RR_LAUNCHED(rc);
+    return rc;
+}

@@ -1,0 +1,474 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+Bar: bit-exact top-K indices, keep-lists, classes and box arithmetic; 1e-5 relative (fp32) for
+scores, RoI features, head outputs and losses.  Run on the B200 box:  pytest -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from rrnet_b200 import synth
+from tests.conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rrnet_b200 import ops as _ops
+    _ops._lib.lib()
+    return _ops
+
+
+def dev(t):
+    return (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+# ===================================================================== decode (a2-a4)
+@pytest.mark.parametrize("B,C,H,W,K,seed", [
+    (2, 10, 40, 56, 100, 21),       # the golden case
+    (1, 10, 128, 128, 500, 101),    # config 1
+    (3, 7, 33, 47, 64, 5),          # odd sizes: C*H*W not a multiple of 4 -> scalar path
+    (1, 2, 8, 8, 64, 9),            # K == H*W (largest legal K)
+    (2, 10, 272, 480, 1500, 202),   # config 2 shape, sample-threshold fast path
+])
+def test_decode_vs_oracle(ops, oracle_mod, B, C, H, W, K, seed):
+    hm = synth.heatmap_logits(B, C, H, W, K, seed)
+    wh, off = synth.wh_offset(B, H, W, seed)
+    dets, inds = ops.decode_topk(dev(hm), dev(wh), dev(off), K)
+    o_dets, o_inds, o_flat = oracle_mod.decode(hm.numpy(), wh.numpy(), off.numpy(), K)
+    np.testing.assert_array_equal(npy(inds), o_inds)
+    d = npy(dets)
+    np.testing.assert_array_equal(d[..., 5], o_dets[..., 5])
+    np.testing.assert_array_equal(d[..., :4], o_dets[..., :4])
+    assert rel_err(d[..., 4], o_dets[..., 4]) < TOL
+
+
+def test_decode_golden(ops):
+    g = load_golden("decode")
+    B, C, H, W, K = g["shape"].tolist()
+    hm = synth.heatmap_logits(B, C, H, W, K, int(g["seed"]))
+    wh, off = synth.wh_offset(B, H, W, int(g["seed"]))
+    dets, inds = ops.decode_topk(dev(hm), dev(wh), dev(off), K)
+    np.testing.assert_array_equal(npy(inds), g["inds"])
+    np.testing.assert_array_equal(npy(dets)[..., :4], g["dets"][..., :4])
+    np.testing.assert_array_equal(npy(dets)[..., 5], g["dets"][..., 5])
+    assert rel_err(npy(dets)[..., 4], g["dets"][..., 4]) < TOL
+
+
+@pytest.mark.parametrize("case", ["constant", "two_level", "dense_hits"])
+def test_decode_ties_and_fallback(ops, oracle_mod, case):
+    """Massive ties / threshold-estimate failures take the exact in-CTA path; the canonical order
+    (logit desc, flat index asc) must still match the oracle exactly."""
+    B, C, H, W, K = 2, 4, 96, 120, 300           # N = 46080 > candidate capacity -> sampling active
+    g = torch.Generator().manual_seed(3)
+    if case == "constant":
+        hm = torch.full((B, C, H, W), -1.25)
+    elif case == "two_level":
+        hm = torch.where(torch.rand(B, C, H, W, generator=g) < 0.4, torch.tensor(2.0), torch.tensor(-3.0))
+    else:                                         # > capacity elements above any sampled threshold
+        hm = torch.randn(B, C, H, W, generator=g).round()
+    wh, off = synth.wh_offset(B, H, W, 3)
+    dets, inds = ops.decode_topk(dev(hm), dev(wh), dev(off), K)
+    o_dets, o_inds, _ = oracle_mod.decode(hm.numpy(), wh.numpy(), off.numpy(), K)
+    np.testing.assert_array_equal(npy(inds), o_inds)
+    np.testing.assert_array_equal(npy(dets)[..., [0, 1, 2, 3, 5]], o_dets[..., [0, 1, 2, 3, 5]])
+
+
+def test_decode_pool3(ops, oracle_mod):
+    B, C, H, W, K = 2, 10, 64, 80, 120
+    hm = synth.heatmap_logits(B, C, H, W, K, 8)
+    wh, off = synth.wh_offset(B, H, W, 8)
+    dets, inds = ops.decode_topk(dev(hm), dev(wh), dev(off), K, pool=3)
+    o_dets, o_inds, _ = oracle_mod.decode(hm.numpy(), wh.numpy(), off.numpy(), K, pool=3)
+    np.testing.assert_array_equal(npy(inds), o_inds)
+    np.testing.assert_array_equal(npy(dets)[..., [0, 1, 2, 3, 5]], o_dets[..., [0, 1, 2, 3, 5]])
+    assert rel_err(npy(dets)[..., 4], o_dets[..., 4]) < TOL
+
+
+def test_decode_rejects_bad_arguments(ops):
+    z = torch.zeros(1, 2, 4, 4).cuda()
+    with pytest.raises(ops.RRNetB200Error):
+        ops.decode_topk(z, z, z, 17)              # K > H*W: torch.topk raises in the reference
+    with pytest.raises(ops.RRNetB200Error):
+        ops.decode_topk(z, z, z, 4, pool=5)
+
+
+# ===================================================================== hard NMS (a5, a10)
+def test_nms_known_answer_all_entry_points(ops):
+    g = load_golden("nms")
+    k = g["known"]
+    bx, sc = dev(k[:, :4].copy()), dev(k[:, 4].copy())
+    assert npy(ops.nms(bx, sc, 0.3, 1, True)).tolist() == [2, 3]       # cpu_nms semantics
+    assert npy(ops.nms(bx, sc, 0.3, 1, False)).tolist() == [2, 3]      # gpu_nms / py_cpu_nms
+    assert npy(ops.nms(bx, sc, 0.3, 0, False)).tolist() == [2, 1, 3]   # torchvision
+    order = np.argsort(-k[:, 4], kind="stable")
+    keep = ops.nms_legacy_host(k[order], 0.3)                           # `_nms` ABI: sorted rows
+    assert order[keep].tolist() == [2, 3]
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.7])
+def test_nms_three_semantics_golden(ops, thr):
+    g = load_golden("nms")
+    d = g["boxes"]
+    bx, sc = dev(d[:, :4].copy()), dev(d[:, 4].copy())
+    t = "%02d" % int(thr * 10)
+    assert npy(ops.nms(bx, sc, thr, 0, False)).tolist() == g["tv_" + t].tolist()
+    assert npy(ops.nms(bx, sc, thr, 1, True)).tolist() == g["cpu_" + t].tolist()
+    assert npy(ops.nms(bx, sc, thr, 1, False)).tolist() == g["py_" + t].tolist()
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1500, 5000])
+def test_nms_sizes_vs_oracle(ops, oracle_mod, n):
+    d = synth.nms_stress_boxes(n, 100 + n).numpy()
+    for po, ge in ((0, False), (1, True)):
+        keep = npy(ops.nms(dev(d[:, :4].copy()), dev(d[:, 4].copy()), 0.7, po, ge))
+        assert keep.tolist() == oracle_mod.nms(d[:, :4], d[:, 4], 0.7, po, ge).tolist()
+
+
+def test_nms_score_ties_are_stable(ops, oracle_mod):
+    d = synth.nms_stress_boxes(400, 77).numpy()
+    d[:, 4] = np.round(d[:, 4] * 8) / 8                                 # heavy score ties
+    keep = npy(ops.nms(dev(d[:, :4].copy()), dev(d[:, 4].copy()), 0.5))
+    assert keep.tolist() == oracle_mod.nms(d[:, :4], d[:, 4], 0.5).tolist()
+
+
+def test_nms_batched_segments(ops, oracle_mod):
+    sizes = [0, 5, 130, 0, 64, 700, 1]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    d = synth.nms_stress_boxes(int(offs[-1]), 55).numpy()
+    keep_idx, keep_cnt = ops.nms_batched(dev(d[:, :4].copy()), dev(d[:, 4].copy()), dev(offs), 0.6)
+    keep_idx, keep_cnt = npy(keep_idx), npy(keep_cnt)
+    for s, n in enumerate(sizes):
+        a, b = offs[s], offs[s + 1]
+        ref = oracle_mod.nms(d[a:b, :4], d[a:b, 4], 0.6) + a
+        assert keep_cnt[s] == len(ref)
+        assert keep_idx[a:a + keep_cnt[s]].tolist() == ref.tolist()
+
+
+def test_nms_empty(ops):
+    e = torch.zeros(0, 4).cuda()
+    assert ops.nms(e, torch.zeros(0).cuda(), 0.5).numel() == 0
+    assert len(ops.nms_legacy_host(np.zeros((0, 5), np.float32), 0.5)) == 0
+
+
+def test_nms_legacy_host_matches_reference_layout(ops, oracle_mod):
+    d = synth.nms_stress_boxes(3000, 9).numpy()
+    order = np.argsort(-d[:, 4], kind="stable")
+    rows = d[order]
+    keep = ops.nms_legacy_host(rows, 0.7)
+    assert keep.tolist() == oracle_mod.nms_sorted(rows, float(np.float32(0.7)), 1, False).tolist()
+
+
+def test_nms_idempotent_20k(ops):
+    """Full-size stress (config 5): NMS of the kept set keeps everything, kept boxes are pairwise
+    below the threshold, and every dropped box overlaps a higher-scored kept box."""
+    d = synth.nms_stress_boxes(20000, synth.SEED_C5)
+    bx, sc = d[:, :4].cuda().contiguous(), d[:, 4].cuda().contiguous()
+    keep = ops.nms(bx, sc, 0.7, 1, False)
+    assert 0 < keep.numel() < 20000
+    again = ops.nms(bx[keep], sc[keep], 0.7, 1, False)
+    assert again.tolist() == list(range(keep.numel()))
+    assert bool((sc[keep][:-1] >= sc[keep][1:]).all())
+
+
+# ===================================================================== stage-1 NMS (a5 + forward loop)
+@pytest.mark.parametrize("B,H,W,K,seed", [(2, 48, 64, 200, 31), (3, 64, 96, 700, 12)])
+def test_stage1_nms_vs_oracle(ops, oracle_mod, B, H, W, K, seed):
+    C = 10
+    hm = synth.heatmap_logits(B, C, H, W, K, seed)
+    wh, off = synth.wh_offset(B, H, W, seed, wh_range=(1.5, 14.0))
+    dets, _ = ops.decode_topk(dev(hm), dev(wh), dev(off), K)
+    bxyxy, scores, clses, counts = ops.stage1_nms(dets, C, 0.7)
+    counts = npy(counts)
+    d = npy(dets)
+    base = 0
+    for b in range(B):
+        kept, _ = oracle_mod.stage1_nms(d[b], C, 0.7)
+        n = kept.shape[0]
+        assert counts[b] == n
+        np.testing.assert_array_equal(npy(bxyxy[base:base + n, 1:]), kept[:, :4])
+        assert (npy(bxyxy[base:base + n, 0]) == b).all()
+        np.testing.assert_array_equal(npy(scores[base:base + n]), kept[:, 4])
+        np.testing.assert_array_equal(npy(clses[base:base + n]), kept[:, 5])
+        base += n
+    assert counts[B] == base
+    assert base < B * K                                   # something was actually suppressed
+
+
+def test_stage1_single_class_worst_case(ops, oracle_mod):
+    """All K boxes in one class (one long segment spanning many 64-wide tiles)."""
+    K = 1500
+    d = synth.nms_stress_boxes(K, 4).numpy()
+    order = np.argsort(-d[:, 4], kind="stable")
+    dets = np.concatenate([d[order], np.full((K, 1), 3, np.float32)], 1)[None]
+    bxyxy, scores, clses, counts = ops.stage1_nms(dev(dets.copy()), 10, 0.7)
+    kept, _ = oracle_mod.stage1_nms(dets[0], 10, 0.7)
+    n = int(npy(counts)[0])
+    assert n == kept.shape[0]
+    np.testing.assert_array_equal(npy(bxyxy[:n, 1:]), kept[:, :4])
+
+
+# ===================================================================== RoIAlign (a6)
+def test_roi_align_golden_edge_cases(ops):
+    g = load_golden("roi_align")
+    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=True)
+    assert rel_err(npy(out), g["out_relu"], floor=1e-3) < TOL
+    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=False)
+    assert rel_err(npy(out), g["out_raw"], floor=1.0) < TOL          # signed taps cancel: relative to max
+
+
+def test_roi_align_vs_oracle_random(ops, oracle_mod):
+    B, C, H, W = 2, 256, 48, 64
+    feat = synth.features(B, C, H, W, 3)
+    g = torch.Generator().manual_seed(4)
+    n = 300
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([W * 1.1, H * 1.1]) - 3.0
+    wh = torch.rand(n, 2, generator=g) * 39.0 + 0.2
+    rois = torch.cat([torch.randint(0, B, (n, 1), generator=g).float(), xy, xy + wh], 1)
+    rois[::17, 3:] = rois[::17, 1:3]                                  # degenerate (w = h = 0)
+    out = npy(ops.roi_align(dev(feat), dev(rois)))
+    ref = oracle_mod.roi_align(feat.numpy(), rois.numpy(), relu=True)
+    assert rel_err(out, ref, floor=1e-3) < TOL
+
+
+def test_roi_align_device_count_and_huge_roi(ops, oracle_mod):
+    B, C, H, W = 1, 8, 120, 150
+    feat = synth.features(B, C, H, W, 6)
+    rois = torch.tensor([[0, -10.0, -10.0, 160.0, 130.0], [0, 3.0, 4.0, 140.0, 9.0], [0, 1.0, 1.0, 5.0, 5.0]])
+    n_dev = torch.tensor([2], dtype=torch.int32).cuda()
+    out = ops.roi_align(dev(feat), dev(rois), n_dev=n_dev)
+    ref = oracle_mod.roi_align(feat.numpy(), rois.numpy()[:2], relu=True)
+    assert rel_err(npy(out[:2]), ref, floor=1e-3) < TOL
+
+
+# ===================================================================== head (a7)
+def test_head_golden_and_oracle(ops, oracle_mod):
+    g = load_golden("head")
+    hp = synth.head_params(int(g["seed"]))
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    y = npy(ops.head_forward(dev(g["x"]), folded))
+    assert rel_err(y, g["y"], floor=1.0) < TOL
+    x = torch.relu(torch.randn(333, 256, 3, 3, generator=torch.Generator().manual_seed(1))) * 2
+    y = npy(ops.head_forward(dev(x), folded))
+    ref = oracle_mod.head(x.numpy(), {k: v.numpy() for k, v in hp.items()})
+    assert rel_err(y, ref, floor=1.0) < TOL
+
+
+# ===================================================================== whole eval path (a1..a8)
+def test_eval_path_golden(ops):
+    g = load_golden("pipeline")
+    B, C, H, W, K = g["shape"].tolist()
+    seed = int(g["seed"])
+    x = synth.eval_inputs(B, H, W, K, seed)
+    hp = synth.head_params(seed)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    path = ops.EvalPath(B, C, H, W, K, folded, keep_roi_feat=True)
+    path.forward(dev(x["hm"]), dev(x["wh"]), dev(x["off"]), dev(x["feat"]))
+    r = path.results()
+    assert r["n"] == g["bxyxy"].shape[0]
+    np.testing.assert_array_equal(npy(r["bxyxy"]), g["bxyxy"])          # keep-lists and order bit-exact
+    np.testing.assert_array_equal(npy(r["clses"]), g["clses"])
+    assert rel_err(npy(r["scores"]), g["scores"]) < TOL
+    roi = npy(path.roi_feat[: r["n"]])
+    assert rel_err(roi[::8], g["roi_feat_every8"], floor=1e-3) < TOL
+    assert rel_err(npy(r["reg"]), g["s2_reg"], floor=1.0) < TOL
+    base = 0
+    for b in range(B):
+        n = r["counts"][b]
+        assert rel_err(npy(r["s1"][base:base + n]), g["s1_b%d" % b]) < TOL
+        assert rel_err(npy(r["s2"][base:base + n]), g["s2_b%d" % b], floor=1e-3) < TOL
+        base += n
+
+
+def test_eval_path_config1_vs_oracle(ops, oracle_mod):
+    """Config 1: B=1, 10x128x128, K=500 -- every stage against the oracle."""
+    B, C, H, W, K = 1, 10, 128, 128, 500
+    x = synth.eval_inputs(B, H, W, K, synth.SEED_C1)
+    hp = synth.head_params(synth.SEED_C1)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    path = ops.EvalPath(B, C, H, W, K, folded, keep_roi_feat=True)
+    path.forward(dev(x["hm"]), dev(x["wh"]), dev(x["off"]), dev(x["feat"]))
+    r = path.results()
+    dets, _, _ = oracle_mod.decode(x["hm"].numpy(), x["wh"].numpy(), x["off"].numpy(), K)
+    kept, _ = oracle_mod.stage1_nms(dets[0], C, 0.7)
+    bxyxy = np.concatenate([np.zeros((kept.shape[0], 1), np.float32), kept[:, :4]], 1)
+    np.testing.assert_array_equal(npy(r["bxyxy"]), bxyxy)
+    roi = oracle_mod.roi_align(x["feat"].numpy(), bxyxy, relu=True)
+    assert rel_err(npy(path.roi_feat[: r["n"]]), roi, floor=1e-3) < TOL
+    reg = oracle_mod.head(roi, {k: v.numpy() for k, v in hp.items()})
+    assert rel_err(npy(r["reg"]), reg, floor=1.0) < TOL
+    s1, s2 = oracle_mod.generate_bbox(bxyxy, npy(r["reg"]), kept[:, 4], kept[:, 5], 0, 4.0)
+    assert rel_err(npy(r["s1"]), s1) < TOL
+    assert rel_err(npy(r["s2"]), s2, floor=1e-3) < TOL
+
+
+def test_eval_path_full_size_properties(ops, oracle_mod):
+    """Config 2 (B=8, 10x272x480, K=1500): exact decode + keep-lists for every image, RoI features and
+    head outputs for a strided subset of RoIs, and batch independence (image b alone == image b in batch)."""
+    B, C, H, W, K = 8, 10, 272, 480, 1500
+    x = synth.eval_inputs(B, H, W, K, synth.SEED_C2)
+    hp = synth.head_params(synth.SEED_C2)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    path = ops.EvalPath(B, C, H, W, K, folded, keep_roi_feat=True)
+    xd = {k: dev(v) for k, v in x.items()}
+    path.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    r = path.results()
+    dets, inds, _ = oracle_mod.decode(x["hm"].numpy(), x["wh"].numpy(), x["off"].numpy(), K)
+    np.testing.assert_array_equal(npy(path.inds), inds)
+    np.testing.assert_array_equal(npy(path.dets)[..., [0, 1, 2, 3, 5]], dets[..., [0, 1, 2, 3, 5]])
+    # scores sorted descending per image
+    s = npy(path.dets)[..., 4]
+    assert (s[:, :-1] >= s[:, 1:]).all()
+    rows = []
+    for b in range(B):
+        kept, _ = oracle_mod.stage1_nms(dets[b], C, 0.7)
+        assert r["counts"][b] == kept.shape[0]
+        rows.append(np.concatenate([np.full((kept.shape[0], 1), b, np.float32), kept[:, :4]], 1))
+    bxyxy = np.concatenate(rows)
+    np.testing.assert_array_equal(npy(r["bxyxy"]), bxyxy)
+    sub = np.arange(0, bxyxy.shape[0], 37)
+    roi = oracle_mod.roi_align(x["feat"].numpy(), bxyxy[sub], relu=True)
+    assert rel_err(npy(path.roi_feat)[sub], roi, floor=1e-3) < TOL
+    reg = oracle_mod.head(roi, {k: v.numpy() for k, v in hp.items()})
+    assert rel_err(npy(r["reg"])[sub], reg, floor=1.0) < TOL
+    # image 5 alone gives exactly the rows it had inside the batch
+    one = ops.EvalPath(1, C, H, W, K, folded)
+    one.forward(xd["hm"][5:6], xd["wh"][5:6], xd["off"][5:6], xd["feat"][5:6])
+    r1 = one.results()
+    lo = sum(r["counts"][:5])
+    hi = lo + r["counts"][5]
+    assert r1["n"] == hi - lo
+    np.testing.assert_array_equal(npy(r1["bxyxy"])[:, 1:], npy(r["bxyxy"])[lo:hi, 1:])
+    np.testing.assert_array_equal(npy(r1["reg"]), npy(r["reg"])[lo:hi])
+    np.testing.assert_array_equal(npy(r1["s2"]), npy(r["s2"])[lo:hi])
+
+
+# ===================================================================== soft-NMS (a9)
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_soft_nms_golden(ops, method):
+    g = load_golden("soft_nms")
+    d = g["boxes"]
+    seg = torch.tensor([0, d.shape[0]], dtype=torch.int32).cuda()
+    rows, src, cnt = ops.soft_nms_batched(dev(d.copy()), seg, sigma=0.5, Nt=0.7, threshold=0.1, method=method)
+    n = int(cnt.item())
+    ref = g["rows_m%d" % method]
+    assert n == ref.shape[0]
+    np.testing.assert_array_equal(npy(rows[:n, :4]), ref[:, :4])
+    assert rel_err(npy(rows[:n, 4]), ref[:, 4]) < TOL
+    np.testing.assert_array_equal(d[npy(src[:n]), :4], ref[:, :4])       # src_idx maps back to input rows
+
+
+def test_soft_nms_segments_vs_oracle(ops, oracle_mod):
+    sizes = [300, 0, 1, 2500, 70]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    d = synth.nms_stress_boxes(int(offs[-1]), 66).numpy()
+    rows, src, cnt = ops.soft_nms_batched(dev(d.copy()), dev(offs), sigma=0.5, Nt=0.7, threshold=0.1, method=2)
+    rows, cnt = npy(rows), npy(cnt)
+    for s, n in enumerate(sizes):
+        a = offs[s]
+        ref = oracle_mod.soft_nms(d[a:a + n], sigma=0.5, Nt=0.7, threshold=0.1, method=2)
+        assert cnt[s] == ref.shape[0]
+        np.testing.assert_array_equal(rows[a:a + cnt[s], :4], ref[:, :4])
+        assert rel_err(rows[a:a + cnt[s], 4], ref[:, 4]) < TOL
+
+
+def test_soft_nms_large_segment_global_path(ops, oracle_mod):
+    d = synth.nms_stress_boxes(7000, 67).numpy()                          # > shared-memory capacity
+    seg = torch.tensor([0, 7000], dtype=torch.int32).cuda()
+    rows, src, cnt = ops.soft_nms_batched(dev(d.copy()), seg, sigma=0.5, Nt=0.7, threshold=0.1, method=2)
+    ref = oracle_mod.soft_nms(d, sigma=0.5, Nt=0.7, threshold=0.1, method=2)
+    n = int(cnt.item())
+    assert n == ref.shape[0]
+    np.testing.assert_array_equal(npy(rows[:n, :4]), ref[:, :4])
+    assert rel_err(npy(rows[:n, 4]), ref[:, 4]) < TOL
+
+
+# ===================================================================== target render (a11)
+def test_render_demo_known_answer(ops):
+    g = load_golden("render")
+    a = g["demo_annos"]
+    annos = torch.zeros(1, a.shape[0] + 3, 8)
+    annos[0, : a.shape[0]] = torch.from_numpy(a)
+    n_obj = torch.tensor([a.shape[0]], dtype=torch.int32)
+    hm, wh, ind, off, msk = ops.render_targets(annos.cuda(), n_obj.cuda(), 540, 960)
+    hm = npy(hm)[0]
+    assert hm.shape == (10, 135, 240) and int((hm == 1).sum()) == 81
+    assert abs(float(hm.astype(np.float64).sum()) - 294.5373923947336) < 1e-3
+    np.testing.assert_array_equal(hm > 0, g["demo_hm"] > 0)
+    np.testing.assert_array_equal(hm == 1, g["demo_hm"] == 1)
+    assert rel_err(hm, g["demo_hm"]) < TOL
+    n = a.shape[0]
+    np.testing.assert_array_equal(npy(wh)[0, :n], g["demo_wh"])
+    np.testing.assert_array_equal(npy(ind)[0, :n], g["demo_ind"])
+    np.testing.assert_array_equal(npy(off)[0, :n], g["demo_off"])
+    np.testing.assert_array_equal(npy(msk)[0, :n], g["demo_mask"])
+    assert (npy(wh)[0, n:] == 0).all() and (npy(msk)[0, n:] == 0).all()   # collate zero padding
+
+
+def test_render_batch_vs_oracle_config3(ops, oracle_mod):
+    """Config 3 targets: B=32 at 512x512; order independence makes the result bit-reproducible."""
+    B = 32
+    annos = synth.train_annos(B, 512, 512, synth.SEED_C3)
+    padded, cnt = synth.pad_annos(annos)
+    hm, wh, ind, off, msk = ops.render_targets(padded.cuda(), cnt.cuda(), 512, 512)
+    hm2 = ops.render_targets(padded.cuda(), cnt.cuda(), 512, 512)[0]
+    assert torch.equal(hm, hm2)
+    for b in (0, 7, 31):
+        r = oracle_mod.render(annos[b].numpy(), 512, 512)
+        np.testing.assert_array_equal(npy(hm[b]) > 0, r["hm"] > 0)
+        np.testing.assert_array_equal(npy(hm[b]) == 1, r["hm"] == 1)
+        assert rel_err(npy(hm[b]), r["hm"]) < TOL
+        n = annos[b].shape[0]
+        np.testing.assert_array_equal(npy(wh[b, :n]), r["wh"])
+        np.testing.assert_array_equal(npy(ind[b, :n]), r["ind"])
+        np.testing.assert_array_equal(npy(off[b, :n]), r["offset"])
+        np.testing.assert_array_equal(npy(msk[b, :n]), r["reg_mask"])
+
+
+# ===================================================================== focal loss (a12)
+def _check_focal(ops, z, gt, loss_ref, grad_ref):
+    zd, gd = dev(z), dev(gt)
+    stats = npy(ops.focal_forward(zd, gd))
+    assert abs(stats[0] - loss_ref) / abs(loss_ref) < TOL
+    assert stats[3] == float((gt == 1).sum())
+    grad = npy(ops.focal_backward(zd, gd, dev(stats.copy()), 1.0))
+    assert rel_err(grad, grad_ref, floor=1.0) < TOL
+    stats2, grad2 = ops.focal_fwd_bwd(zd, gd, 0.5)
+    assert abs(float(stats2[0]) - loss_ref) / abs(loss_ref) < TOL
+    assert rel_err(npy(grad2), 0.5 * np.asarray(grad_ref), floor=1.0) < TOL
+
+
+def test_focal_golden(ops):
+    g = load_golden("focal")
+    _check_focal(ops, g["logits"], g["gt"], float(g["loss"]), g["grad"])
+    _check_focal(ops, g["logits"], g["gt_nopos"], float(g["loss_nopos"]), g["grad_nopos"])
+
+
+def test_focal_config3_vs_oracle(ops, oracle_mod):
+    B = 32
+    annos = synth.train_annos(B, 512, 512, synth.SEED_C3)
+    padded, cnt = synth.pad_annos(annos)
+    gt = ops.render_targets(padded.cuda(), cnt.cuda(), 512, 512)[0]
+    z = torch.randn(B, 10, 128, 128, generator=torch.Generator().manual_seed(synth.SEED_C3)) * 2.0 - 2.5
+    loss, sums, grad = oracle_mod.focal(z.numpy(), npy(gt), want_grad=True)
+    _check_focal(ops, z.numpy(), npy(gt), loss, grad)
+    # deterministic reduction: identical bits on a second run
+    a = ops.focal_forward(z.cuda(), gt)
+    b = ops.focal_forward(z.cuda(), gt)
+    assert torch.equal(a, b)
+
+
+def test_focal_odd_length(ops, oracle_mod):
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(4 * 1001 + 3, generator=g) * 3
+    gt = torch.rand(4 * 1001 + 3, generator=g)
+    gt[::50] = 1.0
+    # 16-byte alignment is required of the base pointers only
+    loss, _, grad = oracle_mod.focal(z.numpy(), gt.numpy(), want_grad=True)
+    _check_focal(ops, z.numpy(), gt.numpy(), loss, grad)
