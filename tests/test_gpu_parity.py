@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from rrnet_b200 import synth
-from tests.conftest import load_golden, rel_err
+from tests.conftest import box_rel_err, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -282,7 +282,7 @@ def test_eval_path_golden(ops):
     for b in range(B):
         n = r["counts"][b]
         assert rel_err(npy(r["s1"][base:base + n]), g["s1_b%d" % b]) < TOL
-        assert rel_err(npy(r["s2"][base:base + n]), g["s2_b%d" % b], floor=1e-3) < TOL
+        assert box_rel_err(npy(r["s2"][base:base + n]), g["s2_b%d" % b]) < TOL
         base += n
 
 
@@ -305,7 +305,7 @@ def test_eval_path_config1_vs_oracle(ops, oracle_mod):
     assert rel_err(npy(r["reg"]), reg, floor=1.0) < TOL
     s1, s2 = oracle_mod.generate_bbox(bxyxy, npy(r["reg"]), kept[:, 4], kept[:, 5], 0, 4.0)
     assert rel_err(npy(r["s1"]), s1) < TOL
-    assert rel_err(npy(r["s2"]), s2, floor=1e-3) < TOL
+    assert box_rel_err(npy(r["s2"]), s2) < TOL
 
 
 def test_eval_path_full_size_properties(ops, oracle_mod):
