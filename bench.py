@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of RRNet's post-backbone path (decode -> stage-1 NMS -> RoIAlign+ReLU ->
+head -> generate_bbox) on synthetic 1088x1920 VisDrone-shaped inputs (BASELINE.json configs[1]:
+batch 8, 10x272x480 heat-map, K=1500, 256-channel stride-4 features).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun for N>1; weak scaling: every rank runs the config-2 batch on its own
+images, then the detections are all-gathered over NCCL for mAP, inside the timed region).
+Prints ONE JSON line on rank 0.  Keys beyond the base contract:
+  roofline      dominant kernel: algorithmic bytes per launch / CUDA-event duration of that kernel
+                inside the timed region, against MEASURED_PEAKS.json (hbm_gbs)
+  cpu_baseline  the reference's CPU call sequence (oracle/ref_port.py: torch CPU + torchvision CPU)
+                timed on this box's host cores on a bounded sample of the same workload
+  e2e           same metric through the public API with HOST (pinned) buffers: H2D of every
+                input and D2H of the result inside the timed region
+  stages_ms     mean per-stage device time from events recorded by the library between stages
+`--impl reference` times the reference arm only (CPU, all host threads, bounded sample per step).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(B=8, C=10, H=272, W=480, K=1500, feat_ch=256)
+WORKLOAD_NAME = "rrnet_eval_post_backbone_1088x1920_b8_k1500"
+METRIC = "images/sec post-backbone decode+RoIAlign+NMS at 1088x1920"
+UNIT = "images/s"
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(steps, warmup, sample_images=1, seed=None):
+    """Time the reference's CPU call sequence (oracle/ref_port.py) on `sample_images` images of the
+    config-2 workload per step, with every host thread torch can use.  Returns (img/s, info)."""
+    from oracle import ref_port
+    from rrnet_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOAD
+    x = synth.eval_inputs(sample_images, w["H"], w["W"], w["K"], synth.SEED_C2 if seed is None else seed)
+    hp = synth.head_params(synth.SEED_C2)
+    stage = {}
+    for _ in range(warmup):
+        ref_port.post_backbone(x["hm"], x["wh"], x["off"], x["feat"], hp, w["K"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref_port.post_backbone(x["hm"], x["wh"], x["off"], x["feat"], hp, w["K"], stage_times=stage)
+    dt = time.perf_counter() - t0
+    ips = sample_images * steps / dt
+    info = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d image(s) of the config-2 workload per step (10x272x480 heat-map, K=%d, 256x272x480 "
+                      "features), %d steps after %d warm-up; torch %s CPU + torchvision CPU call sequence of "
+                      "models/rrnet.py (oracle/ref_port.py), %d threads" % (
+                          sample_images, w["K"], steps, warmup, torch.__version__, cores),
+            "ms_per_image": 1e3 * dt / (steps * sample_images),
+            "stage_ms_per_image": {k: 1e3 * v / (steps * sample_images) for k, v in stage.items()}}
+    return ips, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, max(args.warmup, 1)
+    ips, info = cpu_reference(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": info["ms_per_image"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "step": "1 image (bounded sample of the batch-8 step)", **WORKLOAD},
+            "cpu_baseline": info,
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ roofline helper
+def roi_align_algorithmic_bytes(bxyxy, B, C, H, W):
+    """min(sum_roi C*4*(floor(x2)-floor(x1)+2)*(floor(y2)-floor(y1)+2) clipped to the map,
+    B*C*H*W*4) read + N*C*9*4 write."""
+    import numpy as np
+    r = bxyxy.cpu().numpy().astype(np.float64)
+    x1 = np.clip(np.floor(r[:, 1]), 0, W - 1)
+    x2 = np.clip(np.floor(r[:, 3]) + 1, 0, W - 1)
+    y1 = np.clip(np.floor(r[:, 2]), 0, H - 1)
+    y2 = np.clip(np.floor(r[:, 4]) + 1, 0, H - 1)
+    win = np.maximum(x2 - x1 + 1, 0) * np.maximum(y2 - y1 + 1, 0)
+    read = min(float(win.sum()) * C * 4, float(B) * C * H * W * 4)
+    return read + r.shape[0] * C * 9 * 4, read, float(win.sum()) * C * 4
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def run_product(args):
+    import torch.distributed as dist
+    from rrnet_b200 import ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ops._lib.lib()
+
+    w = WORKLOAD
+    B, C, H, W, K, Cf = w["B"], w["C"], w["H"], w["W"], w["K"], w["feat_ch"]
+    seed = synth.SEED_C2 if world == 1 else synth.SEED_C4 + rank
+    x = synth.eval_inputs(B, H, W, K, seed)
+    hp = synth.head_params(synth.SEED_C2)
+    host = {k: v.pin_memory() for k, v in x.items()}           # e2e inputs live in pinned host memory
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    folded = ops.head_fold({k: v.to(dev) for k, v in hp.items()})
+    path = ops.EvalPath(B, C, H, W, K, folded, device=dev)
+    gathered = gathered_cnt = None
+    if world > 1:
+        gathered = torch.empty(world * B * K, 6, dtype=torch.float32, device=dev)
+        gathered_cnt = torch.empty(world * (B + 1), dtype=torch.int32, device=dev)
+
+    def step(events=None):
+        path.forward(d["hm"], d["wh"], d["off"], d["feat"], stage_events=events)
+        if world > 1:            # all-gather of detections for mAP (padded rows + counts)
+            dist.all_gather_into_tensor(gathered, path.s2)
+            dist.all_gather_into_tensor(gathered_cnt, path.counts)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, device-resident inputs, no host sync inside ----
+    n_ev = args.steps
+    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(n_ev)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    launches0 = ops._lib.launch_count()
+    sync_all()
+    sampler.start()
+    t_beg.record()
+    for i in range(args.steps):
+        step(stage_ev[i])
+    t_end.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = ops._lib.launch_count() - launches0
+    elapsed_ms = t_beg.elapsed_time(t_end)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms / 1e3)
+
+    names = ["decode", "stage1_nms", "roi_align", "head", "generate_bbox"]
+    stage_ms = {n: 0.0 for n in names}
+    for evs in stage_ev:
+        for j, n in enumerate(names):
+            stage_ms[n] += evs[j].elapsed_time(evs[j + 1])
+    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+
+    # ---- e2e: pinned host inputs -> H2D -> path -> D2H of the result, every step ----
+    res_host = torch.empty(B * K, 6, dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty(B + 1, dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = res_host.numel() * 4 + cnt_host.numel() * 4
+
+    def e2e_step():
+        for k in ("hm", "wh", "off", "feat"):
+            d[k].copy_(host[k], non_blocking=True)
+        step()
+        res_host.copy_(path.s2, non_blocking=True)
+        cnt_host.copy_(path.counts, non_blocking=True)
+
+    e2e_step()
+    sync_all()
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_beg.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e_end.record()
+    sync_all()
+    te = torch.tensor([e_beg.elapsed_time(e_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(te.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the step) ----
+    r = path.results()
+    peak, peak_src = measured_peaks()
+    dominant = max(stage_ms, key=stage_ms.get)
+    algo_total, algo_read, window_bytes = roi_align_algorithmic_bytes(r["bxyxy"], B, Cf, H, W)
+    roof_bytes = {
+        "decode": B * C * H * W * 4 + B * K * 16 + B * K * 32,
+        "roi_align": algo_total,
+    }
+    roofline = None
+    if dominant in roof_bytes:
+        ach = roof_bytes[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "algorithmic_bytes": roof_bytes[dominant],
+                    "peak_source": peak_src}
+    else:       # head: fp32 FFMA contraction, 49 valid 3x3 taps -> 993,280 flop per RoI
+        tf = r["n"] * 993280.0 / (stage_ms[dominant] * 1e-3) / 1e12
+        roofline = {"kernel": dominant, "bound": "tensor", "achieved": tf, "peak": 1624.9, "unit": "TFLOP/s",
+                    "frac": tf / 1624.9, "traffic": None, "note": "fp32 FFMA kernel measured against the bf16 tensor peak"}
+    roi_ach = algo_total / (stage_ms["roi_align"] * 1e-3) / 1e9
+    dec_ach = roof_bytes["decode"] / (stage_ms["decode"] * 1e-3) / 1e9
+    extra_roof = {"roi_align_gbs": roi_ach, "roi_align_frac": roi_ach / peak, "decode_gbs": dec_ach,
+                  "decode_frac": dec_ach / peak, "roi_window_bytes_l2": window_bytes,
+                  "head_tflops_fp32": r["n"] * 993280.0 / (stage_ms["head"] * 1e-3) / 1e12}
+
+    # ---- CPU baseline beside it (rank 0, bounded sample) ----
+    cpu_info = None
+    if not args.no_cpu:
+        _, cpu_info = cpu_reference(steps=args.cpu_steps, warmup=1)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, **WORKLOAD, "global_batch": world * B,
+                       "parallelism": "image-sharded x%d, all-gather of detections" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (features 1.07 GB per step)",
+                       "rois_per_step": r["n"]},
+            "clocks": clocks, "gpu_launches": int(launches) * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "roofline": roofline, "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,9 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
  * RRNetOperator.generate_bbox for every image.  All launches go to `stream`, no host sync.
  * Outputs have capacity B*K rows; counts [B+1] as in rr_stage1_nms.
  * roi_feat may be NULL (the workspace then holds it).
+ * stage_events: NULL, or 6 cudaEvent_t handles (as void*) recorded on `stream` before decode and
+ * after decode, stage-1 NMS, RoIAlign, head and generate_bbox (a per-stage timing hook; recording
+ * an event does not synchronise).
  * ---------------------------------------------------------------------------------------- */
 size_t rr_eval_workspace_bytes(int B, int C, int H, int W, int K, int feat_ch);
 int rr_eval_forward(const float* hm, const float* wh, const float* off, const float* feat,
@@ -179,7 +182,7 @@ int rr_eval_forward(const float* hm, const float* wh, const float* off, const fl
                     float* out_dets, int64_t* out_inds,
                     float* out_bxyxy, float* out_scores, float* out_clses, int32_t* out_counts,
                     float* out_reg, float* out_s1, float* out_s2, float* roi_feat,
-                    void* ws, size_t ws_bytes, void* stream);
+                    void* ws, size_t ws_bytes, void* stream, void* const* stage_events);
 
 /* ------------------------------------------------------------------------------------------
  * Training targets: replaces to_heatmap / gaussian_radius / gaussian2d / draw_umich_gaussian

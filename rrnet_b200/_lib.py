@@ -34,7 +34,7 @@ SIGNATURES = {
     "rr_generate_bbox": (c_int, [P, P, P, P, P, c_int, c_float, P, P, P]),
     "rr_eval_workspace_bytes": (c_size_t, [c_int] * 6),
     "rr_eval_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
-                                P, c_float, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+                                P, c_float, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P, P]),
     "rr_render_targets": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "rr_focal_workspace_bytes": (c_size_t, [c_int64]),
     "rr_focal_forward": (c_int, [P, P, c_int64, P, P, c_size_t, P]),

@@ -65,7 +65,7 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
                            float* out_dets, int64_t* out_inds,
                            float* out_bxyxy, float* out_scores, float* out_clses, int32_t* out_counts,
                            float* out_reg, float* out_s1, float* out_s2, float* roi_feat,
-                           void* ws, size_t ws_bytes, void* stream) {
+                           void* ws, size_t ws_bytes, void* stream, void* const* stage_events) {
     if (!hm || !wh || !off || !feat || !head_folded || !out_dets || !out_bxyxy || !out_scores || !out_clses ||
         !out_counts || !out_reg || !out_s1 || !out_s2 || !ws)
         return RR_E_BADARG;
@@ -80,14 +80,25 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     EvalWs w = carve_eval(ws, B, K, C, feat_ch);
     float* rf = roi_feat ? roi_feat : w.roi_feat;
     const int n_cap = B * K;
-    int rc = decode_launch(hm, wh, off, B, C, H, W, K, pool, out_dets, out_inds, w.decode, st);
+    int rc = 0;
+    auto mark = [&](int i) {
+        if (stage_events && stage_events[i]) RR_CUDA(cudaEventRecord((cudaEvent_t)stage_events[i], st), rc);
+    };
+    mark(0);
+    rc = decode_launch(hm, wh, off, B, C, H, W, K, pool, out_dets, out_inds, w.decode, st);
     if (rc) return rc;
+    mark(1);
     rc = stage1_nms_launch(out_dets, B, K, C, nms_thr, out_bxyxy, out_scores, out_clses, out_counts, w.nms, st);
     if (rc) return rc;
+    mark(2);
     const int32_t* n_dev = out_counts + B;
     rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, rf, st);
     if (rc) return rc;
+    mark(3);
     rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);
     if (rc) return rc;
-    return generate_bbox_launch(out_bxyxy, out_reg, out_scores, out_clses, n_dev, n_cap, scale, out_s1, out_s2, st);
+    mark(4);
+    rc = generate_bbox_launch(out_bxyxy, out_reg, out_scores, out_clses, n_dev, n_cap, scale, out_s1, out_s2, st);
+    mark(5);
+    return rc;
 }

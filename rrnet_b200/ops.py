@@ -244,8 +244,15 @@ class EvalPath:
         self.roi_feat = torch.empty(n, feat_ch, 3, 3, **f32) if keep_roi_feat else None
         self.ws = _ws(L.rr_eval_workspace_bytes(B, C, H, W, K, feat_ch), dev)
 
-    def forward(self, hm, wh, off, feat):
+    def forward(self, hm, wh, off, feat, stage_events=None):
+        """stage_events: optional list of 6 torch.cuda.Event(enable_timing=True) recorded by the library
+        before decode and after each of decode / NMS / RoIAlign / head / bbox."""
         B, C, H, W, K, Cf = self.shape
+        ev = None
+        if stage_events is not None:
+            for e in stage_events:
+                e.record()                      # torch creates the CUDA event lazily on first record
+            ev = (ctypes.c_void_p * 6)(*[e.cuda_event for e in stage_events])
         hm, wh, off, feat = _f32(hm, "hm", 4), _f32(wh, "wh", 4), _f32(off, "off", 4), _f32(feat, "feat", 4)
         if tuple(hm.shape) != (B, C, H, W) or tuple(feat.shape) != (B, Cf, H, W):
             raise RRNetB200Error("EvalPath was built for hm %s / feat %s" % ((B, C, H, W), (B, Cf, H, W)))
@@ -253,7 +260,7 @@ class EvalPath:
             _ptr(hm), _ptr(wh), _ptr(off), _ptr(feat), B, C, H, W, K, Cf, self.pool, self.nms_thr,
             _ptr(self.folded), self.scale, _ptr(self.dets), _ptr(self.inds), _ptr(self.bxyxy), _ptr(self.scores),
             _ptr(self.clses), _ptr(self.counts), _ptr(self.reg), _ptr(self.s1), _ptr(self.s2), _ptr(self.roi_feat),
-            _ptr(self.ws), self.ws.numel(), _stream()), "rr_eval_forward")
+            _ptr(self.ws), self.ws.numel(), _stream(), ev), "rr_eval_forward")
         return self
 
     def results(self):
