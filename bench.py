@@ -182,7 +182,7 @@ def run_product(args):
     host = {k: v.pin_memory() for k, v in x.items()}           # e2e inputs live in pinned host memory
     d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     folded = ops.head_fold({k: v.to(dev) for k, v in hp.items()})
-    path = ops.EvalPath(B, C, H, W, K, folded, device=dev)
+    path = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo)
     gathered = gathered_cnt = None
     if world > 1:
         gathered = torch.empty(world * B * K, 6, dtype=torch.float32, device=dev)
@@ -321,6 +321,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

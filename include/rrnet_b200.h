@@ -131,10 +131,15 @@ int rr_soft_nms_batched(float* boxes, const int32_t* seg_offsets, int M, int S,
  *   feat [B,C,H,W]; rois [n_cap,5] = (image index as float, x1,y1,x2,y2)
  *   n_rois_dev: device int32 holding the live row count (rows >= it are skipped), or NULL
  *   to process all n_cap rows.  relu != 0 applies max(v,0) to every tap (fused ReLU).
- *   out [n_cap,C,3,3].
+ *   algo: 0 = tile-centric (each feature tile is staged once in shared memory and serves every
+ *   RoI piece that crosses it; RoIs wider/taller than 64 pixels or over the partial-slot budget
+ *   take the direct path), 1 = direct gather for every RoI.  Both are deterministic.
+ *   out [n_cap,C,3,3].  C <= 1024.
  * ---------------------------------------------------------------------------------------- */
+size_t rr_roi_align_workspace_bytes(int n_cap, int B, int C, int H, int W);
 int rr_roi_align(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
-                 int B, int C, int H, int W, int relu, float* out, void* stream);
+                 int B, int C, int H, int W, int relu, int algo, float* out,
+                 void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Re-regression head (eval mode): replaces RRNet.forward_stage2 ->
@@ -170,7 +175,7 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
  * generate_bbox, i.e. RRNet.forward after forward_stage1 (models/rrnet.py:31-54) plus
  * RRNetOperator.generate_bbox for every image.  All launches go to `stream`, no host sync.
  * Outputs have capacity B*K rows; counts [B+1] as in rr_stage1_nms.
- * roi_feat may be NULL (the workspace then holds it).
+ * roi_feat may be NULL (the workspace then holds it).  roi_algo as in rr_roi_align.
  * stage_events: NULL, or 6 cudaEvent_t handles (as void*) recorded on `stream` before decode and
  * after decode, stage-1 NMS, RoIAlign, head and generate_bbox (a per-stage timing hook; recording
  * an event does not synchronise).
@@ -178,7 +183,7 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
 size_t rr_eval_workspace_bytes(int B, int C, int H, int W, int K, int feat_ch);
 int rr_eval_forward(const float* hm, const float* wh, const float* off, const float* feat,
                     int B, int C, int H, int W, int K, int feat_ch, int pool, double nms_thr,
-                    const float* head_folded, float scale,
+                    int roi_algo, const float* head_folded, float scale,
                     float* out_dets, int64_t* out_inds,
                     float* out_bxyxy, float* out_scores, float* out_clses, int32_t* out_counts,
                     float* out_reg, float* out_s1, float* out_s2, float* roi_feat,

@@ -27,14 +27,15 @@ SIGNATURES = {
     "rr_nms_legacy_host": (c_int, [P, P, P, c_int, c_int, c_float, c_int]),
     "rr_soft_nms_workspace_bytes": (c_size_t, [c_int]),
     "rr_soft_nms_batched": (c_int, [P, P, c_int, c_int, c_float, c_float, c_float, c_int, P, P, P, c_size_t, P]),
-    "rr_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "rr_roi_align_workspace_bytes": (c_size_t, [c_int] * 5),
+    "rr_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
     "rr_head_folded_floats": (c_size_t, []),
     "rr_head_fold": (c_int, [P] * 9 + [P]),
     "rr_head_forward": (c_int, [P, P, c_int, P, P, P]),
     "rr_generate_bbox": (c_int, [P, P, P, P, P, c_int, c_float, P, P, P]),
     "rr_eval_workspace_bytes": (c_size_t, [c_int] * 6),
     "rr_eval_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
-                                P, c_float, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P, P]),
+                                c_int, P, c_float, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P, P]),
     "rr_render_targets": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "rr_focal_workspace_bytes": (c_size_t, [c_int64]),
     "rr_focal_forward": (c_int, [P, P, c_int64, P, P, c_size_t, P]),

@@ -14,19 +14,22 @@ int decode_launch(const float*, const float*, const float*, int, int, int, int, 
 size_t decode_ws_bytes(int B);
 int stage1_nms_launch(const float*, int, int, int, double, float*, float*, float*, int32_t*, void*, cudaStream_t);
 size_t stage1_nms_ws_bytes(int B, int K, int C);
-int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, float*, cudaStream_t);
+int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, void*,
+                     cudaStream_t);
+size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W);
 int head_forward_launch(const float*, const int32_t*, int, const float*, float*, cudaStream_t);
 int generate_bbox_launch(const float*, const float*, const float*, const float*, const int32_t*, int, float,
                          float*, float*, cudaStream_t);
 
 struct EvalWs {
-    void* decode; void* nms; float* roi_feat; size_t bytes;
+    void* decode; void* nms; void* roi; float* roi_feat; size_t bytes;
 };
-static EvalWs carve_eval(void* ws, int B, int K, int C, int feat_ch) {
+static EvalWs carve_eval(void* ws, int B, int K, int C, int H, int W, int feat_ch) {
     Carver cv(ws);
     EvalWs w;
     w.decode = cv.take<char>(decode_ws_bytes(B));
     w.nms = cv.take<char>(stage1_nms_ws_bytes(B, K, C));
+    w.roi = cv.take<char>(roi_align_ws_bytes(B * K, B, feat_ch, H, W));
     w.roi_feat = cv.take<float>((size_t)B * K * feat_ch * RR_POOL * RR_POOL);
     w.bytes = cv.off;
     return w;
@@ -54,14 +57,13 @@ RR_API const char* rr_error_string(int code) {
 }
 
 RR_API size_t rr_eval_workspace_bytes(int B, int C, int H, int W, int K, int feat_ch) {
-    (void)H; (void)W;
-    if (B <= 0 || C <= 0 || K <= 0 || feat_ch <= 0) return 0;
-    return carve_eval(nullptr, B, K, C, feat_ch).bytes;
+    if (B <= 0 || C <= 0 || K <= 0 || feat_ch <= 0 || H <= 0 || W <= 0) return 0;
+    return carve_eval(nullptr, B, K, C, H, W, feat_ch).bytes;
 }
 
 RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, const float* feat,
                            int B, int C, int H, int W, int K, int feat_ch, int pool, double nms_thr,
-                           const float* head_folded, float scale,
+                           int roi_algo, const float* head_folded, float scale,
                            float* out_dets, int64_t* out_inds,
                            float* out_bxyxy, float* out_scores, float* out_clses, int32_t* out_counts,
                            float* out_reg, float* out_s1, float* out_s2, float* roi_feat,
@@ -71,13 +73,13 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
         return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
     if (feat_ch != RR_HEAD_CH) return RR_E_RANGE;               // the head is 256-channel (fasterrcnn_detector.py:9)
-    if (pool != 0 && pool != 3) return RR_E_BADARG;
+    if ((pool != 0 && pool != 3) || roi_algo < 0 || roi_algo > 1) return RR_E_BADARG;
     if (C > RR_MAX_CLASSES || K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;
     if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
-    if (ws_bytes < carve_eval(nullptr, B, K, C, feat_ch).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    if (ws_bytes < carve_eval(nullptr, B, K, C, H, W, feat_ch).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     if (((uintptr_t)out_reg & 15) || ((uintptr_t)head_folded & 15)) return RR_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    EvalWs w = carve_eval(ws, B, K, C, feat_ch);
+    EvalWs w = carve_eval(ws, B, K, C, H, W, feat_ch);
     float* rf = roi_feat ? roi_feat : w.roi_feat;
     const int n_cap = B * K;
     int rc = 0;
@@ -92,7 +94,7 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     if (rc) return rc;
     mark(2);
     const int32_t* n_dev = out_counts + B;
-    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, rf, st);
+    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, roi_algo, rf, w.roi, st);
     if (rc) return rc;
     mark(3);
     rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);

@@ -1,5 +1,5 @@
 // RoIAlign (3x3 bins, adaptive sampling, aligned=False) with the ReLU of the feature map fused
-// into the taps, for sm_100a.
+// in, for sm_100a.
 //
 // Replaces torchvision.ops.roi_align(torch.relu(pre_feat[-1]), bxyxys, (3,3))
 // (models/rrnet.py:51): the reference first writes a full ReLU copy of the feature map
@@ -11,11 +11,30 @@
 // where Ay[ph][Y] (resp. Ax[pw][X]) accumulates, over the samples of bin ph (pw), the weight
 // that sample puts on pixel row Y (column X): hy on y_low, ly on y_high, 0 if the sample is
 // outside [-1, H] (torchvision zeroes those samples).  A sample is valid iff both its row and
-// its column are valid, so validity is separable too.  Each CTA builds Ax/Ay once per RoI in
-// shared memory; then every warp walks the RoI's pixel window of one channel at a time with
-// lanes on consecutive columns (coalesced row segments), keeps three row-contracted
-// accumulators per lane and finishes with a 9-value warp reduction.  Every feature element in
-// the window is read exactly once per (RoI, channel) and no intermediate copy is made.
+// its column are valid, so validity is separable too.  Every pixel therefore contributes to a
+// RoI independently of its neighbours, which allows the sum to be cut along tile borders.
+//
+// Two kernels implement it:
+//
+//  * TILE path (default).  The RoI windows of a detector's top-K boxes overlap heavily (4.5x at
+//    config 2: 5.3 GB of window bytes over a 1.07 GB map), so gathering per RoI is bound by L2,
+//    not HBM.  Instead the map is cut into 32x24-pixel tiles; a work item is (tile, 32 channels,
+//    <= 32 RoI pieces).  A persistent CTA stages the tile once from HBM into shared memory
+//    (coalesced 128-byte rows, ReLU applied on the way in, channel stride odd so that
+//    lane = channel reads are bank-conflict free) and every warp then evaluates (piece, bin
+//    column) units with lane = channel: no cross-lane reduction, all 32 lanes busy whatever the
+//    piece shape, weights warp-uniform.  Pieces of one RoI land in private partial slots
+//    ([slot][9][C], coalesced stores) and a combine kernel adds them in a fixed order, so the
+//    result is deterministic (no floating-point atomics).  Each feature element is read from
+//    HBM once per step (tiles without RoIs are never read).
+//    Supporting kernels: roi_prep (geometry, separable weights, per-tile piece counts),
+//    roi_scan (one CTA: partial-slot offsets, tile list offsets, work items), roi_fill (tile
+//    lists), roi_combine.
+//
+//  * DIRECT path.  One CTA per RoI walks the RoI window straight from global memory with
+//    lanes on consecutive columns.  Used for RoIs whose window exceeds 64 pixels on an axis,
+//    when the partial-slot budget is exhausted, when C is not a multiple of 32, or on request
+//    (algo = 1).
 //
 // The separable order of summation differs from torchvision's sample-by-sample sum at the
 // 1e-7 level (all terms are >= 0 after ReLU, so there is no cancellation); parity is held to
@@ -25,7 +44,22 @@
 namespace rr {
 
 constexpr int kRoiThreads = 256;
-constexpr int kMaxWin = 96;          // fast path: window rows/cols held in shared memory
+constexpr int kMaxWin = 96;          // direct path: window rows/cols held in shared memory
+
+constexpr int kTW = 32;              // tile width  (one 128-byte line per (channel,row))
+constexpr int kTH = 24;              // tile height
+constexpr int kTC = 32;              // channels per work item (lane = channel)
+constexpr int kChStride = kTW * kTH + 1;   // odd: lane = channel reads hit 32 different banks
+constexpr int kTileThreads = 512;
+constexpr int kTileWarps = kTileThreads / 32;
+constexpr int kTileSmem = kTC * kChStride * (int)sizeof(float);
+constexpr int kMaxWinT = 64;         // tile path: window extent limit per axis
+constexpr int kMaxPieces = 12;       // ceil-spans of a 64-window: 3 tile columns x 4 tile rows
+constexpr int kChunk = 32;           // RoI pieces per work item
+constexpr int kSlotsPerRoi = 4;      // partial-slot budget: kSlotsPerRoi * n_cap + #tiles
+
+enum { kFlagTile = 0, kFlagDirect = 1, kFlagZero = 2 };
+enum { kCtlItems = 0, kCtlTicket = 1, kCtlDirect = 2, kCtlWords = 8 };
 
 // Per-axis sample geometry of one RoI (torchvision roi_align_kernel: pre_calc_for_bilinear_interpolate).
 struct AxisGeom {
@@ -33,6 +67,17 @@ struct AxisGeom {
     int grid;           // samples per bin
     int lo, n;          // first pixel touched, number of pixels touched (window extent)
 };
+
+struct __align__(16) RoiPrep {
+    int img, flags;
+    int x_lo, nx, y_lo, ny;           // pixel window touched by valid samples
+    int tx0, ty0, ntx, nty;           // tile range of the window
+    int slot_base;                    // first partial slot (ntx*nty consecutive slots)
+    float count;                      // samples per bin (divisor)
+    signed char cx_lo[4], cx_hi[4];   // per bin column: window-relative pixel range (lo > hi: empty)
+    signed char cy_lo[4], cy_hi[4];
+};
+static_assert(sizeof(RoiPrep) == 64, "RoiPrep is 64 bytes");
 
 // position/weights of sample (p, i) on one axis; returns false when the sample is out of range
 __device__ __forceinline__ bool axis_sample(float start, float bin, int grid, int p, int i, int size,
@@ -89,28 +134,23 @@ __device__ __forceinline__ float axis_weight(const AxisGeom& g, int p, int k, in
     return acc;
 }
 
-__global__ void __launch_bounds__(kRoiThreads)
-roi_align_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
-                 const int* __restrict__ n_rois_dev, int n_cap, int B, int C, int H, int W, int relu,
-                 float* __restrict__ out) {
-    __shared__ float s_ax[RR_POOL][kMaxWin];
-    __shared__ float s_ay[RR_POOL][kMaxWin];
-    __shared__ AxisGeom s_gx, s_gy;
-    const int n = blockIdx.x;
-    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
-    if (n >= live) return;
+// --------------------------------------------------------------------------------------------
+// DIRECT path: one RoI per CTA iteration, straight from global memory.
+// --------------------------------------------------------------------------------------------
+__device__ void roi_direct_one(const float* __restrict__ feat, const float* __restrict__ r,
+                               int B, int C, int H, int W, int relu, float* __restrict__ o,
+                               float (*s_ax)[kMaxWin], float (*s_ay)[kMaxWin], AxisGeom* s_g) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* r = rois + (size_t)n * 5;
     const int bi = (int)r[0];
-    float* o = out + (size_t)n * C * (RR_POOL * RR_POOL);
     if (bi < 0 || bi >= B) {                       // invalid image index: defined output, no fault
         for (int i = tid; i < C * RR_POOL * RR_POOL; i += blockDim.x) o[i] = 0.f;
         return;
     }
-    if (tid == 0) s_gx = axis_geom(r[1], r[3], W);
-    if (tid == 32) s_gy = axis_geom(r[2], r[4], H);
+    __syncthreads();                               // previous iteration done with the shared tables
+    if (tid == 0) s_g[0] = axis_geom(r[1], r[3], W);
+    if (tid == 32) s_g[1] = axis_geom(r[2], r[4], H);
     __syncthreads();
-    const AxisGeom gx = s_gx, gy = s_gy;
+    const AxisGeom gx = s_g[0], gy = s_g[1];
     const float count = (float)max(gx.grid * gy.grid, 1);
     if (gx.n == 0 || gy.n == 0) {                  // RoI entirely outside the map -> zeros
         for (int i = tid; i < C * RR_POOL * RR_POOL; i += blockDim.x) o[i] = 0.f;
@@ -194,10 +234,401 @@ roi_align_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
     }
 }
 
+// Grid-stride over the list of RoIs routed to the direct path (built by roi_scan).
+__global__ void __launch_bounds__(kRoiThreads)
+roi_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
+                  const int* __restrict__ direct_list, const int* __restrict__ ctl,
+                  int B, int C, int H, int W, int relu, float* __restrict__ out) {
+    __shared__ float s_ax[RR_POOL][kMaxWin];
+    __shared__ float s_ay[RR_POOL][kMaxWin];
+    __shared__ AxisGeom s_g[2];
+    const int n_direct = ctl[kCtlDirect];
+    for (int i = blockIdx.x; i < n_direct; i += gridDim.x) {
+        const int n = direct_list[i];
+        roi_direct_one(feat, rois + (size_t)n * 5, B, C, H, W, relu,
+                       out + (size_t)n * C * (RR_POOL * RR_POOL), s_ax, s_ay, s_g);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// TILE path, step 1: per-RoI geometry, separable weights, tile range, per-tile piece counts.
+// One warp per RoI.
+// --------------------------------------------------------------------------------------------
+struct TileDims { int ntx, nty, tiles_per_img; };
+
+__device__ __forceinline__ void bin_ranges(const AxisGeom& g, int size, int lane, signed char* lo3, signed char* hi3) {
+    int lo[RR_POOL], hi[RR_POOL];
+#pragma unroll
+    for (int p = 0; p < RR_POOL; ++p) { lo[p] = 127; hi[p] = -1; }
+    const int total = RR_POOL * g.grid;
+    for (int t = lane; t < total; t += 32) {
+        const int p = t / g.grid, i = t - p * g.grid;
+        int l0, h0; float wl, wh;
+        if (axis_sample(g.start, g.bin, g.grid, p, i, size, l0, h0, wl, wh)) {
+#pragma unroll
+            for (int q = 0; q < RR_POOL; ++q)
+                if (q == p) { lo[q] = min(lo[q], l0 - g.lo); hi[q] = max(hi[q], h0 - g.lo); }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < RR_POOL; ++p) {
+        lo3[p] = (signed char)__reduce_min_sync(0xffffffffu, lo[p]);
+        hi3[p] = (signed char)__reduce_max_sync(0xffffffffu, hi[p]);
+    }
+    lo3[3] = 127; hi3[3] = -1;
+}
+
+__global__ void __launch_bounds__(256)
+roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_dev, int n_cap,
+                int B, int C, int H, int W, int force_direct, TileDims td,
+                RoiPrep* __restrict__ prep, float* __restrict__ wx, float4* __restrict__ wy4,
+                int* __restrict__ tile_count) {
+    const int lane = lane_id();
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
+    if (n >= live) return;
+    const float* r = rois + (size_t)n * 5;
+    RoiPrep rp;
+    rp.img = (int)r[0];
+    rp.flags = kFlagZero;
+    rp.x_lo = rp.nx = rp.y_lo = rp.ny = 0;
+    rp.tx0 = rp.ty0 = rp.ntx = rp.nty = 0;
+    rp.slot_base = 0;
+    rp.count = 1.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { rp.cx_lo[p] = rp.cy_lo[p] = 127; rp.cx_hi[p] = rp.cy_hi[p] = -1; }
+    if (rp.img >= 0 && rp.img < B) {
+        const AxisGeom gx = axis_geom(r[1], r[3], W), gy = axis_geom(r[2], r[4], H);
+        if (gx.n > 0 && gy.n > 0) {
+            rp.x_lo = gx.lo; rp.nx = gx.n; rp.y_lo = gy.lo; rp.ny = gy.n;
+            rp.count = (float)max(gx.grid * gy.grid, 1);
+            if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0) {
+                rp.flags = kFlagDirect;
+            } else {
+                rp.flags = kFlagTile;
+                rp.tx0 = gx.lo / kTW; rp.ntx = (gx.lo + gx.n - 1) / kTW - rp.tx0 + 1;
+                rp.ty0 = gy.lo / kTH; rp.nty = (gy.lo + gy.n - 1) / kTH - rp.ty0 + 1;
+                bin_ranges(gx, W, lane, rp.cx_lo, rp.cx_hi);
+                bin_ranges(gy, H, lane, rp.cy_lo, rp.cy_hi);
+                float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
+                float4* wyn = wy4 + (size_t)n * kMaxWinT;
+                for (int k = lane; k < kMaxWinT; k += 32) {
+                    float a[RR_POOL], b[RR_POOL];
+#pragma unroll
+                    for (int p = 0; p < RR_POOL; ++p) {
+                        a[p] = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? axis_weight(gx, p, k, W) : 0.f;
+                        b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? axis_weight(gy, p, k, H) : 0.f;
+                        wxn[p * kMaxWinT + k] = a[p];
+                    }
+                    wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
+                }
+                const int pieces = rp.ntx * rp.nty;
+                if (lane < pieces) {
+                    const int ty = rp.ty0 + lane / rp.ntx, tx = rp.tx0 + lane % rp.ntx;
+                    atomicAdd(tile_count + rp.img * td.tiles_per_img + ty * td.ntx + tx, 1);
+                }
+            }
+        }
+    }
+    if (lane == 0) prep[n] = rp;
+}
+
+// --------------------------------------------------------------------------------------------
+// TILE path, step 2 (one CTA): exclusive scans -> partial-slot base per RoI, list offset per
+// tile, work items (tile, list start, piece count); RoIs over the slot budget and oversized
+// RoIs are appended to the direct list.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();                               // s_warp reuse across calls
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarp ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;                   // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(1024)
+roi_scan_kernel(RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap,
+                int n_tiles, int slot_cap, const int* __restrict__ tile_count,
+                int* __restrict__ tile_off, int4* __restrict__ items, int* __restrict__ direct_list,
+                int* __restrict__ ctl) {
+    __shared__ int s_warp[33];
+    __shared__ int s_direct;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
+    if (tid == 0) s_direct = 0;
+    // ---- partial-slot bases (RoI order => deterministic) ----
+    {
+        const int per = (live + nt - 1) / nt;
+        const int i0 = min(tid * per, live), i1 = min(i0 + per, live);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += (prep[i].flags == kFlagTile) ? prep[i].ntx * prep[i].nty : 0;
+        int total;
+        int base = block_exclusive_scan(sum, s_warp, total);
+        for (int i = i0; i < i1; ++i) {
+            const int f = prep[i].flags;
+            if (f == kFlagTile) {
+                const int pieces = prep[i].ntx * prep[i].nty;
+                if (base + pieces > slot_cap) {
+                    prep[i].flags = kFlagDirect;   // over budget: its tile_count entries stay, roi_fill skips it
+                    direct_list[atomicAdd(&s_direct, 1)] = i;
+                } else {
+                    prep[i].slot_base = base;
+                }
+                base += pieces;
+            } else if (f == kFlagDirect) {
+                direct_list[atomicAdd(&s_direct, 1)] = i;
+            }
+        }
+    }
+    // ---- tile list offsets and work items ----
+    {
+        const int per = (n_tiles + nt - 1) / nt;
+        const int t0 = min(tid * per, n_tiles), t1 = min(t0 + per, n_tiles);
+        int sum = 0, chunks = 0;
+        for (int t = t0; t < t1; ++t) { int c = tile_count[t]; sum += c; chunks += (c + kChunk - 1) / kChunk; }
+        int total, n_items;
+        int off = block_exclusive_scan(sum, s_warp, total);
+        int ioff = block_exclusive_scan(chunks, s_warp, n_items);
+        for (int t = t0; t < t1; ++t) {
+            const int c = tile_count[t];
+            tile_off[t] = off;
+            for (int k = 0; k < c; k += kChunk) items[ioff++] = make_int4(t, off + k, min(kChunk, c - k), 0);
+            off += c;
+        }
+        if (tid == 0) { tile_off[n_tiles] = total; ctl[kCtlItems] = n_items; ctl[kCtlTicket] = 0; }
+    }
+    __syncthreads();
+    if (tid == 0) ctl[kCtlDirect] = s_direct;
+}
+
+// TILE path, step 3: tile lists (order inside a tile is irrelevant: every piece owns its slot).
+__global__ void __launch_bounds__(256)
+roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap,
+                TileDims td, const int* __restrict__ tile_off, int* __restrict__ tile_fill,
+                int* __restrict__ list) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
+    if (n >= live) return;
+    const RoiPrep rp = prep[n];
+    if (rp.flags != kFlagTile) return;
+    for (int j = 0; j < rp.nty; ++j)
+        for (int i = 0; i < rp.ntx; ++i) {
+            const int t = rp.img * td.tiles_per_img + (rp.ty0 + j) * td.ntx + rp.tx0 + i;
+            list[tile_off[t] + atomicAdd(tile_fill + t, 1)] = n;
+        }
+}
+
+// --------------------------------------------------------------------------------------------
+// TILE path, step 4: persistent CTAs pull (work item, channel group) tickets.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads, 2)
+roi_tile_kernel(const float* __restrict__ feat, const RoiPrep* __restrict__ prep,
+                const float* __restrict__ wx, const float4* __restrict__ wy4,
+                const int* __restrict__ list, const int4* __restrict__ items,
+                const int* __restrict__ tile_off, const int* __restrict__ tile_fill,
+                int* __restrict__ ctl, int C, int H, int W, int relu, TileDims td,
+                float* __restrict__ partial) {
+    extern __shared__ float s_tile[];              // [kTC][kChStride]
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ngroups = C / kTC;
+    const int n_work = ctl[kCtlItems] * ngroups;
+    for (;;) {
+        __syncthreads();                           // everyone is done with s_tile / s_ticket
+        if (tid == 0) s_ticket = atomicAdd(ctl + kCtlTicket, 1);
+        __syncthreads();
+        const int work = s_ticket;
+        if (work >= n_work) break;
+        const int4 it = items[work / ngroups];
+        const int g = work % ngroups;
+        const int t = it.x;
+        const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
+        const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
+        const int px0 = tx * kTW, py0 = ty * kTH;
+        const int n_pieces = min(it.z, tile_off[t] + tile_fill[t] - it.y);
+
+        // ---- stage the tile: 32 channels x kTH rows of 32 pixels, ReLU on the way in ----
+        {
+            const float* src = feat + ((size_t)img * C + (size_t)g * kTC) * H * W;
+            const int gx = px0 + lane;
+            const bool xin = gx < W;
+            constexpr int kRows = kTC * kTH, kUnroll = 8;
+            for (int r0 = warp * kUnroll; r0 < kRows; r0 += kTileWarps * kUnroll) {
+                float v[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int r = r0 + u, c = r / kTH, y = r - c * kTH;
+                    const int gy = py0 + y;
+                    v[u] = (xin && gy < H) ? __ldg(src + ((size_t)c * H + gy) * W + gx) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int r = r0 + u, c = r / kTH, y = r - c * kTH;
+                    s_tile[c * kChStride + y * kTW + lane] = relu ? fmaxf(v[u], 0.f) : v[u];
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- units: (piece, bin column pw), lane = channel ----
+        for (int u = warp; u < n_pieces * RR_POOL; u += kTileWarps) {
+            const int piece = u / RR_POOL, pw = u - piece * RR_POOL;
+            const int roi = __ldg(list + it.y + piece);
+            const RoiPrep* rp = prep + roi;
+            const int x_lo = rp->x_lo, y_lo = rp->y_lo;
+            const int c0 = max(x_lo + rp->cx_lo[pw], px0), c1 = min(x_lo + rp->cx_hi[pw], px0 + kTW - 1);
+            const int r0 = max(y_lo, py0), r1 = min(y_lo + rp->ny - 1, py0 + kTH - 1);
+            const int ncols = c1 - c0 + 1, nrows = r1 - r0 + 1;
+            const int slot = rp->slot_base + (ty - rp->ty0) * rp->ntx + (tx - rp->tx0);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if (ncols > 0 && nrows > 0) {
+                const float wxv = lane < ncols ? __ldg(wx + (size_t)roi * (RR_POOL * kMaxWinT) + pw * kMaxWinT + (c0 - x_lo) + lane) : 0.f;
+                float4 wyv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < nrows) wyv = __ldg(wy4 + (size_t)roi * kMaxWinT + (r0 - y_lo) + lane);
+                const float* fb = s_tile + lane * kChStride + (r0 - py0) * kTW + (c0 - px0);
+                for (int cc = 0; cc < ncols; cc += 8) {
+                    float w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = __shfl_sync(0xffffffffu, wxv, (cc + j) & 31);
+                    const int nj = ncols - cc;
+                    const float* fr = fb + cc;
+                    for (int y = 0; y < nrows; ++y, fr += kTW) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nj) s = fmaf(w[j], fr[j], s);
+                        a0 = fmaf(__shfl_sync(0xffffffffu, wyv.x, y), s, a0);
+                        a1 = fmaf(__shfl_sync(0xffffffffu, wyv.y, y), s, a1);
+                        a2 = fmaf(__shfl_sync(0xffffffffu, wyv.z, y), s, a2);
+                    }
+                }
+            }
+            float* po = partial + ((size_t)slot * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
+            po[0] = a0;
+            po[(size_t)RR_POOL * C] = a1;
+            po[(size_t)2 * RR_POOL * C] = a2;
+        }
+    }
+}
+
+// TILE path, step 5: out[n,c,bin] = (sum over the RoI's pieces, fixed order) / count.
+__global__ void __launch_bounds__(256)
+roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap, int C,
+                   const float* __restrict__ partial, float* __restrict__ out) {
+    extern __shared__ float s_out[];               // [C][9] (+1 pad per channel row of 9 is not needed: stride 9 is odd)
+    const int n = blockIdx.x;
+    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
+    if (n >= live) return;
+    const RoiPrep rp = prep[n];
+    if (rp.flags == kFlagDirect) return;           // written by roi_direct_kernel
+    const int pieces = rp.flags == kFlagTile ? rp.ntx * rp.nty : 0;
+    constexpr int kBins = RR_POOL * RR_POOL;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc[kBins];
+#pragma unroll
+        for (int q = 0; q < kBins; ++q) acc[q] = 0.f;
+        for (int p = 0; p < pieces; ++p) {
+            const float* src = partial + (size_t)(rp.slot_base + p) * kBins * C + c;
+#pragma unroll
+            for (int q = 0; q < kBins; ++q) acc[q] += __ldg(src + (size_t)q * C);
+        }
+#pragma unroll
+        for (int q = 0; q < kBins; ++q) s_out[c * kBins + q] = acc[q] / rp.count;
+    }
+    __syncthreads();
+    float* o = out + (size_t)n * C * kBins;
+    for (int i = threadIdx.x; i < C * kBins; i += blockDim.x) o[i] = s_out[i];
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+struct RoiWs {
+    RoiPrep* prep; float* wx; float4* wy4;
+    int* zeroed; size_t zeroed_bytes;              // tile_count | tile_fill | ctl  (one memset)
+    int* tile_count; int* tile_fill; int* ctl;
+    int* tile_off; int4* items; int* direct_list; int* list; float* partial;
+    int n_tiles, slot_cap; TileDims td;
+    size_t bytes;
+};
+
+static RoiWs carve_roi(void* ws, int n_cap, int B, int C, int H, int W) {
+    RoiWs w;
+    w.td.ntx = (W + kTW - 1) / kTW;
+    w.td.nty = (H + kTH - 1) / kTH;
+    w.td.tiles_per_img = w.td.ntx * w.td.nty;
+    w.n_tiles = B * w.td.tiles_per_img;
+    w.slot_cap = kSlotsPerRoi * n_cap + w.n_tiles;
+    Carver cv(ws);
+    w.prep = cv.take<RoiPrep>(n_cap);
+    w.wx = cv.take<float>((size_t)n_cap * RR_POOL * kMaxWinT);
+    w.wy4 = cv.take<float4>((size_t)n_cap * kMaxWinT);
+    w.zeroed = cv.take<int>((size_t)2 * w.n_tiles + kCtlWords);
+    w.zeroed_bytes = ((size_t)2 * w.n_tiles + kCtlWords) * sizeof(int);
+    w.tile_count = w.zeroed; w.tile_fill = w.zeroed + w.n_tiles; w.ctl = w.zeroed + 2 * w.n_tiles;
+    w.tile_off = cv.take<int>((size_t)w.n_tiles + 1);
+    w.items = cv.take<int4>((size_t)w.n_tiles + (size_t)n_cap * kMaxPieces / kChunk + 1);
+    w.direct_list = cv.take<int>(n_cap);
+    w.list = cv.take<int>((size_t)n_cap * kMaxPieces);
+    w.partial = cv.take<float>((size_t)w.slot_cap * RR_POOL * RR_POOL * C);
+    w.bytes = cv.off;
+    return w;
+}
+
+size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W) {
+    return carve_roi(nullptr, n_cap, B, C, H, W).bytes;
+}
+
 int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
-                     int B, int C, int H, int W, int relu, float* out, cudaStream_t st) {
+                     int B, int C, int H, int W, int relu, int algo, float* out, void* ws, cudaStream_t st) {
     int rc = 0;
-    roi_align_kernel<<<n_cap, kRoiThreads, 0, st>>>(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, out);
+    RoiWs w = carve_roi(ws, n_cap, B, C, H, W);
+    RR_CUDA(cudaMemsetAsync(w.zeroed, 0, w.zeroed_bytes, st), rc);
+    if (rc) return rc;
+    const int force_direct = algo == 1;
+    roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
+                                                    w.prep, w.wx, w.wy4, w.tile_count);
+    RR_LAUNCHED(rc);
+    roi_scan_kernel<<<1, 1024, 0, st>>>(w.prep, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
+                                        w.tile_off, w.items, w.direct_list, w.ctl);
+    RR_LAUNCHED(rc);
+    if (!force_direct && C % kTC == 0) {
+        roi_fill_kernel<<<(n_cap + 255) / 256, 256, 0, st>>>(w.prep, n_rois_dev, n_cap, w.td, w.tile_off,
+                                                            w.tile_fill, w.list);
+        RR_LAUNCHED(rc);
+        static bool attr_set = false;
+        if (!attr_set) {
+            RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
+            attr_set = true;
+        }
+        roi_tile_kernel<<<2 * kSMs, kTileThreads, kTileSmem, st>>>(feat, w.prep, w.wx, w.wy4, w.list, w.items,
+                                                                  w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
+                                                                  w.td, w.partial);
+        RR_LAUNCHED(rc);
+    }
+    roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
+        w.prep, n_rois_dev, n_cap, C, w.partial, out);
+    RR_LAUNCHED(rc);
+    roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * kSMs, kRoiThreads, 0, st>>>(
+        feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
     RR_LAUNCHED(rc);
     return rc;
 }
@@ -206,10 +637,18 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
 
 using namespace rr;
 
+RR_API size_t rr_roi_align_workspace_bytes(int n_cap, int B, int C, int H, int W) {
+    if (n_cap <= 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return roi_align_ws_bytes(n_cap, B, C, H, W);
+}
+
 RR_API int rr_roi_align(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
-                        int B, int C, int H, int W, int relu, float* out, void* stream) {
+                        int B, int C, int H, int W, int relu, int algo, float* out,
+                        void* ws, size_t ws_bytes, void* stream) {
     if (n_cap == 0) return 0;
-    if (!feat || !rois || !out) return RR_E_BADARG;
-    if (n_cap < 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return RR_E_BADARG;
-    return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, out, (cudaStream_t)stream);
+    if (!feat || !rois || !out || !ws) return RR_E_BADARG;
+    if (n_cap < 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0 || algo < 0 || algo > 1) return RR_E_BADARG;
+    if (C > 1024) return RR_E_RANGE;                 // roi_combine stages one RoI (C*9 floats) in shared memory
+    if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, out, ws, (cudaStream_t)stream);
 }

@@ -142,8 +142,9 @@ def soft_nms_batched(boxes5, seg_offsets, sigma=0.5, Nt=0.3, threshold=0.001, me
 
 
 # --------------------------------------------------------------------------------- RoIAlign / head / bbox
-def roi_align(feat, rois, n_dev=None, relu=True):
-    """torchvision.ops.roi_align(relu(feat), rois, (3,3)) (models/rrnet.py:51) -> [n,C,3,3]."""
+def roi_align(feat, rois, n_dev=None, relu=True, algo=0):
+    """torchvision.ops.roi_align(relu(feat), rois, (3,3)) (models/rrnet.py:51) -> [n,C,3,3].
+    algo 0 = tile-centric kernel (default), 1 = direct per-RoI gather."""
     feat, rois = _f32(feat, "feat", 4), _f32(rois, "rois", 2)
     B, C, H, W = feat.shape
     n = rois.shape[0]
@@ -152,8 +153,12 @@ def roi_align(feat, rois, n_dev=None, relu=True):
     out = torch.empty(n, C, 3, 3, dtype=torch.float32, device=feat.device)
     if n_dev is not None:
         n_dev = _i32(n_dev, "n_dev")
-    check(_lib.lib().rr_roi_align(_ptr(feat), _ptr(rois), _ptr(n_dev), n, B, C, H, W, int(bool(relu)), _ptr(out),
-                                  _stream()), "rr_roi_align")
+    if n == 0:
+        return out
+    L = _lib.lib()
+    ws = _ws(L.rr_roi_align_workspace_bytes(n, B, C, H, W), feat.device)
+    check(L.rr_roi_align(_ptr(feat), _ptr(rois), _ptr(n_dev), n, B, C, H, W, int(bool(relu)), int(algo), _ptr(out),
+                         _ptr(ws), ws.numel(), _stream()), "rr_roi_align")
     return out
 
 
@@ -224,11 +229,12 @@ class EvalPath:
     RoIAlign+ReLU -> head -> generate_bbox in one C-ABI call (rr_eval_forward).  CUDA-graph capturable."""
 
     def __init__(self, B, C, H, W, K, head_folded, feat_ch=256, pool=0, nms_thr=0.7, scale=4.0, device=None,
-                 keep_roi_feat=False):
+                 keep_roi_feat=False, roi_algo=0):
         L = _lib.lib()
         dev = torch.device(device if device is not None else "cuda")
         self.shape = (B, C, H, W, K, feat_ch)
         self.pool, self.nms_thr, self.scale = int(pool), float(nms_thr), float(scale)
+        self.roi_algo = int(roi_algo)
         self.folded = _f32(head_folded, "head_folded")
         n = B * K
         f32 = dict(dtype=torch.float32, device=dev)
@@ -258,7 +264,7 @@ class EvalPath:
             raise RRNetB200Error("EvalPath was built for hm %s / feat %s" % ((B, C, H, W), (B, Cf, H, W)))
         check(_lib.lib().rr_eval_forward(
             _ptr(hm), _ptr(wh), _ptr(off), _ptr(feat), B, C, H, W, K, Cf, self.pool, self.nms_thr,
-            _ptr(self.folded), self.scale, _ptr(self.dets), _ptr(self.inds), _ptr(self.bxyxy), _ptr(self.scores),
+            self.roi_algo, _ptr(self.folded), self.scale, _ptr(self.dets), _ptr(self.inds), _ptr(self.bxyxy), _ptr(self.scores),
             _ptr(self.clses), _ptr(self.counts), _ptr(self.reg), _ptr(self.s1), _ptr(self.s2), _ptr(self.roi_feat),
             _ptr(self.ws), self.ws.numel(), _stream(), ev), "rr_eval_forward")
         return self

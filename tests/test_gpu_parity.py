@@ -215,34 +215,80 @@ def test_stage1_single_class_worst_case(ops, oracle_mod):
 
 
 # ===================================================================== RoIAlign (a6)
-def test_roi_align_golden_edge_cases(ops):
+ALGOS = [0, 1]      # 0 = tile-centric kernel (+ direct fallback), 1 = direct gather for every RoI
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_roi_align_golden_edge_cases(ops, algo):
     g = load_golden("roi_align")
-    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=True)
+    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=True, algo=algo)
     assert rel_err(npy(out), g["out_relu"], floor=1e-3) < TOL
-    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=False)
+    out = ops.roi_align(dev(g["feat"]), dev(g["rois"]), relu=False, algo=algo)
     assert rel_err(npy(out), g["out_raw"], floor=1.0) < TOL          # signed taps cancel: relative to max
 
 
-def test_roi_align_vs_oracle_random(ops, oracle_mod):
-    B, C, H, W = 2, 256, 48, 64
-    feat = synth.features(B, C, H, W, 3)
-    g = torch.Generator().manual_seed(4)
-    n = 300
+def _random_rois(n, B, H, W, seed, wh_max=39.0):
+    g = torch.Generator().manual_seed(seed)
     xy = torch.rand(n, 2, generator=g) * torch.tensor([W * 1.1, H * 1.1]) - 3.0
-    wh = torch.rand(n, 2, generator=g) * 39.0 + 0.2
+    wh = torch.rand(n, 2, generator=g) * wh_max + 0.2
     rois = torch.cat([torch.randint(0, B, (n, 1), generator=g).float(), xy, xy + wh], 1)
     rois[::17, 3:] = rois[::17, 1:3]                                  # degenerate (w = h = 0)
-    out = npy(ops.roi_align(dev(feat), dev(rois)))
+    return rois
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_roi_align_vs_oracle_random(ops, oracle_mod, algo):
+    B, C, H, W = 2, 256, 48, 64
+    feat = synth.features(B, C, H, W, 3)
+    rois = _random_rois(300, B, H, W, 4)
+    out = npy(ops.roi_align(dev(feat), dev(rois), algo=algo))
     ref = oracle_mod.roi_align(feat.numpy(), rois.numpy(), relu=True)
     assert rel_err(out, ref, floor=1e-3) < TOL
 
 
-def test_roi_align_device_count_and_huge_roi(ops, oracle_mod):
+def test_roi_align_tile_path_mixed_sizes(ops, oracle_mod):
+    """Odd map size (partial edge tiles, W not a multiple of 32), RoIs from sub-pixel to larger than the
+    64-pixel tile-path limit (those take the direct path inside the same call), unsorted image indices."""
+    B, C, H, W = 3, 64, 77, 150
+    feat = synth.features(B, C, H, W, 9)
+    rois = _random_rois(500, B, H, W, 10, wh_max=90.0)
+    rois[5] = torch.tensor([1.0, -200.0, -200.0, -150.0, -150.0])      # entirely outside -> zeros
+    rois[6] = torch.tensor([7.0, 1.0, 1.0, 9.0, 9.0])                  # invalid image index -> zeros
+    rois[7] = torch.tensor([0.0, 31.5, 23.5, 32.5, 24.5])              # straddles a tile corner
+    rois[8] = torch.tensor([2.0, 0.0, 0.0, 63.0, 63.0])                # widest tile-path window
+    out = ops.roi_align(dev(feat), dev(rois), algo=0)
+    ok = np.ones(500, bool); ok[6] = False
+    ref = oracle_mod.roi_align(feat.numpy(), rois.numpy()[ok], relu=True)
+    assert rel_err(npy(out)[ok], ref, floor=1e-3) < TOL
+    assert float(out[6].abs().max()) == 0.0 and float(out[5].abs().max()) == 0.0
+    # the two algorithms agree to rounding and each is deterministic run to run
+    out1 = ops.roi_align(dev(feat), dev(rois), algo=1)
+    assert rel_err(npy(out), npy(out1), floor=1e-3) < TOL
+    assert torch.equal(out, ops.roi_align(dev(feat), dev(rois), algo=0))
+
+
+def test_roi_align_channels_not_multiple_of_32_and_slot_overflow(ops, oracle_mod):
+    feat = synth.features(1, 8, 40, 50, 11)                               # C=8: every RoI takes the direct path
+    rois = _random_rois(64, 1, 40, 50, 12)
+    out = npy(ops.roi_align(dev(feat), dev(rois), algo=0))
+    assert rel_err(out, oracle_mod.roi_align(feat.numpy(), rois.numpy(), relu=True), floor=1e-3) < TOL
+    # 60x60 RoIs over a tiny-tile grid: 9-12 pieces each, more than the 4-per-RoI slot budget allows ->
+    # the RoIs past the budget fall back to the direct path, results unchanged
+    feat = synth.features(1, 32, 96, 128, 13)
+    g = torch.Generator().manual_seed(14)
+    xy = torch.rand(200, 2, generator=g) * torch.tensor([60.0, 30.0]) + 1.0
+    rois = torch.cat([torch.zeros(200, 1), xy, xy + 60.0], 1)
+    out = npy(ops.roi_align(dev(feat), dev(rois), algo=0))
+    assert rel_err(out, oracle_mod.roi_align(feat.numpy(), rois.numpy(), relu=True), floor=1e-3) < TOL
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_roi_align_device_count_and_huge_roi(ops, oracle_mod, algo):
     B, C, H, W = 1, 8, 120, 150
     feat = synth.features(B, C, H, W, 6)
     rois = torch.tensor([[0, -10.0, -10.0, 160.0, 130.0], [0, 3.0, 4.0, 140.0, 9.0], [0, 1.0, 1.0, 5.0, 5.0]])
     n_dev = torch.tensor([2], dtype=torch.int32).cuda()
-    out = ops.roi_align(dev(feat), dev(rois), n_dev=n_dev)
+    out = ops.roi_align(dev(feat), dev(rois), n_dev=n_dev, algo=algo)
     ref = oracle_mod.roi_align(feat.numpy(), rois.numpy()[:2], relu=True)
     assert rel_err(npy(out[:2]), ref, floor=1e-3) < TOL
 
