@@ -52,10 +52,11 @@ constexpr int kTC = 32;              // channels per work item (lane = channel)
 constexpr int kChStride = kTW * kTH + 1;   // odd: lane = channel reads hit 32 different banks
 constexpr int kTileThreads = 512;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kTileSmem = kTC * kChStride * (int)sizeof(float);
+constexpr int kChunk = 32;           // RoI pieces per work item
+constexpr int kTileTileFloats = (kTC * kChStride + 3) / 4 * 4;      // tile, padded to 16 bytes
+constexpr int kTileSmem = (kTileTileFloats + kChunk * 2 * 4 + kChunk * kTH * 4) * (int)sizeof(float);   // + piece descriptors + row weights
 constexpr int kMaxWinT = 64;         // tile path: window extent limit per axis
 constexpr int kMaxPieces = 12;       // ceil-spans of a 64-window: 3 tile columns x 4 tile rows
-constexpr int kChunk = 32;           // RoI pieces per work item
 constexpr int kSlotsPerRoi = 4;      // partial-slot budget: kSlotsPerRoi * n_cap + #tiles
 
 enum { kFlagTile = 0, kFlagDirect = 1, kFlagZero = 2 };
@@ -252,7 +253,7 @@ roi_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois
 
 // --------------------------------------------------------------------------------------------
 // TILE path, step 1: per-RoI geometry, separable weights, tile range, per-tile piece counts.
-// One warp per RoI.
+// One warp per RoI.  meta[n] = number of tile pieces (0: output is all zeros), or -1: direct path.
 // --------------------------------------------------------------------------------------------
 struct TileDims { int ntx, nty, tiles_per_img; };
 
@@ -281,8 +282,8 @@ __device__ __forceinline__ void bin_ranges(const AxisGeom& g, int size, int lane
 __global__ void __launch_bounds__(256)
 roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_dev, int n_cap,
                 int B, int C, int H, int W, int force_direct, TileDims td,
-                RoiPrep* __restrict__ prep, float* __restrict__ wx, float4* __restrict__ wy4,
-                int* __restrict__ tile_count) {
+                RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ wx,
+                float4* __restrict__ wy4, int* __restrict__ tile_count) {
     const int lane = lane_id();
     const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
@@ -297,6 +298,7 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
     rp.count = 1.f;
 #pragma unroll
     for (int p = 0; p < 4; ++p) { rp.cx_lo[p] = rp.cy_lo[p] = 127; rp.cx_hi[p] = rp.cy_hi[p] = -1; }
+    int m = 0;
     if (rp.img >= 0 && rp.img < B) {
         const AxisGeom gx = axis_geom(r[1], r[3], W), gy = axis_geom(r[2], r[4], H);
         if (gx.n > 0 && gy.n > 0) {
@@ -304,6 +306,7 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
             rp.count = (float)max(gx.grid * gy.grid, 1);
             if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0) {
                 rp.flags = kFlagDirect;
+                m = -1;
             } else {
                 rp.flags = kFlagTile;
                 rp.tx0 = gx.lo / kTW; rp.ntx = (gx.lo + gx.n - 1) / kTW - rp.tx0 + 1;
@@ -312,31 +315,32 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
                 bin_ranges(gy, H, lane, rp.cy_lo, rp.cy_hi);
                 float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
                 float4* wyn = wy4 + (size_t)n * kMaxWinT;
-                for (int k = lane; k < kMaxWinT; k += 32) {
-                    float a[RR_POOL], b[RR_POOL];
+                const int kmax = max(gx.n, gy.n);
+                for (int k = lane; k < kmax; k += 32) {
+                    float b[RR_POOL];
 #pragma unroll
                     for (int p = 0; p < RR_POOL; ++p) {
-                        a[p] = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? axis_weight(gx, p, k, W) : 0.f;
+                        const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? axis_weight(gx, p, k, W) : 0.f;
                         b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? axis_weight(gy, p, k, H) : 0.f;
-                        wxn[p * kMaxWinT + k] = a[p];
+                        if (k < gx.n) wxn[p * kMaxWinT + k] = a;
                     }
-                    wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
+                    if (k < gy.n) wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
                 }
-                const int pieces = rp.ntx * rp.nty;
-                if (lane < pieces) {
+                m = rp.ntx * rp.nty;
+                if (lane < m) {
                     const int ty = rp.ty0 + lane / rp.ntx, tx = rp.tx0 + lane % rp.ntx;
                     atomicAdd(tile_count + rp.img * td.tiles_per_img + ty * td.ntx + tx, 1);
                 }
             }
         }
     }
-    if (lane == 0) prep[n] = rp;
+    if (lane == 0) { prep[n] = rp; meta[n] = m; }
 }
 
 // --------------------------------------------------------------------------------------------
-// TILE path, step 2 (one CTA): exclusive scans -> partial-slot base per RoI, list offset per
-// tile, work items (tile, list start, piece count); RoIs over the slot budget and oversized
-// RoIs are appended to the direct list.
+// TILE path, step 2 (one CTA): exclusive scans -> partial-slot base per RoI (slot[n]; -1 = direct
+// path, which also takes the RoIs that do not fit the slot budget), list offset per tile, work
+// items (tile, list start, piece count), the direct list.
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
     const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
@@ -364,42 +368,57 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
     return s_warp[warp] + inc - v;
 }
 
-__global__ void __launch_bounds__(1024)
-roi_scan_kernel(RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap,
+constexpr int kScanThreads = 1024;
+constexpr int kScanPer = 16;                       // elements per thread and round (4 x int4, coalesced per warp)
+
+__global__ void __launch_bounds__(kScanThreads)
+roi_scan_kernel(const int* __restrict__ meta, const int* __restrict__ n_rois_dev, int n_cap,
                 int n_tiles, int slot_cap, const int* __restrict__ tile_count,
-                int* __restrict__ tile_off, int4* __restrict__ items, int* __restrict__ direct_list,
-                int* __restrict__ ctl) {
+                int* __restrict__ slot, int* __restrict__ tile_off, int4* __restrict__ items,
+                int* __restrict__ direct_list, int* __restrict__ ctl) {
     __shared__ int s_warp[33];
     __shared__ int s_direct;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     if (tid == 0) s_direct = 0;
-    // ---- partial-slot bases (RoI order => deterministic) ----
-    {
-        const int per = (live + nt - 1) / nt;
-        const int i0 = min(tid * per, live), i1 = min(i0 + per, live);
+    __syncthreads();
+    // ---- partial-slot bases in RoI order (deterministic); meta/slot are padded to a multiple of 4 ----
+    int carry = 0;
+    for (int base0 = 0; base0 < live; base0 += kScanThreads * kScanPer) {
+        const int i0 = base0 + tid * kScanPer;
+        int v[kScanPer];
+#pragma unroll
+        for (int q = 0; q < kScanPer / 4; ++q) {
+            int4 t = make_int4(0, 0, 0, 0);
+            if (i0 + 4 * q < live) t = *reinterpret_cast<const int4*>(meta + i0 + 4 * q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
         int sum = 0;
-        for (int i = i0; i < i1; ++i) sum += (prep[i].flags == kFlagTile) ? prep[i].ntx * prep[i].nty : 0;
+#pragma unroll
+        for (int q = 0; q < kScanPer; ++q) sum += (i0 + q < live && v[q] > 0) ? v[q] : 0;
         int total;
-        int base = block_exclusive_scan(sum, s_warp, total);
-        for (int i = i0; i < i1; ++i) {
-            const int f = prep[i].flags;
-            if (f == kFlagTile) {
-                const int pieces = prep[i].ntx * prep[i].nty;
-                if (base + pieces > slot_cap) {
-                    prep[i].flags = kFlagDirect;   // over budget: its tile_count entries stay, roi_fill skips it
-                    direct_list[atomicAdd(&s_direct, 1)] = i;
-                } else {
-                    prep[i].slot_base = base;
-                }
-                base += pieces;
-            } else if (f == kFlagDirect) {
-                direct_list[atomicAdd(&s_direct, 1)] = i;
+        int run = carry + block_exclusive_scan(sum, s_warp, total);
+        carry += total;
+#pragma unroll
+        for (int q = 0; q < kScanPer; ++q) {
+            const int i = i0 + q;
+            if (i < live) {
+                int sb;
+                if (v[q] < 0) sb = -1;
+                else if (v[q] == 0) sb = 0;
+                else { sb = (run + v[q] <= slot_cap) ? run : -1; run += v[q]; }
+                if (sb < 0) direct_list[atomicAdd(&s_direct, 1)] = i;
+                v[q] = sb;
             }
         }
+#pragma unroll
+        for (int q = 0; q < kScanPer / 4; ++q)
+            if (i0 + 4 * q < live)
+                *reinterpret_cast<int4*>(slot + i0 + 4 * q) = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
     // ---- tile list offsets and work items ----
     {
+        const int nt = blockDim.x;
         const int per = (n_tiles + nt - 1) / nt;
         const int t0 = min(tid * per, n_tiles), t1 = min(t0 + per, n_tiles);
         int sum = 0, chunks = 0;
@@ -419,126 +438,215 @@ roi_scan_kernel(RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, 
     if (tid == 0) ctl[kCtlDirect] = s_direct;
 }
 
-// TILE path, step 3: tile lists (order inside a tile is irrelevant: every piece owns its slot).
+// --------------------------------------------------------------------------------------------
+// TILE path, step 3: tile lists of piece descriptors (order inside a tile is irrelevant: every
+// piece owns its slot).  A descriptor is 8 ints:
+//   roi, slot, rows = r0 | nrows<<8 | wy_off<<16, cols[3] = c0 | ncols<<8 | wx_off<<16, 0, 0
+// (r0/c0 tile-local start, wy_off offset of the first row inside the RoI window), followed in two side
+// arrays by the piece's slices of the separable weights: list_wx[pos][3][32], list_wy[pos][kTH] (zero padded).
+// --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap,
-                TileDims td, const int* __restrict__ tile_off, int* __restrict__ tile_fill,
-                int* __restrict__ list) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
+                const float* __restrict__ wx, const float4* __restrict__ wy4,
+                const int* __restrict__ n_rois_dev, int n_cap, TileDims td,
+                const int* __restrict__ tile_off, int* __restrict__ tile_fill,
+                int4* __restrict__ list, float* __restrict__ list_wx, float4* __restrict__ list_wy) {
+    const int lane = lane_id();
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();      // one warp per RoI
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     if (n >= live) return;
     const RoiPrep rp = prep[n];
-    if (rp.flags != kFlagTile) return;
-    for (int j = 0; j < rp.nty; ++j)
+    const int sb = slot[n];
+    if (rp.flags != kFlagTile || sb < 0) return;
+    const float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
+    const float4* wyn = wy4 + (size_t)n * kMaxWinT;
+    for (int j = 0; j < rp.nty; ++j) {
+        const int py0 = (rp.ty0 + j) * kTH;
+        const int r0 = max(rp.y_lo, py0), r1 = min(rp.y_lo + rp.ny - 1, py0 + kTH - 1);
+        const int nrows = r1 - r0 + 1, wyo = r0 - rp.y_lo;
+        const int rows = (r0 - py0) | (nrows << 8) | (wyo << 16);
         for (int i = 0; i < rp.ntx; ++i) {
+            const int px0 = (rp.tx0 + i) * kTW;
+            int cols[RR_POOL], ncol[RR_POOL], wxo[RR_POOL];
+#pragma unroll
+            for (int p = 0; p < RR_POOL; ++p) {
+                const int c0 = max(rp.x_lo + rp.cx_lo[p], px0), c1 = min(rp.x_lo + rp.cx_hi[p], px0 + kTW - 1);
+                ncol[p] = max(c1 - c0 + 1, 0);
+                wxo[p] = c0 - rp.x_lo;
+                cols[p] = ncol[p] > 0 ? ((c0 - px0) | (ncol[p] << 8)) : 0;
+            }
             const int t = rp.img * td.tiles_per_img + (rp.ty0 + j) * td.ntx + rp.tx0 + i;
-            list[tile_off[t] + atomicAdd(tile_fill + t, 1)] = n;
+            int pos = 0;
+            if (lane == 0) pos = tile_off[t] + atomicAdd(tile_fill + t, 1);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (lane == 0) {
+                list[2 * pos] = make_int4(n, sb + j * rp.ntx + i, rows, cols[0]);
+                list[2 * pos + 1] = make_int4(cols[1], cols[2], 0, 0);
+            }
+            // the piece's slices of the separable weights, zero padded, in list order
+            if (lane < kTH)
+                list_wy[(size_t)pos * kTH + lane] = lane < nrows ? wyn[wyo + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < RR_POOL; ++p)
+                list_wx[((size_t)pos * RR_POOL + p) * kTW + lane] = lane < ncol[p] ? wxn[p * kMaxWinT + wxo[p] + lane] : 0.f;
         }
+    }
 }
 
 // --------------------------------------------------------------------------------------------
 // TILE path, step 4: persistent CTAs pull (work item, channel group) tickets.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileThreads, 2)
-roi_tile_kernel(const float* __restrict__ feat, const RoiPrep* __restrict__ prep,
-                const float* __restrict__ wx, const float4* __restrict__ wy4,
-                const int* __restrict__ list, const int4* __restrict__ items,
-                const int* __restrict__ tile_off, const int* __restrict__ tile_fill,
-                int* __restrict__ ctl, int C, int H, int W, int relu, TileDims td,
-                float* __restrict__ partial) {
-    extern __shared__ float s_tile[];              // [kTC][kChStride]
-    __shared__ int s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ngroups = C / kTC;
-    const int n_work = ctl[kCtlItems] * ngroups;
-    for (;;) {
-        __syncthreads();                           // everyone is done with s_tile / s_ticket
-        if (tid == 0) s_ticket = atomicAdd(ctl + kCtlTicket, 1);
-        __syncthreads();
-        const int work = s_ticket;
-        if (work >= n_work) break;
-        const int4 it = items[work / ngroups];
-        const int g = work % ngroups;
-        const int t = it.x;
-        const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
-        const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
-        const int px0 = tx * kTW, py0 = ty * kTH;
-        const int n_pieces = min(it.z, tile_off[t] + tile_fill[t] - it.y);
+template <int NJ>
+__device__ __forceinline__ void unit_rows(const float* __restrict__ fr, const float4* __restrict__ s_wy, int nrows,
+                                          const float (&w)[8], float& a0, float& a1, float& a2) {
+#pragma unroll 2
+    for (int y = 0; y < nrows; ++y, fr += kTW) {
+        float s = w[0] * fr[0];
+#pragma unroll
+        for (int j = 1; j < NJ; ++j) s = fmaf(w[j], fr[j], s);
+        const float4 wy = s_wy[y];                 // warp-uniform address: one broadcast wavefront
+        a0 = fmaf(wy.x, s, a0);
+        a1 = fmaf(wy.y, s, a1);
+        a2 = fmaf(wy.z, s, a2);
+    }
+}
 
-        // ---- stage the tile: 32 channels x kTH rows of 32 pixels, ReLU on the way in ----
+// one channel of the tile: kTH coalesced 128-byte rows -> shared memory, ReLU on the way in.
+// p points at (row py0, clamped column) of the channel plane; rows past the map are clamped too
+// (those tile cells are never read: piece ranges are clipped to the map), so no load is predicated.
+__device__ __forceinline__ float ldg_row(const float* p, unsigned row_bytes, unsigned y) {
+    unsigned long long a;                          // one IMAD.WIDE.U32 per row address
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row_bytes), "r"(y), "l"(p));
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(a));
+    return v;
+}
+
+template <bool kFull>
+__device__ __forceinline__ void stage_channels(const float* __restrict__ p, size_t plane, float* __restrict__ d,
+                                               int W, int rows_valid, int relu) {
+    constexpr int kPer = kTC / kTileWarps;         // channels per warp: all kPer*kTH row loads are in flight together
+    const unsigned row_bytes = (unsigned)W * 4u;
+    float v[kPer][kTH];
+#pragma unroll
+    for (int cc = 0; cc < kPer; ++cc)
+#pragma unroll
+        for (int y = 0; y < kTH; ++y)
+            v[cc][y] = ldg_row(p + cc * plane, row_bytes, kFull ? (unsigned)y : (unsigned)min(y, rows_valid - 1));
+#pragma unroll
+    for (int cc = 0; cc < kPer; ++cc)
+#pragma unroll
+        for (int y = 0; y < kTH; ++y) d[cc * kChStride + y * kTW] = relu ? fmaxf(v[cc][y], 0.f) : v[cc][y];
+}
+
+// Persistent CTAs, two per SM (while one stages its next tile the other one computes).  Per ticket:
+// stage tile + piece tables -> barrier -> every warp evaluates its (piece, bin column) units -> barrier.
+// The next ticket is fetched by one thread during the compute phase.
+__global__ void __launch_bounds__(kTileThreads, 2)
+roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
+                const float* __restrict__ list_wx, const float4* __restrict__ list_wy,
+                const int4* __restrict__ items, const int* __restrict__ tile_off,
+                const int* __restrict__ tile_fill, int* __restrict__ ctl,
+                int C, int H, int W, int relu, TileDims td, float* __restrict__ partial) {
+    extern __shared__ float s_tile[];              // [kTC][kChStride] | int4 s_desc[kChunk][2] | float4 s_wy[kChunk][kTH]
+    __shared__ int s_work[2][8];                   // ticket decode: g, list start, pieces (-1: done), px0, py0, img
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int4* s_desc = reinterpret_cast<int4*>(s_tile + kTileTileFloats);
+    float4* s_wy = reinterpret_cast<float4*>(s_desc + 2 * kChunk);
+
+    auto fetch = [&](int* wk) {                    // one thread: next ticket -> decoded work item
+        const int ngroups = C / kTC;
+        const int work = atomicAdd(ctl + kCtlTicket, 1);
+        int n_pieces = -1;
+        if (work < ctl[kCtlItems] * ngroups) {
+            const int4 it = items[work / ngroups];
+            const int t = it.x;
+            const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
+            const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
+            n_pieces = max(min(it.z, tile_off[t] + tile_fill[t] - it.y), 0);
+            wk[0] = work % ngroups; wk[1] = it.y;
+            wk[3] = tx * kTW; wk[4] = ty * kTH; wk[5] = img;
+        }
+        wk[2] = n_pieces;
+    };
+    constexpr int kFetchTid = kTileThreads - 32;   // lane 0 of the last warp (it gets the fewest units)
+    if (tid == kFetchTid) fetch(s_work[0]);
+    __syncthreads();
+    for (int buf = 0;; buf ^= 1) {
+        const int n_pieces = s_work[buf][2];
+        if (n_pieces < 0) break;
+        const int g = s_work[buf][0], list0 = s_work[buf][1];
+        const int px0 = s_work[buf][3], py0 = s_work[buf][4], img = s_work[buf][5];
+
+        // ---- piece descriptors and row weights of this item -> shared (contiguous in list order) ----
+        if (tid < 2 * n_pieces) s_desc[tid] = __ldg(list + 2 * (size_t)list0 + tid);
+        for (int i = tid; i < n_pieces * kTH; i += kTileThreads) s_wy[i] = __ldg(list_wy + (size_t)list0 * kTH + i);
+        // ---- stage the tile: each warp brings in kTC/kTileWarps channels, ReLU on the way in ----
         {
-            const float* src = feat + ((size_t)img * C + (size_t)g * kTC) * H * W;
-            const int gx = px0 + lane;
-            const bool xin = gx < W;
-            constexpr int kRows = kTC * kTH, kUnroll = 8;
-            for (int r0 = warp * kUnroll; r0 < kRows; r0 += kTileWarps * kUnroll) {
-                float v[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int r = r0 + u, c = r / kTH, y = r - c * kTH;
-                    const int gy = py0 + y;
-                    v[u] = (xin && gy < H) ? __ldg(src + ((size_t)c * H + gy) * W + gx) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int r = r0 + u, c = r / kTH, y = r - c * kTH;
-                    s_tile[c * kChStride + y * kTW + lane] = relu ? fmaxf(v[u], 0.f) : v[u];
-                }
-            }
+            const int gx = min(px0 + lane, W - 1);
+            const int rows_valid = min(kTH, H - py0);
+            const int c = warp * (kTC / kTileWarps);
+            const size_t plane = (size_t)H * W;
+            const float* p = feat + (((size_t)img * C + (size_t)g * kTC + c) * H + py0) * W + gx;
+            float* d = s_tile + c * kChStride + lane;
+            if (rows_valid == kTH) stage_channels<true>(p, plane, d, W, rows_valid, relu);
+            else stage_channels<false>(p, plane, d, W, rows_valid, relu);
         }
         __syncthreads();
+        if (tid == kFetchTid) fetch(s_work[buf ^ 1]);   // next ticket, overlapped with the compute below
 
         // ---- units: (piece, bin column pw), lane = channel ----
-        for (int u = warp; u < n_pieces * RR_POOL; u += kTileWarps) {
+        const int n_units = n_pieces * RR_POOL;
+        const float* wxp = list_wx + (size_t)list0 * RR_POOL * kTW + lane;     // unit u: wxp[u * kTW]
+        float wxv = warp < n_units ? __ldg(wxp + warp * kTW) : 0.f;
+        for (int u = warp; u < n_units; u += kTileWarps) {
             const int piece = u / RR_POOL, pw = u - piece * RR_POOL;
-            const int roi = __ldg(list + it.y + piece);
-            const RoiPrep* rp = prep + roi;
-            const int x_lo = rp->x_lo, y_lo = rp->y_lo;
-            const int c0 = max(x_lo + rp->cx_lo[pw], px0), c1 = min(x_lo + rp->cx_hi[pw], px0 + kTW - 1);
-            const int r0 = max(y_lo, py0), r1 = min(y_lo + rp->ny - 1, py0 + kTH - 1);
-            const int ncols = c1 - c0 + 1, nrows = r1 - r0 + 1;
-            const int slot = rp->slot_base + (ty - rp->ty0) * rp->ntx + (tx - rp->tx0);
+            const int4 d0 = s_desc[2 * piece], d1 = s_desc[2 * piece + 1];
+            const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
+            const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
+            const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
+            const float wcur = wxv;
+            if (u + kTileWarps < n_units) wxv = __ldg(wxp + (u + kTileWarps) * kTW);   // prefetch the next unit's
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            if (ncols > 0 && nrows > 0) {
-                const float wxv = lane < ncols ? __ldg(wx + (size_t)roi * (RR_POOL * kMaxWinT) + pw * kMaxWinT + (c0 - x_lo) + lane) : 0.f;
-                float4 wyv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < nrows) wyv = __ldg(wy4 + (size_t)roi * kMaxWinT + (r0 - y_lo) + lane);
-                const float* fb = s_tile + lane * kChStride + (r0 - py0) * kTW + (c0 - px0);
-                for (int cc = 0; cc < ncols; cc += 8) {
-                    float w[8];
+            const float* fb = s_tile + lane * kChStride + r0 * kTW + c0;
+            const float4* wyp = s_wy + piece * kTH;
+            for (int cc = 0; cc < ncols; cc += 8) {
+                float w[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = __shfl_sync(0xffffffffu, wxv, (cc + j) & 31);
-                    const int nj = ncols - cc;
-                    const float* fr = fb + cc;
-                    for (int y = 0; y < nrows; ++y, fr += kTW) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < nj) s = fmaf(w[j], fr[j], s);
-                        a0 = fmaf(__shfl_sync(0xffffffffu, wyv.x, y), s, a0);
-                        a1 = fmaf(__shfl_sync(0xffffffffu, wyv.y, y), s, a1);
-                        a2 = fmaf(__shfl_sync(0xffffffffu, wyv.z, y), s, a2);
-                    }
+                for (int j = 0; j < 8; ++j) w[j] = __shfl_sync(0xffffffffu, wcur, (cc + j) & 31);
+                const float* fr = fb + cc;
+                switch (min(ncols - cc, 8)) {
+                    case 1: unit_rows<1>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 2: unit_rows<2>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 3: unit_rows<3>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 4: unit_rows<4>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 5: unit_rows<5>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 6: unit_rows<6>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    case 7: unit_rows<7>(fr, wyp, nrows, w, a0, a1, a2); break;
+                    default: unit_rows<8>(fr, wyp, nrows, w, a0, a1, a2); break;
                 }
             }
-            float* po = partial + ((size_t)slot * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
+            float* po = partial + ((size_t)d0.y * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
             po[0] = a0;
             po[(size_t)RR_POOL * C] = a1;
             po[(size_t)2 * RR_POOL * C] = a2;
         }
+        __syncthreads();                           // shared tables free again; s_work[buf ^ 1] is visible
     }
 }
 
 // TILE path, step 5: out[n,c,bin] = (sum over the RoI's pieces, fixed order) / count.
 __global__ void __launch_bounds__(256)
-roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_rois_dev, int n_cap, int C,
+roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
+                   const int* __restrict__ n_rois_dev, int n_cap, int C,
                    const float* __restrict__ partial, float* __restrict__ out) {
-    extern __shared__ float s_out[];               // [C][9] (+1 pad per channel row of 9 is not needed: stride 9 is odd)
+    extern __shared__ float s_out[];               // [C][9]
     const int n = blockIdx.x;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     if (n >= live) return;
+    const int sb = slot[n];
+    if (sb < 0) return;                            // written by roi_direct_kernel
     const RoiPrep rp = prep[n];
-    if (rp.flags == kFlagDirect) return;           // written by roi_direct_kernel
     const int pieces = rp.flags == kFlagTile ? rp.ntx * rp.nty : 0;
     constexpr int kBins = RR_POOL * RR_POOL;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -546,7 +654,7 @@ roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_r
 #pragma unroll
         for (int q = 0; q < kBins; ++q) acc[q] = 0.f;
         for (int p = 0; p < pieces; ++p) {
-            const float* src = partial + (size_t)(rp.slot_base + p) * kBins * C + c;
+            const float* src = partial + (size_t)(sb + p) * kBins * C + c;
 #pragma unroll
             for (int q = 0; q < kBins; ++q) acc[q] += __ldg(src + (size_t)q * C);
         }
@@ -562,10 +670,10 @@ roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ n_r
 // host side
 // --------------------------------------------------------------------------------------------
 struct RoiWs {
-    RoiPrep* prep; float* wx; float4* wy4;
+    RoiPrep* prep; int* meta; int* slot; float* wx; float4* wy4;
     int* zeroed; size_t zeroed_bytes;              // tile_count | tile_fill | ctl  (one memset)
     int* tile_count; int* tile_fill; int* ctl;
-    int* tile_off; int4* items; int* direct_list; int* list; float* partial;
+    int* tile_off; int4* items; int* direct_list; int4* list; float* list_wx; float4* list_wy; float* partial;
     int n_tiles, slot_cap; TileDims td;
     size_t bytes;
 };
@@ -579,6 +687,8 @@ static RoiWs carve_roi(void* ws, int n_cap, int B, int C, int H, int W) {
     w.slot_cap = kSlotsPerRoi * n_cap + w.n_tiles;
     Carver cv(ws);
     w.prep = cv.take<RoiPrep>(n_cap);
+    w.meta = cv.take<int>((size_t)n_cap + 4);
+    w.slot = cv.take<int>((size_t)n_cap + 4);
     w.wx = cv.take<float>((size_t)n_cap * RR_POOL * kMaxWinT);
     w.wy4 = cv.take<float4>((size_t)n_cap * kMaxWinT);
     w.zeroed = cv.take<int>((size_t)2 * w.n_tiles + kCtlWords);
@@ -587,7 +697,9 @@ static RoiWs carve_roi(void* ws, int n_cap, int B, int C, int H, int W) {
     w.tile_off = cv.take<int>((size_t)w.n_tiles + 1);
     w.items = cv.take<int4>((size_t)w.n_tiles + (size_t)n_cap * kMaxPieces / kChunk + 1);
     w.direct_list = cv.take<int>(n_cap);
-    w.list = cv.take<int>((size_t)n_cap * kMaxPieces);
+    w.list = cv.take<int4>((size_t)2 * n_cap * kMaxPieces);
+    w.list_wx = cv.take<float>((size_t)n_cap * kMaxPieces * RR_POOL * kTW);
+    w.list_wy = cv.take<float4>((size_t)n_cap * kMaxPieces * kTH);
     w.partial = cv.take<float>((size_t)w.slot_cap * RR_POOL * RR_POOL * C);
     w.bytes = cv.off;
     return w;
@@ -605,27 +717,27 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
     if (rc) return rc;
     const int force_direct = algo == 1;
     roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
-                                                    w.prep, w.wx, w.wy4, w.tile_count);
+                                                    w.prep, w.meta, w.wx, w.wy4, w.tile_count);
     RR_LAUNCHED(rc);
-    roi_scan_kernel<<<1, 1024, 0, st>>>(w.prep, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
-                                        w.tile_off, w.items, w.direct_list, w.ctl);
+    roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
+                                                w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
     RR_LAUNCHED(rc);
     if (!force_direct && C % kTC == 0) {
-        roi_fill_kernel<<<(n_cap + 255) / 256, 256, 0, st>>>(w.prep, n_rois_dev, n_cap, w.td, w.tile_off,
-                                                            w.tile_fill, w.list);
+        roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
+                                                        w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
         RR_LAUNCHED(rc);
         static bool attr_set = false;
         if (!attr_set) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
             attr_set = true;
         }
-        roi_tile_kernel<<<2 * kSMs, kTileThreads, kTileSmem, st>>>(feat, w.prep, w.wx, w.wy4, w.list, w.items,
+        roi_tile_kernel<<<2 * kSMs, kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
                                                                   w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
                                                                   w.td, w.partial);
         RR_LAUNCHED(rc);
     }
     roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
-        w.prep, n_rois_dev, n_cap, C, w.partial, out);
+        w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
     RR_LAUNCHED(rc);
     roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * kSMs, kRoiThreads, 0, st>>>(
         feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
