@@ -44,6 +44,7 @@ extern "C" {
 #define RR_HEAD_CH         256   /* re-regression head input channels (fixed by the reference) */
 #define RR_HEAD_MID        64
 #define RR_POOL            3     /* RoIAlign output is 3x3 (models/rrnet.py:51) */
+#define RR_DECODE_RAW_SCORES 0x100
 
 int         rr_version(void);
 const char* rr_error_string(int code);
@@ -56,7 +57,9 @@ uint64_t    rr_launch_count(void);
  *   hm  [B,C,H,W] heat-map LOGITS (sigmoid is applied inside, :119)
  *   wh  [B,2,H,W] (ch0 = w, ch1 = h), off [B,2,H,W] (ch0 = x, ch1 = y)
  *   pool: 0 = RRNet's path (no peak suppression); 3 = 3x3 max-pool peak keep
- *         (operators/centernet_operator.py:204-210 semantics)
+ *         (operators/centernet_operator.py:204-210 semantics).  OR-ing RR_DECODE_RAW_SCORES
+ *         into it makes the call a plain RRNet._topk (models/rrnet.py:93-109): hm then holds
+ *         scores (no sigmoid is applied) and wh / off may be NULL (x1=x2=x, y1=y2=y).
  *   out_dets [B,K,6] = x1,y1,x2,y2,score,cls  sorted by score descending (ties: flat index asc)
  *   out_inds [B,K]   = y*W+x (int64, as the reference's `inds`), may be NULL
  * One global top-K over C*H*W per image == the reference's two-stage top-K on tie-free input.

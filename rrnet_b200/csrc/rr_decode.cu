@@ -323,7 +323,7 @@ __device__ void bitonic_sort_desc(unsigned long long* s_e, int P) {
 
 __global__ void __launch_bounds__(kSelectThreads)
 decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
-                     const float* __restrict__ off, int C, int H, int W, int K, int pool,
+                     const float* __restrict__ off, int C, int H, int W, int K, int pool, int raw,
                      const unsigned int* __restrict__ count, const unsigned long long* __restrict__ cand,
                      float* __restrict__ out_dets, long long* __restrict__ out_inds) {
     extern __shared__ unsigned long long s_e[];          // [P], P = pow2 >= candidates
@@ -347,8 +347,8 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
     __syncthreads();
     bitonic_sort_desc(s_e, P);
 
-    const float* whb = wh + (size_t)b * 2 * HW;
-    const float* ofb = off + (size_t)b * 2 * HW;
+    const float* whb = wh ? wh + (size_t)b * 2 * HW : nullptr;
+    const float* ofb = off ? off + (size_t)b * 2 * HW : nullptr;
     for (int k = tid; k < K; k += blockDim.x) {
         const unsigned long long e = s_e[k];
         const unsigned key = (unsigned)(e >> 32);
@@ -356,10 +356,11 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
         const int cls = flat / HW, ind = flat - cls * HW;
         const int yi = ind / W, xi = ind - yi * W;                  // models/rrnet.py:99-100
         const float logit = key2f(key);
-        const float score = (logit == -CUDART_INF_F) ? 0.0f : sigmoid_f32(logit);   // :119
-        const float xs = __fadd_rn((float)xi, __ldg(ofb + ind));         // :126
-        const float ys = __fadd_rn((float)yi, __ldg(ofb + HW + ind));    // :127
-        float w = __ldg(whb + ind), h = __ldg(whb + HW + ind);
+        // raw: the map already holds scores (RRNet._topk on its own, :93-109); a pooled-out entry is heat*0
+        const float score = (logit == -CUDART_INF_F) ? 0.0f : (raw ? logit : sigmoid_f32(logit));   // :119
+        const float xs = ofb ? __fadd_rn((float)xi, __ldg(ofb + ind)) : (float)xi;         // :126
+        const float ys = ofb ? __fadd_rn((float)yi, __ldg(ofb + HW + ind)) : (float)yi;    // :127
+        float w = whb ? __ldg(whb + ind) : 0.f, h = whb ? __ldg(whb + HW + ind) : 0.f;
         w = (w < 0.0f) ? 0.0f : w;                                   // :128 clamp(min=0), NaN passes
         h = (h < 0.0f) ? 0.0f : h;
         const float px = __fsub_rn(xs, __fmul_rn(w, 0.5f));          // :133 (w/2 is exact)
@@ -375,8 +376,9 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
 }
 
 int decode_launch(const float* hm, const float* wh, const float* off, int B, int C, int H, int W,
-                  int K, int pool, float* out_dets, int64_t* out_inds, void* ws, cudaStream_t st) {
+                  int K, int mode, float* out_dets, int64_t* out_inds, void* ws, cudaStream_t st) {
     int rc = 0;
+    const int pool = mode & 0xff, raw = (mode & RR_DECODE_RAW_SCORES) ? 1 : 0;
     DecodeWs w = carve_decode(ws, B);
     const int N = C * H * W;
     decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
@@ -394,7 +396,7 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
         RR_CUDA(cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
         attr_set = true;
     }
-    decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, w.count, w.cand,
+    decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
                                                          out_dets, (long long*)out_inds);
     RR_LAUNCHED(rc);
     return rc;
@@ -416,9 +418,11 @@ RR_API int rr_decode_topk(const float* hm, const float* wh, const float* off,
                           int B, int C, int H, int W, int K, int pool,
                           float* out_dets, int64_t* out_inds,
                           void* ws, size_t ws_bytes, void* stream) {
-    if (!hm || !wh || !off || !out_dets || !ws) return RR_E_BADARG;
+    if (!hm || !out_dets || !ws) return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
-    if (pool != 0 && pool != 3) return RR_E_BADARG;
+    const int pl = pool & ~RR_DECODE_RAW_SCORES;
+    if (pl != 0 && pl != 3) return RR_E_BADARG;
+    if (!(pool & RR_DECODE_RAW_SCORES) && (!wh || !off)) return RR_E_BADARG;   // wh/off optional only for plain top-K
     if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
     if (K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;   // torch.topk raises (:96)
     if (ws_bytes < decode_ws_bytes(B) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;

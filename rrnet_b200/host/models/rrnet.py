@@ -1,0 +1,208 @@
+"""models/rrnet.py -- RRNet with the post-backbone path on the sm_100a kernels.
+
+Same attributes (num_stacks, num_classes, nms_type, nms_per_class, backbone, hm, wh, offset_reg,
+head_detector), same methods and return types as the reference class (models/rrnet.py:11-157).
+The backbone and the three stage-1 convolution heads are outside this path (cuDNN): they are taken
+from the reference when it is importable (utils.model_tools.get_backbone, detectors.centernet_detector)
+or passed in as modules."""
+import torch
+import torch.nn as nn
+
+from rrnet_b200 import ops
+from ..detectors.fasterrcnn_detector import FasterRCNNDetector
+from ..ext.nms.nms_wrapper import soft_nms
+
+
+def _reference_stage1(cfg):
+    try:
+        from utils.model_tools import get_backbone                       # reference modules (sys.path)
+        from detectors.centernet_detector import CenterNetDetector, CenterNetWHDetector
+    except ImportError as e:
+        raise ImportError("RRNet needs backbone/hm/wh/offset_reg modules: pass them in, or put the reference "
+                          "repo on sys.path so its backbones/ and detectors/ can be imported (%s)" % e)
+    ns = cfg.Model.num_stacks
+    return (get_backbone(cfg.Model.backbone, num_stacks=ns),
+            CenterNetDetector(planes=cfg.num_classes, num_stacks=ns, hm=True),
+            CenterNetWHDetector(planes=1, num_stacks=ns),
+            CenterNetDetector(planes=2, num_stacks=ns))
+
+
+class RRNet(nn.Module):
+    def __init__(self, cfg, backbone=None, hm=None, wh=None, offset_reg=None):
+        super(RRNet, self).__init__()
+        self.num_stacks = cfg.Model.num_stacks
+        self.num_classes = cfg.num_classes
+        self.nms_type = cfg.Model.nms_type_for_stage1
+        self.nms_per_class = cfg.Model.nms_per_class_for_stage1
+        if backbone is None or hm is None or wh is None or offset_reg is None:
+            backbone, hm, wh, offset_reg = _reference_stage1(cfg)
+        self.backbone = backbone
+        self.hm = hm
+        self.wh = wh
+        self.offset_reg = offset_reg
+        self.head_detector = FasterRCNNDetector()
+
+    # ------------------------------------------------------------------ models/rrnet.py:25-54
+    def forward(self, x, k=1500):
+        pre_feat = self.backbone(x)
+        hms, whs, offsets = self.forward_stage1(pre_feat)
+        feat = pre_feat[-1]
+        fused = (not self.training) and not torch.is_grad_enabled() and self.nms_type != 'soft_nms' \
+            and self.nms_per_class and feat.size(1) == 256
+        if fused:
+            # decode -> per-class NMS -> RoIAlign(+ReLU) -> head in one C-ABI call, one host sync for N
+            B, C, H, W = hms[-1].shape
+            path = ops.EvalPath(B, C, H, W, k, self.head_detector.folded(), device=feat.device)
+            path.forward(hms[-1], whs[-1], offsets[-1], feat)
+            r = path.results()
+            return hms, whs, offsets, r["reg"], r["bxyxy"], r["scores"], r["clses"]
+        bboxs = self.transform_bbox(hms[-1], whs[-1], offsets[-1], k)     # (bs, k, 6)
+        bxyxys, scores, clses = [], [], []
+        for b_idx in range(bboxs.size(0)):
+            bbox = self.nms(bboxs[b_idx])
+            xyxy = bbox[:, :4]
+            scores.append(bbox[:, 4])
+            clses.append(bbox[:, 5])
+            batch_idx = torch.ones((xyxy.size(0), 1), device=xyxy.device) * b_idx
+            bxyxys.append(torch.cat((batch_idx, xyxy), dim=1))
+        bxyxys = torch.cat(bxyxys, dim=0)
+        scores = torch.cat(scores, dim=0)
+        clses = torch.cat(clses, dim=0)
+        roi_feat = _RoIAlignReLU.apply(feat, bxyxys)
+        stage2_reg = self.forward_stage2(roi_feat)
+        return hms, whs, offsets, stage2_reg, bxyxys, scores, clses
+
+    # ------------------------------------------------------------------ models/rrnet.py:56-80
+    def nms(self, bbox):
+        """bbox [K,6] (x1,y1,x2,y2,score,cls) -> kept rows: classes ascending, score descending inside.
+        When bbox carries gradients (training: criterion back-propagates through the kept boxes,
+        rrnet_operator.py:82-83) the rows are gathered from bbox by index so autograd keeps working."""
+        device = bbox.device
+        if bbox.requires_grad and torch.is_grad_enabled() and self.nms_type != 'soft_nms':
+            d = bbox.detach()
+            if self.nms_per_class:
+                order = torch.sort(d[:, 5], stable=True).indices
+                cls_u, counts = torch.unique_consecutive(d[order, 5], return_counts=True)
+                seg = torch.zeros(cls_u.numel() + 1, dtype=torch.int32, device=device)
+                seg[1:] = torch.cumsum(counts, 0).int()
+            else:
+                order = torch.arange(d.size(0), device=device)
+                seg = torch.tensor([0, d.size(0)], dtype=torch.int32, device=device)
+            ds = d[order]
+            keep_idx, keep_cnt = ops.nms_batched(ds[:, :4].contiguous(), ds[:, 4].contiguous(), seg, 0.7)
+            seg_h, cnt_h = seg.tolist(), keep_cnt.tolist()
+            rows = torch.cat([keep_idx[seg_h[s]: seg_h[s] + c] for s, c in enumerate(cnt_h)]).long()
+            return bbox[order[rows]]
+        if self.nms_type == 'soft_nms':
+            if self.nms_per_class:
+                keep = [torch.from_numpy(soft_nms(bbox[bbox[:, 5] == c].detach().cpu().numpy(), Nt=0.7,
+                                                  threshold=0.1, method=2)).to(device)
+                        for c in bbox[:, 5].unique()]
+                return torch.cat(keep)
+            return torch.from_numpy(soft_nms(bbox.detach().cpu().numpy(), Nt=0.7, threshold=0.1, method=2)).to(device)
+        if self.nms_per_class:
+            bx, sc, cl, counts = ops.stage1_nms(bbox.detach().unsqueeze(0).contiguous(), self.num_classes, 0.7)
+            n = int(counts[0].item())
+            return torch.cat((bx[:n, 1:], sc[:n, None], cl[:n, None]), dim=1)
+        keep_idx = ops.nms(bbox[:, :4].contiguous(), bbox[:, 4].contiguous(), 0.7)
+        return bbox[keep_idx]
+
+    # ------------------------------------------------------------------ models/rrnet.py:83-115
+    @staticmethod
+    def _gather_feat(feat, ind, mask=None):
+        dim = feat.size(2)
+        ind = ind.unsqueeze(2).expand(ind.size(0), ind.size(1), dim)
+        feat = feat.gather(1, ind)
+        if mask is not None:
+            mask = mask.unsqueeze(2).expand_as(feat)
+            feat = feat[mask]
+            feat = feat.view(-1, dim)
+        return feat
+
+    def _topk(self, scores, k=1500):
+        """scores [B,C,H,W] (already sigmoid-ed) -> topk_score [B,k], topk_inds [B,k] int64 (y*W+x),
+        topk_clses [B,k] int32, topk_ys, topk_xs [B,k] float: one global top-k per image (== the
+        reference's two-stage top-k; ties ordered by flat index)."""
+        dets, inds = ops.decode_topk(scores, None, None, k, raw_scores=True)
+        return dets[..., 4], inds, dets[..., 5].int(), dets[..., 1], dets[..., 0]
+
+    def _transpose_and_gather_feat(self, feat, ind):
+        """feat [B,ch,H,W], ind [B,K] -> [B,K,ch]; gathers from the NCHW map directly (the reference
+        permutes the whole map to NHWC first)."""
+        b, ch = feat.size(0), feat.size(1)
+        idx = ind.view(b, 1, -1).expand(b, ch, -1)
+        return feat.reshape(b, ch, -1).gather(2, idx).permute(0, 2, 1).contiguous()
+
+    # ------------------------------------------------------------------ models/rrnet.py:117-138
+    def transform_bbox(self, hm, wh, offset, k=250):
+        """hm LOGITS [B,C,H,W], wh, offset [B,2,H,W] -> [B,k,6] = x1,y1,x2,y2,score,cls (stride-4 units)."""
+        if torch.is_grad_enabled() and (wh.requires_grad or offset.requires_grad or hm.requires_grad):
+            return _DecodeFn.apply(hm, wh, offset, k)
+        dets, _ = ops.decode_topk(hm, wh, offset, k, want_inds=False)
+        return dets
+
+    # ------------------------------------------------------------------ models/rrnet.py:140-157
+    def forward_stage1(self, feats):
+        hms, whs, offsets = [], [], []
+        for i in range(self.num_stacks):
+            feat = torch.relu(feats[i])
+            hms.append(self.hm(feat, i))
+            whs.append(self.wh(feat, i))
+            offsets.append(self.offset_reg(feat, i))
+        return hms, whs, offsets
+
+    def forward_stage2(self, feats,):
+        return self.head_detector(feats)
+
+
+class _RoIAlignReLU(torch.autograd.Function):
+    """roi_align(relu(feat), rois, (3,3)) with the fused kernel; the backward (training only) scatters
+    through torchvision's roi_align backward on relu(feat) -- RoIAlign backward is outside this round's
+    kernels (SURVEY 8b lists it as part of rr_roi_align's `_backward`, still to come)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois):
+        ctx.save_for_backward(feat, rois)
+        return ops.roi_align(feat.detach(), rois.detach(), relu=True)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import torchvision
+        feat, rois = ctx.saved_tensors
+        with torch.enable_grad():
+            f = feat.detach().requires_grad_(True)
+            out = torchvision.ops.roi_align(torch.relu(f), rois, (3, 3))
+            (g,) = torch.autograd.grad(out, f, grad_out)
+        return g, None
+
+
+class _DecodeFn(torch.autograd.Function):
+    """transform_bbox with gradients to wh / offset / hm (the reference's top-k + gathers are
+    differentiable and criterion back-propagates through the stage-1 boxes).  Forward is the decode
+    kernel; backward is a K-point scatter in torch."""
+
+    @staticmethod
+    def forward(ctx, hm, wh, off, k):
+        dets, inds = ops.decode_topk(hm.detach(), wh.detach(), off.detach(), k)
+        ctx.save_for_backward(dets, inds, wh)
+        ctx.hm_shape = hm.shape
+        ctx.mark_non_differentiable(inds)
+        return dets
+
+    @staticmethod
+    def backward(ctx, g):
+        dets, inds, wh = ctx.saved_tensors
+        B, C, H, W = ctx.hm_shape
+        g = g.contiguous()
+        wh_flat = wh.detach().reshape(B, 2, H * W)
+        w_raw = wh_flat.gather(2, inds[:, None, :].expand(B, 2, -1))             # [B,2,K]
+        passes = (w_raw >= 0).float()                                             # clamp(min=0) backward
+        g_off = torch.stack((g[..., 0] + g[..., 2], g[..., 1] + g[..., 3]), dim=1)            # [B,2,K]
+        g_wh = torch.stack((0.5 * (g[..., 2] - g[..., 0]), 0.5 * (g[..., 3] - g[..., 1])), dim=1) * passes
+        idx = inds[:, None, :].expand(B, 2, -1)
+        d_off = torch.zeros(B, 2, H * W, device=g.device).scatter_add_(2, idx, g_off).view(B, 2, H, W)
+        d_wh = torch.zeros(B, 2, H * W, device=g.device).scatter_add_(2, idx, g_wh).view(B, 2, H, W)
+        s = dets[..., 4]
+        flat = dets[..., 5].long() * (H * W) + inds
+        d_hm = torch.zeros(B, C * H * W, device=g.device).scatter_add_(1, flat, g[..., 4] * s * (1 - s)).view(B, C, H, W)
+        return d_hm, d_wh, d_off, None

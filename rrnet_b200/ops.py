@@ -46,12 +46,22 @@ def _ws(nbytes, device):
 
 
 # --------------------------------------------------------------------------------- decode
-def decode_topk(hm, wh, off, K, pool=0, want_inds=True):
-    """models/rrnet.py:117-138 on logits.  -> dets [B,K,6] (x1,y1,x2,y2,score,cls), inds [B,K] int64."""
-    hm, wh, off = _f32(hm, "hm", 4), _f32(wh, "wh", 4), _f32(off, "off", 4)
+DECODE_RAW_SCORES = 0x100
+
+
+def decode_topk(hm, wh, off, K, pool=0, want_inds=True, raw_scores=False):
+    """models/rrnet.py:117-138 on logits.  -> dets [B,K,6] (x1,y1,x2,y2,score,cls), inds [B,K] int64.
+    raw_scores=True: hm already holds scores (RRNet._topk alone, :93-109); wh/off may then be None."""
+    hm = _f32(hm, "hm", 4)
     B, C, H, W = hm.shape
-    if tuple(wh.shape) != (B, 2, H, W) or tuple(off.shape) != (B, 2, H, W):
-        raise RRNetB200Error("wh/off must be [B,2,H,W] matching hm")
+    if raw_scores and wh is None and off is None:
+        pool = int(pool) | DECODE_RAW_SCORES
+    else:
+        wh, off = _f32(wh, "wh", 4), _f32(off, "off", 4)
+        if tuple(wh.shape) != (B, 2, H, W) or tuple(off.shape) != (B, 2, H, W):
+            raise RRNetB200Error("wh/off must be [B,2,H,W] matching hm")
+        if raw_scores:
+            pool = int(pool) | DECODE_RAW_SCORES
     L = _lib.lib()
     dets = torch.empty(B, K, 6, dtype=torch.float32, device=hm.device)
     inds = torch.empty(B, K, dtype=torch.int64, device=hm.device) if want_inds else None

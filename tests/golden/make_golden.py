@@ -211,6 +211,45 @@ def gold_focal(ref):
     save("focal", **res)
 
 
+def gold_criterion(ref):
+    """RRNetOperator.criterion (rrnet_operator.py:42-84) on the pipeline inputs: the four losses and the
+    gradient of (hm + 0.1 wh + off + s2) w.r.t. the stage-1 maps of stack 0."""
+    B, C, H, W, K = 2, 10, 48, 64, 200
+    seed = 31
+    x = synth.eval_inputs(B, H, W, K, seed)
+    hp = synth.head_params(seed)
+    hm = x["hm"].clone().requires_grad_(True)
+    wh = x["wh"].clone().requires_grad_(True)
+    off = x["off"].clone().requires_grad_(True)
+    net = ref.make_net((hm, wh, off))
+    net.load_state_dict(synth.head_state_dict(hp), strict=False)
+    annos = synth.train_annos(B, H * 4, W * 4, 81, n_range=(10, 25))
+    # make a few ground-truth boxes coincide with stage-1 boxes so that the stage-2 loss has positives
+    with torch.no_grad():
+        dets = net.transform_bbox(x["hm"], x["wh"], x["off"], K)
+    for b in range(B):
+        for j in range(4):
+            d = dets[b, 3 * j]
+            x1, y1, x2, y2 = [float(v) * 4 for v in d[:4]]
+            if x2 - x1 > 4 and y2 - y1 > 4 and x1 > 2 and y1 > 2 and x2 * 1.05 < W * 4 - 2 and y2 < H * 4 - 2:
+                annos[b][j, :4] = torch.tensor([x1 + 0.5, y1 - 0.5, (x2 - x1) * 1.05, (y2 - y1) * 0.97])
+    from datasets.drones_det import DronesDET
+    batch = []
+    for b, a in enumerate(annos):
+        img, an, g_hm, g_wh, g_ind, g_off, g_msk = ref.TF.to_heatmap((torch.zeros(3, H * 4, W * 4), a.clone()))
+        batch.append((img, an, g_hm, g_wh, g_ind, g_off, g_msk, "img%d" % b))
+    imgs, c_annos, g_hms, g_whs, g_inds, g_offs, g_msks, _ = DronesDET.collate_fn_ctnet(batch)
+    outs = net([x["feat"], x["feat"]], k=K)
+    targets = (g_hms, g_whs, g_inds, g_offs, g_msks, c_annos.clone())
+    hm_l, wh_l, off_l, s2_l = ref.O.RRNetOperator.criterion(ref.fake_op, outs, targets)
+    total = hm_l + 0.1 * wh_l + off_l + s2_l
+    total.backward()
+    save("criterion", shape=np.array([B, C, H, W, K]), seed=seed, annos=c_annos, n_obj=np.array([a.shape[0] for a in annos]),
+         gt_hms=g_hms, gt_whs=g_whs, gt_inds=g_inds, gt_offs=g_offs, gt_masks=g_msks,
+         losses=np.array([float(hm_l), float(wh_l), float(off_l), float(s2_l)], np.float64),
+         grad_hm=hm.grad, grad_wh=wh.grad, grad_off=off.grad)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -224,6 +263,7 @@ def main():
     gold_pipeline(ref)
     gold_render(ref)
     gold_focal(ref)
+    gold_criterion(ref)
 
 
 if __name__ == "__main__":

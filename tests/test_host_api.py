@@ -1,0 +1,246 @@
+"""The host-side mirror of the reference's Python interface (rrnet_b200.host) against the golden
+fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py) -- these tests read like
+calls into the reference's own modules.  GPU only (the mirror has no CPU path)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from rrnet_b200 import synth
+from tests.conftest import box_rel_err, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+NS = types.SimpleNamespace
+CFG = NS(num_classes=10, Train=NS(scale_factor=4),
+         Model=NS(num_stacks=2, backbone="hourglass", nms_type_for_stage1="nms", nms_per_class_for_stage1=True))
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rrnet_b200.host.models.rrnet import RRNet
+    from rrnet_b200.host.operators.rrnet_operator import RRNetOperator
+    from rrnet_b200.host.ext.nms import nms_wrapper
+    from rrnet_b200.host.ext.nms.nms import cpu_nms, gpu_nms, py_cpu_nms
+    from rrnet_b200.host.modules.loss.focalloss import FocalLossHM
+    from rrnet_b200.host.modules.loss.functional import focal_loss_for_hm
+    from rrnet_b200.host.datasets.transforms.transforms import ToHeatmap
+    return NS(RRNet=RRNet, RRNetOperator=RRNetOperator, nms_wrapper=nms_wrapper, cpu_nms=cpu_nms, gpu_nms=gpu_nms,
+              py_cpu_nms=py_cpu_nms, FocalLossHM=FocalLossHM, focal_loss_for_hm=focal_loss_for_hm, ToHeatmap=ToHeatmap)
+
+
+class _Identity(nn.Module):
+    def forward(self, feats):
+        return feats
+
+
+class _Fixed(nn.Module):
+    """Stands in for a stage-1 convolution head: returns a chosen map for every stack."""
+
+    def __init__(self, t):
+        super().__init__()
+        self.t = t
+
+    def forward(self, feat, i):
+        return self.t
+
+
+def make_net(host, hm, wh, off, seed):
+    net = host.RRNet(CFG, backbone=_Identity(), hm=_Fixed(hm), wh=_Fixed(wh), offset_reg=_Fixed(off)).cuda().eval()
+    missing = net.load_state_dict({k: v.cuda() for k, v in synth.head_state_dict(synth.head_params(seed)).items()},
+                                  strict=False)
+    assert not missing.unexpected_keys
+    return net
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ ext/nms
+def test_nms_wrapper_known_answers(host):
+    """ext/nms/nms_wrapper.py:37-55: nms(thresh=0.3) -> rows [2,3]; soft_nms keeps all five."""
+    g = load_golden("nms")
+    anchor = g["known"].copy()
+    rows = host.nms_wrapper.nms(anchor, 0.3)
+    np.testing.assert_array_equal(rows, anchor[[2, 3]])
+    np.testing.assert_array_equal(host.nms_wrapper.nms(anchor, 0.3, gpu_id=None), anchor[g["known_cpu_nms"]])
+    assert host.nms_wrapper.nms(anchor[:0], 0.3) == []
+    assert host.gpu_nms.gpu_nms(anchor, 0.3) == [2, 3]
+    assert host.cpu_nms.cpu_nms(anchor, 0.3) == g["known_cpu_nms"].tolist()
+    assert host.py_cpu_nms.py_cpu_nms(anchor, 0.3) == g["known_py_cpu_nms"].tolist()
+    soft = host.nms_wrapper.soft_nms(anchor.copy(), Nt=0.4, sigma=0.3)
+    assert soft.shape[0] == 5 and rel_err(soft, g["known_soft_rows"]) < TOL
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.7])
+def test_nms_entry_points_golden(host, thr):
+    g = load_golden("nms")
+    d = g["boxes"]
+    t = "%02d" % int(thr * 10)
+    assert host.cpu_nms.cpu_nms(d.copy(), thr) == g["cpu_" + t].tolist()
+    assert host.py_cpu_nms.py_cpu_nms(d.copy(), thr) == g["py_" + t].tolist()
+    assert host.gpu_nms.gpu_nms(d.copy(), thr) == g["py_" + t].tolist()        # same semantics as py_cpu_nms
+    np.testing.assert_array_equal(host.nms_wrapper.nms(d.copy(), thr), d[g["py_" + t]])
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_soft_nms_wrapper_golden(host, method):
+    g = load_golden("soft_nms")
+    d = g["boxes"].copy()
+    rows = host.nms_wrapper.soft_nms(d, sigma=0.5, Nt=0.7, threshold=0.1, method=method)
+    ref = g["rows_m%d" % method]
+    assert rows.shape == ref.shape
+    np.testing.assert_array_equal(rows[:, :4], ref[:, :4])                       # same survivors, same order
+    assert rel_err(rows[:, 4], ref[:, 4]) < TOL
+    # float64 input is converted to a temporary: the caller's array is untouched and its first rows come
+    # back (the reference's aliasing quirk, nms_wrapper.py:13-19)
+    d64 = g["boxes"].astype(np.float64)
+    rows64 = host.nms_wrapper.soft_nms(d64, sigma=0.5, Nt=0.7, threshold=0.1, method=method)
+    np.testing.assert_array_equal(rows64, g["boxes"].astype(np.float64)[: ref.shape[0]])
+
+
+def test_ext_nms_golden(host):
+    g = load_golden("soft_nms")
+    out = host.RRNetOperator._ext_nms(torch.from_numpy(g["ext_in"].copy()))
+    assert not out.is_cuda and tuple(out.shape) == g["ext_out"].shape
+    assert box_rel_err(npy(out), g["ext_out"]) < TOL
+    empty = torch.zeros(0, 6)
+    assert host.RRNetOperator._ext_nms(empty) is empty
+
+
+# ------------------------------------------------------------------ models/rrnet.py
+def test_topk_and_transform_bbox_golden(host):
+    g = load_golden("decode")
+    B, C, H, W, K = g["shape"].tolist()
+    seed = int(g["seed"])
+    hm = synth.heatmap_logits(B, C, H, W, K, seed).cuda()
+    wh, off = [t.cuda() for t in synth.wh_offset(B, H, W, seed)]
+    net = make_net(host, hm, wh, off, seed)
+    with torch.no_grad():
+        scores, inds, clses, ys, xs = net._topk(torch.sigmoid(hm), K)
+        dets = net.transform_bbox(hm, wh, off, K)
+    np.testing.assert_array_equal(npy(inds), g["inds"])
+    np.testing.assert_array_equal(npy(clses), g["clses"])
+    np.testing.assert_array_equal(npy(ys), g["ys"])
+    np.testing.assert_array_equal(npy(xs), g["xs"])
+    assert inds.dtype == torch.int64 and clses.dtype == torch.int32
+    assert rel_err(npy(scores), g["scores"]) < TOL                # the GPU's sigmoid differs from torch CPU's by an ulp
+    np.testing.assert_array_equal(npy(dets)[..., [0, 1, 2, 3, 5]], g["dets"][..., [0, 1, 2, 3, 5]])
+    assert rel_err(npy(dets)[..., 4], g["dets"][..., 4]) < TOL
+    # _transpose_and_gather_feat == the reference's permute+gather
+    feat = torch.randn(B, 3, H, W, device="cuda")
+    got = net._transpose_and_gather_feat(feat, inds)
+    ref = feat.permute(0, 2, 3, 1).reshape(B, H * W, 3).gather(1, inds[:, :, None].expand(B, K, 3))
+    assert torch.equal(got, ref)
+
+
+def test_forward_generate_bbox_ext_nms_golden(host):
+    """RRNet.forward (7-tuple) -> RRNetOperator.generate_bbox(outs, b) -> _ext_nms, as evaluation_process does."""
+    g = load_golden("pipeline")
+    B, C, H, W, K = g["shape"].tolist()
+    seed = int(g["seed"])
+    x = {k: v.cuda() for k, v in synth.eval_inputs(B, H, W, K, seed).items()}
+    net = make_net(host, x["hm"], x["wh"], x["off"], seed)
+    op = host.RRNetOperator(CFG, model=net)
+    with torch.no_grad():
+        outs = net([x["feat"], x["feat"]], k=K)
+    hms, whs, offs, s2_reg, bxyxy, scores, clses = outs
+    assert len(hms) == 2 and hms[0] is x["hm"]
+    np.testing.assert_array_equal(npy(bxyxy), g["bxyxy"])
+    np.testing.assert_array_equal(npy(clses), g["clses"])
+    assert rel_err(npy(scores), g["scores"]) < TOL
+    assert rel_err(npy(s2_reg), g["s2_reg"], floor=1.0) < TOL
+    for b in range(B):
+        s1, s2 = op.generate_bbox(outs, b)
+        assert rel_err(npy(s1), g["s1_b%d" % b]) < TOL
+        assert box_rel_err(npy(s2), g["s2_b%d" % b]) < TOL
+        final = op._ext_nms(s2)
+        assert tuple(final.shape) == g["final_b%d" % b].shape
+        assert box_rel_err(npy(final), g["final_b%d" % b]) < 2e-5
+    # the unfused path (per-image nms + roi_align + head through the class methods) gives the same rows
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False         # the PyTorch head (training graph) must run in fp32 to compare
+    try:
+        with torch.enable_grad():
+            x["wh"].requires_grad_(True)
+            outs2 = net([x["feat"], x["feat"]], k=K)
+            x["wh"].requires_grad_(False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    np.testing.assert_array_equal(npy(outs2[4]), g["bxyxy"])
+    assert rel_err(npy(outs2[3]), g["s2_reg"], floor=1.0) < TOL
+
+
+def test_nms_method_matches_oracle(host, oracle_mod):
+    B, C, H, W, K = 1, 10, 48, 64, 300
+    x = synth.eval_inputs(B, H, W, K, 17)
+    net = make_net(host, x["hm"].cuda(), x["wh"].cuda(), x["off"].cuda(), 17)
+    with torch.no_grad():
+        bbox = net.transform_bbox(x["hm"].cuda(), x["wh"].cuda(), x["off"].cuda(), K)[0]
+        kept = net.nms(bbox)
+    ref, _ = oracle_mod.stage1_nms(npy(bbox), C, 0.7)
+    np.testing.assert_array_equal(npy(kept), ref)
+
+
+# ------------------------------------------------------------------ loss / targets / criterion
+def test_focal_loss_hm_module_golden(host):
+    g = load_golden("focal")
+    z = torch.from_numpy(g["logits"]).cuda().requires_grad_(True)
+    gt = torch.from_numpy(g["gt"]).cuda()
+    loss = host.FocalLossHM.from_logits(z, gt)
+    (2.0 * loss).backward()                                        # upstream scale goes through autograd
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < TOL
+    assert rel_err(npy(z.grad) / 2.0, g["grad"], floor=1e-3) < TOL
+    # reference call form: FocalLossHM()(clamp(sigmoid(z)), gt)  (rrnet_operator.py:55-57)
+    p = torch.clamp(torch.sigmoid(torch.from_numpy(g["logits"]).cuda()), min=1e-4, max=1 - 1e-4)
+    loss_p = host.FocalLossHM()(p, gt)
+    assert abs(float(loss_p) - float(g["loss"])) / abs(float(g["loss"])) < 1e-4
+
+
+def test_to_heatmap_transform_demo_known_answer(host):
+    """datasets/transforms: ToHeatmap on the reference's demo annotation: 81 positives, sum 294.5373923947336."""
+    g = load_golden("render")
+    annos = torch.from_numpy(g["demo_annos"])
+    img, a, hm, wh, ind, off, msk = host.ToHeatmap(scale_factor=4, cls_num=10)((torch.zeros(3, 540, 960), annos))
+    assert tuple(hm.shape) == (10, 135, 240) and int((hm == 1).sum()) == 81
+    assert rel_err(npy(hm), g["demo_hm"], floor=1e-6) < 1e-6     # expf ulp; positives (== 1.0) are exact, checked above
+    assert abs(float(hm.double().sum()) - 294.5373923947336) < 1e-4
+    np.testing.assert_array_equal(npy(ind), g["demo_ind"])
+    assert rel_err(npy(wh), g["demo_wh"]) < TOL and rel_err(npy(off), g["demo_off"], floor=1e-3) < TOL
+    assert msk.dtype == torch.bool and np.array_equal(npy(msk).astype(np.float32), g["demo_mask"])
+
+
+def test_criterion_golden(host):
+    """RRNetOperator.criterion: four losses and the gradients w.r.t. the stage-1 maps vs the reference."""
+    g = load_golden("criterion")
+    B, C, H, W, K = g["shape"].tolist()
+    seed = int(g["seed"])
+    x = {k: v.cuda() for k, v in synth.eval_inputs(B, H, W, K, seed).items()}
+    hm = x["hm"].clone().requires_grad_(True)
+    wh = x["wh"].clone().requires_grad_(True)
+    off = x["off"].clone().requires_grad_(True)
+    net = make_net(host, hm, wh, off, seed)
+    op = host.RRNetOperator(CFG, model=net)
+    torch.backends.cudnn.allow_tf32 = False
+    outs = net([x["feat"], x["feat"]], k=K)
+    annos = torch.from_numpy(g["annos"]).cuda()
+    # targets rendered on the GPU from the padded annotations (replaces to_heatmap + collate_fn_ctnet)
+    from rrnet_b200.host.datasets.transforms.functional import to_heatmap_batch
+    n_obj = torch.from_numpy(g["n_obj"]).int().cuda()
+    gt_hms, gt_whs, gt_inds, gt_offs, gt_masks = to_heatmap_batch(annos, n_obj, H * 4, W * 4)
+    assert rel_err(npy(gt_hms), g["gt_hms"], floor=1e-6) < 1e-6
+    np.testing.assert_array_equal(npy(gt_hms) == 1, g["gt_hms"] == 1)
+    np.testing.assert_array_equal(npy(gt_inds), g["gt_inds"])
+    targets = (gt_hms, gt_whs, gt_inds, gt_offs, gt_masks, annos.clone())
+    hm_l, wh_l, off_l, s2_l = op.criterion(outs, targets)
+    got = np.array([float(hm_l), float(wh_l), float(off_l), float(s2_l)])
+    assert np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])) < 2e-5, (got, g["losses"])
+    (hm_l + 0.1 * wh_l + off_l + s2_l).backward()
+    assert rel_err(npy(hm.grad), g["grad_hm"], floor=1e-3) < 1e-4
+    assert rel_err(npy(wh.grad), g["grad_wh"], floor=1e-3) < 1e-4
+    assert rel_err(npy(off.grad), g["grad_off"], floor=1e-3) < 1e-4
