@@ -14,8 +14,11 @@ int decode_launch(const float*, const float*, const float*, int, int, int, int, 
 size_t decode_ws_bytes(int B);
 int stage1_nms_launch(const float*, int, int, int, double, float*, float*, float*, int32_t*, void*, cudaStream_t);
 size_t stage1_nms_ws_bytes(int B, int K, int C);
-int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, int, float*, void*,
+int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, int, int, float*, void*,
                      cudaStream_t);
+void roi_align_ws_views(void*, int, int, int, int, int, const float**, const int**, const int**, const float**);
+int head_forward_launch_partial(const float*, const float*, const int*, const int*, const float*, const int32_t*, int,
+                                const float*, float*, cudaStream_t);
 size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W);
 int head_forward_launch(const float*, const int32_t*, int, const float*, float*, cudaStream_t);
 int generate_bbox_launch(const float*, const float*, const float*, const float*, const int32_t*, int, float,
@@ -94,10 +97,19 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     if (rc) return rc;
     mark(2);
     const int32_t* n_dev = out_counts + B;
-    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, roi_algo, rf, w.roi, st);
+    // roi_feat requested: materialise it (combine) and feed the head from it; otherwise the head sums the
+    // tile-path partial slots itself and only direct-path RoIs go through the buffer
+    const int fused = roi_feat == nullptr && roi_algo == 0;
+    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, roi_algo, fused ? 0 : 1, rf, w.roi, st);
     if (rc) return rc;
     mark(3);
-    rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);
+    if (fused) {
+        const float* partial; const int* slot; const int* pieces; const float* count;
+        roi_align_ws_views(w.roi, n_cap, B, feat_ch, H, W, &partial, &slot, &pieces, &count);
+        rc = head_forward_launch_partial(rf, partial, slot, pieces, count, n_dev, n_cap, head_folded, out_reg, st);
+    } else {
+        rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);
+    }
     if (rc) return rc;
     mark(4);
     rc = generate_bbox_launch(out_bxyxy, out_reg, out_scores, out_clses, n_dev, n_cap, scale, out_s1, out_s2, st);

@@ -282,7 +282,7 @@ __device__ __forceinline__ void bin_ranges(const AxisGeom& g, int size, int lane
 __global__ void __launch_bounds__(256)
 roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_dev, int n_cap,
                 int B, int C, int H, int W, int force_direct, TileDims td,
-                RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ wx,
+                RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ cnt_arr, float* __restrict__ wx,
                 float4* __restrict__ wy4, int* __restrict__ tile_count) {
     const int lane = lane_id();
     const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
@@ -334,7 +334,7 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
             }
         }
     }
-    if (lane == 0) { prep[n] = rp; meta[n] = m; }
+    if (lane == 0) { prep[n] = rp; meta[n] = m; cnt_arr[n] = rp.count; }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -670,7 +670,7 @@ roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slo
 // host side
 // --------------------------------------------------------------------------------------------
 struct RoiWs {
-    RoiPrep* prep; int* meta; int* slot; float* wx; float4* wy4;
+    RoiPrep* prep; int* meta; int* slot; float* cnt; float* wx; float4* wy4;
     int* zeroed; size_t zeroed_bytes;              // tile_count | tile_fill | ctl  (one memset)
     int* tile_count; int* tile_fill; int* ctl;
     int* tile_off; int4* items; int* direct_list; int4* list; float* list_wx; float4* list_wy; float* partial;
@@ -689,6 +689,7 @@ static RoiWs carve_roi(void* ws, int n_cap, int B, int C, int H, int W) {
     w.prep = cv.take<RoiPrep>(n_cap);
     w.meta = cv.take<int>((size_t)n_cap + 4);
     w.slot = cv.take<int>((size_t)n_cap + 4);
+    w.cnt = cv.take<float>((size_t)n_cap);
     w.wx = cv.take<float>((size_t)n_cap * RR_POOL * kMaxWinT);
     w.wy4 = cv.take<float4>((size_t)n_cap * kMaxWinT);
     w.zeroed = cv.take<int>((size_t)2 * w.n_tiles + kCtlWords);
@@ -709,15 +710,24 @@ size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W) {
     return carve_roi(nullptr, n_cap, B, C, H, W).bytes;
 }
 
+// views into the workspace for a consumer that sums the partial slots itself (the fused head)
+void roi_align_ws_views(void* ws, int n_cap, int B, int C, int H, int W, const float** partial, const int** slot,
+                        const int** pieces, const float** count) {
+    RoiWs w = carve_roi(ws, n_cap, B, C, H, W);
+    *partial = w.partial; *slot = w.slot; *pieces = w.meta; *count = w.cnt;
+}
+
+// combine == 0: leave the tile-path RoIs as partial slots (out only receives the direct-path RoIs)
 int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
-                     int B, int C, int H, int W, int relu, int algo, float* out, void* ws, cudaStream_t st) {
+                     int B, int C, int H, int W, int relu, int algo, int combine, float* out, void* ws,
+                     cudaStream_t st) {
     int rc = 0;
     RoiWs w = carve_roi(ws, n_cap, B, C, H, W);
     RR_CUDA(cudaMemsetAsync(w.zeroed, 0, w.zeroed_bytes, st), rc);
     if (rc) return rc;
     const int force_direct = algo == 1;
     roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
-                                                    w.prep, w.meta, w.wx, w.wy4, w.tile_count);
+                                                    w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
     RR_LAUNCHED(rc);
     roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
                                                 w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
@@ -736,9 +746,11 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
                                                                   w.td, w.partial);
         RR_LAUNCHED(rc);
     }
-    roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
-        w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
-    RR_LAUNCHED(rc);
+    if (combine) {
+        roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
+            w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
+        RR_LAUNCHED(rc);
+    }
     roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * kSMs, kRoiThreads, 0, st>>>(
         feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
     RR_LAUNCHED(rc);
@@ -762,5 +774,5 @@ RR_API int rr_roi_align(const float* feat, const float* rois, const int32_t* n_r
     if (n_cap < 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0 || algo < 0 || algo > 1) return RR_E_BADARG;
     if (C > 1024) return RR_E_RANGE;                 // roi_combine stages one RoI (C*9 floats) in shared memory
     if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
-    return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, out, ws, (cudaStream_t)stream);
+    return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, 1, out, ws, (cudaStream_t)stream);
 }

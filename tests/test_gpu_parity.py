@@ -383,6 +383,17 @@ def test_eval_path_full_size_properties(ops, oracle_mod):
     assert rel_err(npy(path.roi_feat)[sub], roi, floor=1e-3) < TOL
     reg = oracle_mod.head(roi, {k: v.numpy() for k, v in hp.items()})
     assert rel_err(npy(r["reg"])[sub], reg, floor=1.0) < TOL
+    # the fused form (head sums the RoIAlign partial slots itself, no RoI feature tensor) is bit-identical
+    fused = ops.EvalPath(B, C, H, W, K, folded)
+    fused.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    rf = fused.results()
+    assert rf["n"] == r["n"]
+    np.testing.assert_array_equal(npy(rf["reg"]), npy(r["reg"]))
+    np.testing.assert_array_equal(npy(rf["s2"]), npy(r["s2"]))
+    # the direct-gather RoIAlign agrees to rounding
+    direct = ops.EvalPath(B, C, H, W, K, folded, roi_algo=1)
+    direct.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    assert rel_err(npy(direct.results()["reg"]), npy(r["reg"]), floor=1.0) < TOL
     # image 5 alone gives exactly the rows it had inside the batch
     one = ops.EvalPath(1, C, H, W, K, folded)
     one.forward(xd["hm"][5:6], xd["wh"][5:6], xd["off"][5:6], xd["feat"][5:6])
