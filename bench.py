@@ -142,6 +142,74 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def cuda_reference(x_dev, hp_dev, K, reps=5):
+    """The reference's own GPU path for the same batch: its unmodified call sequence (torch sigmoid/topk/
+    gather, torchvision.ops.nms per class with the host syncs that implies, torch.relu + torchvision
+    roi_align, the Bottleneck head through cuDNN) on CUDA tensors -- oracle/ref_port.post_backbone.
+    This is the baseline BASELINE.json's ">=10x" target names.  Returns ms per batch."""
+    from oracle import ref_port
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for _ in range(2):
+            ref_port.post_backbone(x_dev["hm"], x_dev["wh"], x_dev["off"], x_dev["feat"], hp_dev, K)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref_port.post_backbone(x_dev["hm"], x_dev["wh"], x_dev["off"], x_dev["feat"], hp_dev, K)
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
+def aux_kernels(dev, peak):
+    """The other rows of the scope table, timed alone (CUDA events, L2 flushed between repetitions):
+    training side at config 3 (B=32, 10x128x128) and the config-5 NMS stress (20k boxes, one class)."""
+    from rrnet_b200 import ops, synth
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, reps=10):
+        fn(); fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps
+
+    out = {}
+    B, C, h, w = 32, 10, 128, 128
+    g = torch.Generator().manual_seed(synth.SEED_C3)
+    z = (torch.randn(B, C, h, w, generator=g) * 2 - 2).to(dev)
+    annos, n_obj = synth.pad_annos(synth.train_annos(B, 512, 512, synth.SEED_C3))
+    annos, n_obj = annos.to(dev), n_obj.to(dev)
+    gt = ops.render_targets(annos, n_obj, 512, 512)[0]
+    n = z.numel()
+    ms = timed(lambda: ops.focal_fwd_bwd(z, gt))
+    out["focal_fwd_bwd_c3"] = {"ms": ms, "algorithmic_bytes": 3 * n * 4, "gbs": 3 * n * 4 / ms / 1e6,
+                               "frac_of_hbm_peak": 3 * n * 4 / ms / 1e6 / peak}
+    ms = timed(lambda: ops.focal_forward(z, gt))
+    out["focal_fwd_c3"] = {"ms": ms, "algorithmic_bytes": 2 * n * 4, "gbs": 2 * n * 4 / ms / 1e6,
+                           "frac_of_hbm_peak": 2 * n * 4 / ms / 1e6 / peak}
+    ms = timed(lambda: ops.render_targets(annos, n_obj, 512, 512))
+    rb = annos.numel() * 4 + n * 4
+    out["render_targets_c3"] = {"ms": ms, "algorithmic_bytes": rb, "gbs": rb / ms / 1e6, "frac_of_hbm_peak": rb / ms / 1e6 / peak,
+                                "objects": int(n_obj.sum())}
+    d = synth.nms_stress_boxes(20000, synth.SEED_C5).to(dev)
+    seg = torch.tensor([0, 20000], dtype=torch.int32, device=dev)
+    boxes, scores = d[:, :4].contiguous(), d[:, 4].contiguous()
+    ms = timed(lambda: ops.nms_batched(boxes, scores, seg, 0.7, 0, False), reps=5)
+    out["nms_20k_boxes_c5"] = {"ms": ms, "pairs": 20000 * 19999 // 2, "giou_per_s": 20000 * 19999 / 2 / ms / 1e6,
+                               "bound": "fp32 ALU + serial greedy chain (SURVEY 8d)"}
+    d5 = synth.nms_stress_boxes(5000, synth.SEED_C5 + 1).to(dev)
+    seg5 = torch.tensor([0, 5000], dtype=torch.int32, device=dev)
+    ms = timed(lambda: ops.soft_nms_batched(d5, seg5, 0.5, 0.7, 0.1, 2), reps=5)
+    out["soft_nms_5k_boxes"] = {"ms": ms, "bound": "serial selection chain"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ roofline helper
 def roi_align_algorithmic_bytes(bxyxy, B, C, H, W):
     """min(sum_roi C*4*(floor(x2)-floor(x1)+2)*(floor(y2)-floor(y1)+2) clipped to the map,
@@ -271,25 +339,44 @@ def run_product(args):
     peak, peak_src = measured_peaks()
     dominant = max(stage_ms, key=stage_ms.get)
     algo_total, algo_read, window_bytes = roi_align_algorithmic_bytes(r["bxyxy"], B, Cf, H, W)
+    # fused eval path: the RoI feature tensor is never written (the head sums the partial slots), so the
+    # RoIAlign stage's algorithmic bytes are the feature reads only ("0 write when fused with head")
     roof_bytes = {
         "decode": B * C * H * W * 4 + B * K * 16 + B * K * 32,
-        "roi_align": algo_total,
+        "roi_align": algo_read,
     }
+    traffic = {}
+    tp = os.path.join(REPO, "profiles", "traffic.json")       # dram bytes per launch from the ncu --set full capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     roofline = None
     if dominant in roof_bytes:
         ach = roof_bytes[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "algorithmic_bytes": roof_bytes[dominant],
+                    "frac": ach / peak, "traffic": traffic.get(dominant), "algorithmic_bytes": roof_bytes[dominant],
                     "peak_source": peak_src}
     else:       # head: fp32 FFMA contraction, 49 valid 3x3 taps -> 993,280 flop per RoI
         tf = r["n"] * 993280.0 / (stage_ms[dominant] * 1e-3) / 1e12
         roofline = {"kernel": dominant, "bound": "tensor", "achieved": tf, "peak": 1624.9, "unit": "TFLOP/s",
                     "frac": tf / 1624.9, "traffic": None, "note": "fp32 FFMA kernel measured against the bf16 tensor peak"}
-    roi_ach = algo_total / (stage_ms["roi_align"] * 1e-3) / 1e9
+    roi_ach = algo_read / (stage_ms["roi_align"] * 1e-3) / 1e9
     dec_ach = roof_bytes["decode"] / (stage_ms["decode"] * 1e-3) / 1e9
     extra_roof = {"roi_align_gbs": roi_ach, "roi_align_frac": roi_ach / peak, "decode_gbs": dec_ach,
                   "decode_frac": dec_ach / peak, "roi_window_bytes_l2": window_bytes,
                   "head_tflops_fp32": r["n"] * 993280.0 / (stage_ms["head"] * 1e-3) / 1e12}
+
+    # ---- the reference's own CUDA/torch path on the same batch, and the other scope rows, beside it ----
+    ref_cuda = None
+    aux = None
+    if not args.no_aux:
+        try:
+            ms = cuda_reference(d, {k: v.to(dev) for k, v in hp.items()}, K)
+            ref_cuda = {"ms_per_step": ms, "value": B / (ms / 1e3), "unit": UNIT,
+                        "what": "reference call sequence (torch + torchvision CUDA ops, cuDNN head, fp32) on the same "
+                                "device-resident batch, wall clock incl. its host syncs"}
+        except Exception as e:                                       # torchvision CUDA ops missing on the box
+            ref_cuda = {"unavailable": repr(e)[:200]}
+        aux = aux_kernels(dev, peak)
 
     # ---- CPU baseline beside it (rank 0, bounded sample) ----
     cpu_info = None
@@ -306,7 +393,8 @@ def run_product(args):
             "clocks": clocks, "gpu_launches": int(launches) * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
-            "roofline": roofline, "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info}
+            "roofline": roofline, "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info,
+            "reference_cuda": ref_cuda, "aux": aux}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -321,6 +409,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
     ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -94,7 +94,7 @@ def post_backbone(hm, wh, off, feat, hp, K, nms_thr=0.7, scale=4.0, stage_times=
     t1 = time.perf_counter()
     kept = [per_class_nms(rows[b], nms_thr) for b in range(rows.shape[0])]
     counts = [k.shape[0] for k in kept]
-    bxyxy = torch.cat([torch.cat([torch.full((k.shape[0], 1), float(b)), k[:, :4]], 1) for b, k in enumerate(kept)])
+    bxyxy = torch.cat([torch.cat([torch.full((k.shape[0], 1), float(b), device=k.device), k[:, :4]], 1) for b, k in enumerate(kept)])
     scores = torch.cat([k[:, 4] for k in kept])
     clses = torch.cat([k[:, 5] for k in kept])
     t2 = time.perf_counter()
