@@ -170,14 +170,35 @@ def aux_kernels(dev, peak):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timed(fn, reps=10):
+        """Device time of one fn() with a cold L2: a CUDA graph of reps x (flush L2, fn) minus a graph of
+        reps x (flush L2), so that neither Python / ctypes launch overhead nor the flush is counted."""
         fn(); fn()
-        tot = 0.0
-        for _ in range(reps):
-            flush.fill_(1)
+        torch.cuda.synchronize()
+
+        def graph_ms(with_fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    flush.fill_(1)
+                    if with_fn:
+                        fn()
+            g.replay()
+            torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record(); b.synchronize()
-            tot += a.elapsed_time(b)
-        return tot / reps
+            a.record(); g.replay(); b.record(); b.synchronize()
+            return a.elapsed_time(b)
+
+        try:
+            return max(graph_ms(True) - graph_ms(False), 0.0) / reps
+        except Exception:                                # not capturable: eager launches (includes launch gaps)
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); b.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / reps
 
     out = {}
     B, C, h, w = 32, 10, 128, 128

@@ -29,7 +29,7 @@ namespace rr {
 
 constexpr int kCap = 16384;          // candidate capacity per image (== RR_MAX_TOPK)
 constexpr int kSampleThreads = 1024;
-constexpr int kSamplesPerThread = 16;
+constexpr int kSamplesPerThread = 32;
 constexpr int kCollectThreads = 256;
 constexpr int kStage = 1024;         // per-CTA staging entries in decode_collect_kernel
 constexpr int kSelectThreads = 1024;
@@ -84,42 +84,38 @@ decode_sample_kernel(const float* __restrict__ hm, int H, int W, int N, int K, i
     const float* img = hm + (size_t)b * N;
     const int HW = H * W;
     const unsigned nlines = (unsigned)N / 32u;
-    unsigned keys[kSamplesPerThread];
     const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-    for (int it = 0; it < kSamplesPerThread; ++it) {
-        unsigned L = (unsigned)(warp * kSamplesPerThread + it);
-        unsigned line = (unsigned)(((unsigned long long)L * 2654435761ull + 12345ull) % nlines);
-        unsigned flat = line * 32u + (unsigned)lane;
-        float v = __ldg(img + flat);
-        if (pool == 3) v = pooled_value(img, H, W, HW, flat, v);
-        keys[it] = f2key(v);
-    }
-    // target population count T in [K, kCap]; sample rank r = T * S / N
-    const int S = kSampleThreads * kSamplesPerThread;
-    int target = max(3 * K, K + 2048);
+    // target population count T in (K, kCap]: centred so that the candidate count lands in (K, 4096] with
+    // ~3 sigma on either side at config 2 (the select kernel sorts the next power of two)
+    int target = max(2 * K, K + 1300);
     target = min(target, (K + kCap) / 2);
+    // samples per thread so that the sample rank of the threshold, r = T * S / N, is about 128
+    int spt = (int)((128ll * N + (long long)target * kSampleThreads - 1) / ((long long)target * kSampleThreads));
+    spt = min(max(spt, 1), kSamplesPerThread);
+    const int S = kSampleThreads * spt;
     int r = (int)(((long long)target * S + N - 1) / N);
-    r = max(r, 8);
-    // largest key t with #{sample keys >= t} >= r  (MSB-first descent, 32 block-wide counts)
+    r = min(max(r, 8), kSampleThreads / 2);
+    // Every thread keeps the MAXIMUM of its samples; the r-th largest of the 1024 maxima estimates the
+    // r-th largest sample (the top r << 1024 samples almost surely sit in different threads; a collision
+    // only lowers the threshold slightly, i.e. a few more candidates).  The estimate need not be exact:
+    // the select kernel falls back to an exact search when the candidate count leaves [K, kCap].
+    unsigned m = 0u;
+#pragma unroll 8
+    for (int it = 0; it < kSamplesPerThread; ++it) {
+        if (it < spt) {
+            unsigned L = (unsigned)(warp * spt + it);
+            unsigned line = (unsigned)(((unsigned long long)L * 2654435761ull + 12345ull) % nlines);
+            unsigned flat = line * 32u + (unsigned)lane;
+            float v = __ldg(img + flat);
+            if (pool == 3) v = pooled_value(img, H, W, HW, flat, v);
+            m = max(m, f2key(v));
+        }
+    }
+    // largest t with #{threads : m >= t} >= r  (MSB-first descent, one counting barrier per bit)
     unsigned t = 0;
     for (int bit = 31; bit >= 0; --bit) {
-        unsigned trial = t | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int it = 0; it < kSamplesPerThread; ++it) c += (keys[it] >= trial);
-        // __syncthreads_count counts threads with non-zero predicate; we need the SUM
-        __shared__ int s_warp[kSampleThreads / 32];
-        int ws = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
-        if (lane == 0) s_warp[warp] = ws;
-        __syncthreads();
-        int tot = (lane < kSampleThreads / 32) ? s_warp[lane] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        __syncthreads();
-        if (tot >= r) t = trial;
+        const unsigned trial = t | (1u << bit);
+        if (__syncthreads_count(m >= trial) >= r) t = trial;
     }
     if (tid == 0) thr_key[b] = t;
 }

@@ -118,16 +118,26 @@ __device__ __forceinline__ bool focal_block_reduce(float pos, float neg, int npo
     return s_last;
 }
 
+// final sum by the last block, in a fixed order (thread t adds partials t, t+256, ...; then a fixed
+// shuffle tree and a fixed sweep over the warps) -> bit-reproducible, and parallel
 __device__ __forceinline__ void focal_finish(const double* partial, float* stats) {
-    // one thread, fixed order -> bit-reproducible
+    __shared__ double s_f[3][kFocalThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a = 0, b = 0, c = 0;
-    for (unsigned int k = 0; k < gridDim.x; ++k) {
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += kFocalThreads) {
         a += __ldcg(partial + k * 3 + 0);
         b += __ldcg(partial + k * 3 + 1);
         c += __ldcg(partial + k * 3 + 2);
     }
-    const double loss = (c == 0.0) ? -b : -(a + b) / c;            // functional.py:47-50
-    stats[0] = (float)loss; stats[1] = (float)a; stats[2] = (float)b; stats[3] = (float)c;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { s_f[0][warp] = a; s_f[1][warp] = b; s_f[2][warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = c = 0;
+        for (int w = 0; w < kFocalThreads / 32; ++w) { a += s_f[0][w]; b += s_f[1][w]; c += s_f[2][w]; }
+        const double loss = (c == 0.0) ? -b : -(a + b) / c;            // functional.py:47-50
+        stats[0] = (float)loss; stats[1] = (float)a; stats[2] = (float)b; stats[3] = (float)c;
+    }
 }
 
 __global__ void __launch_bounds__(kFocalThreads)
@@ -137,10 +147,10 @@ focal_forward_kernel(const float* __restrict__ logits, const float* __restrict__
     float pos = 0.f, neg = 0.f;
     int npos = 0;
     focal_accumulate(logits, gt, n, pos, neg, npos);
-    if (focal_block_reduce(pos, neg, npos, partial, ticket) && threadIdx.x == 0) {
+    if (focal_block_reduce(pos, neg, npos, partial, ticket)) {     // block-uniform: the last block to finish
         __threadfence();
         focal_finish(partial, stats);
-        *ticket = 0u;                                             // ready for the next launch
+        if (threadIdx.x == 0) *ticket = 0u;                       // ready for the next launch
     }
 }
 
@@ -179,11 +189,10 @@ focal_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__
     float pos = 0.f, neg = 0.f;
     int npos = 0;
     focal_accumulate(logits, gt, n, pos, neg, npos);
-    if (focal_block_reduce(pos, neg, npos, partial, ticket) && threadIdx.x == 0) {
+    if (focal_block_reduce(pos, neg, npos, partial, ticket)) {
         __threadfence();
         focal_finish(partial, stats);
-        *ticket = 0u;
-        __threadfence();
+        if (threadIdx.x == 0) { *ticket = 0u; __threadfence(); }
     }
     cg::this_grid().sync();
     const float np = __ldcg(stats + 3);

@@ -257,19 +257,28 @@ roi_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois
 // --------------------------------------------------------------------------------------------
 struct TileDims { int ntx, nty, tiles_per_img; };
 
-__device__ __forceinline__ void bin_ranges(const AxisGeom& g, int size, int lane, signed char* lo3, signed char* hi3) {
+constexpr int kMaxSamples = 72;      // 3 * grid, grid <= 22 for windows of at most kMaxWinT pixels
+
+// Per-warp table of one axis' bilinear samples (in sample order) + per-bin pixel ranges.
+struct AxisTable { int low[kMaxSamples]; int high[kMaxSamples]; float wl[kMaxSamples]; };
+
+__device__ __forceinline__ void axis_table(const AxisGeom& g, int size, int lane, AxisTable& tb,
+                                           signed char* lo3, signed char* hi3) {
     int lo[RR_POOL], hi[RR_POOL];
 #pragma unroll
     for (int p = 0; p < RR_POOL; ++p) { lo[p] = 127; hi[p] = -1; }
     const int total = RR_POOL * g.grid;
     for (int t = lane; t < total; t += 32) {
         const int p = t / g.grid, i = t - p * g.grid;
-        int l0, h0; float wl, wh;
+        int l0 = -1, h0 = -1; float wl = 0.f, wh;
         if (axis_sample(g.start, g.bin, g.grid, p, i, size, l0, h0, wl, wh)) {
 #pragma unroll
             for (int q = 0; q < RR_POOL; ++q)
                 if (q == p) { lo[q] = min(lo[q], l0 - g.lo); hi[q] = max(hi[q], h0 - g.lo); }
+        } else {
+            l0 = h0 = -1;
         }
+        tb.low[t] = l0; tb.high[t] = h0; tb.wl[t] = wl;
     }
 #pragma unroll
     for (int p = 0; p < RR_POOL; ++p) {
@@ -277,6 +286,20 @@ __device__ __forceinline__ void bin_ranges(const AxisGeom& g, int size, int lane
         hi3[p] = (signed char)__reduce_max_sync(0xffffffffu, hi[p]);
     }
     lo3[3] = 127; hi3[3] = -1;
+    __syncwarp();
+}
+
+// weight bin p puts on pixel pix: the table's samples of that bin, in sample order (== axis_weight)
+__device__ __forceinline__ float table_weight(const AxisTable& tb, int grid, int p, int pix) {
+    float acc = 0.f;
+    const int t0 = p * grid;
+    for (int i = 0; i < grid; ++i) {
+        const int l0 = tb.low[t0 + i], h0 = tb.high[t0 + i];
+        const float wl = tb.wl[t0 + i];
+        if (l0 == pix) acc += 1.f - wl;
+        if (h0 == pix && l0 >= 0) acc += wl;
+    }
+    return acc;
 }
 
 __global__ void __launch_bounds__(256)
@@ -284,10 +307,13 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
                 int B, int C, int H, int W, int force_direct, TileDims td,
                 RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ cnt_arr, float* __restrict__ wx,
                 float4* __restrict__ wy4, int* __restrict__ tile_count) {
+    __shared__ AxisTable s_tab[8][2];
     const int lane = lane_id();
     const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     if (n >= live) return;
+    AxisTable& tx = s_tab[warp_id()][0];
+    AxisTable& ty = s_tab[warp_id()][1];
     const float* r = rois + (size_t)n * 5;
     RoiPrep rp;
     rp.img = (int)r[0];
@@ -304,15 +330,16 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
         if (gx.n > 0 && gy.n > 0) {
             rp.x_lo = gx.lo; rp.nx = gx.n; rp.y_lo = gy.lo; rp.ny = gy.n;
             rp.count = (float)max(gx.grid * gy.grid, 1);
-            if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0) {
+            if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0 ||
+                RR_POOL * gx.grid > kMaxSamples || RR_POOL * gy.grid > kMaxSamples) {
                 rp.flags = kFlagDirect;
                 m = -1;
             } else {
                 rp.flags = kFlagTile;
                 rp.tx0 = gx.lo / kTW; rp.ntx = (gx.lo + gx.n - 1) / kTW - rp.tx0 + 1;
                 rp.ty0 = gy.lo / kTH; rp.nty = (gy.lo + gy.n - 1) / kTH - rp.ty0 + 1;
-                bin_ranges(gx, W, lane, rp.cx_lo, rp.cx_hi);
-                bin_ranges(gy, H, lane, rp.cy_lo, rp.cy_hi);
+                axis_table(gx, W, lane, tx, rp.cx_lo, rp.cx_hi);
+                axis_table(gy, H, lane, ty, rp.cy_lo, rp.cy_hi);
                 float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
                 float4* wyn = wy4 + (size_t)n * kMaxWinT;
                 const int kmax = max(gx.n, gy.n);
@@ -320,16 +347,16 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
                     float b[RR_POOL];
 #pragma unroll
                     for (int p = 0; p < RR_POOL; ++p) {
-                        const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? axis_weight(gx, p, k, W) : 0.f;
-                        b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? axis_weight(gy, p, k, H) : 0.f;
+                        const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? table_weight(tx, gx.grid, p, gx.lo + k) : 0.f;
+                        b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? table_weight(ty, gy.grid, p, gy.lo + k) : 0.f;
                         if (k < gx.n) wxn[p * kMaxWinT + k] = a;
                     }
                     if (k < gy.n) wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
                 }
                 m = rp.ntx * rp.nty;
                 if (lane < m) {
-                    const int ty = rp.ty0 + lane / rp.ntx, tx = rp.tx0 + lane % rp.ntx;
-                    atomicAdd(tile_count + rp.img * td.tiles_per_img + ty * td.ntx + tx, 1);
+                    const int tyi = rp.ty0 + lane / rp.ntx, txi = rp.tx0 + lane % rp.ntx;
+                    atomicAdd(tile_count + rp.img * td.tiles_per_img + tyi * td.ntx + txi, 1);
                 }
             }
         }
