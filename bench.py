@@ -167,19 +167,25 @@ def aux_kernels(dev, peak):
     """The other rows of the scope table, timed alone (CUDA events, L2 flushed between repetitions):
     training side at config 3 (B=32, 10x128x128) and the config-5 NMS stress (20k boxes, one class)."""
     from rrnet_b200 import ops, synth
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # L2 flush by READING 256 MB (a write flush would leave 126 MB of dirty lines whose write-back is then
+    # billed to the kernel under test)
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def do_flush():
+        torch.sum(flush, dim=0, keepdim=True, out=sink)
 
     def timed(fn, reps=10):
         """Device time of one fn() with a cold L2: a CUDA graph of reps x (flush L2, fn) minus a graph of
         reps x (flush L2), so that neither Python / ctypes launch overhead nor the flush is counted."""
-        fn(); fn()
+        fn(); fn(); do_flush()
         torch.cuda.synchronize()
 
         def graph_ms(with_fn):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for _ in range(reps):
-                    flush.fill_(1)
+                    do_flush()
                     if with_fn:
                         fn()
             g.replay()
@@ -194,7 +200,7 @@ def aux_kernels(dev, peak):
             torch.cuda.synchronize()
             tot = 0.0
             for _ in range(reps):
-                flush.fill_(1)
+                do_flush()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); fn(); b.record(); b.synchronize()
                 tot += a.elapsed_time(b)
