@@ -283,8 +283,13 @@ def run_product(args):
         gathered = torch.empty(world * B * K, 6, dtype=torch.float32, device=dev)
         gathered_cnt = torch.empty(world * (B + 1), dtype=torch.int32, device=dev)
 
+    graph = None if args.no_graph else path.capture(d["hm"], d["wh"], d["off"], d["feat"])
+
     def step(events=None):
-        path.forward(d["hm"], d["wh"], d["off"], d["feat"], stage_events=events)
+        if graph is not None and events is None:
+            graph.replay()                 # the same launches, submitted as one CUDA graph
+        else:
+            path.forward(d["hm"], d["wh"], d["off"], d["feat"], stage_events=events)
         if world > 1:            # all-gather of detections for mAP (padded rows + counts)
             dist.all_gather_into_tensor(gathered, path.s2)
             dist.all_gather_into_tensor(gathered_cnt, path.counts)
@@ -295,25 +300,25 @@ def run_product(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    launches0 = ops._lib.launch_count()
+    path.forward(d["hm"], d["wh"], d["off"], d["feat"])
+    launches_per_step = ops._lib.launch_count() - launches0     # kernels of ours per step (same inside the graph)
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
 
     # ---- timed region: K steps, device-resident inputs, no host sync inside ----
-    n_ev = args.steps
-    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(n_ev)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
-    launches0 = ops._lib.launch_count()
     sync_all()
     sampler.start()
     t_beg.record()
     for i in range(args.steps):
-        step(stage_ev[i])
+        step()
     t_end.record()
     sync_all()
     clocks = sampler.stop()
-    launches = ops._lib.launch_count() - launches0
+    launches = launches_per_step * args.steps
     elapsed_ms = t_beg.elapsed_time(t_end)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -321,12 +326,19 @@ def run_product(args):
     elapsed_ms = float(t.item())
     value = world * B * args.steps / (elapsed_ms / 1e3)
 
+    # ---- per-stage device times: a second, eager loop with events recorded by the library between stages ----
+    n_ev = min(args.steps, 20)
+    stage_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(n_ev)]
+    for i in range(n_ev):
+        step(stage_ev[i])
+    sync_all()
+
     names = ["decode", "stage1_nms", "roi_align", "head", "generate_bbox"]
     stage_ms = {n: 0.0 for n in names}
     for evs in stage_ev:
         for j, n in enumerate(names):
             stage_ms[n] += evs[j].elapsed_time(evs[j + 1])
-    stage_ms = {n: v / args.steps for n, v in stage_ms.items()}
+    stage_ms = {n: v / n_ev for n, v in stage_ms.items()}
 
     # ---- e2e: pinned host inputs -> H2D -> path -> D2H of the result, every step ----
     res_host = torch.empty(B * K, 6, dtype=torch.float32).pin_memory()
@@ -416,6 +428,7 @@ def run_product(args):
             "config": {"workload": WORKLOAD_NAME, **WORKLOAD, "global_batch": world * B,
                        "parallelism": "image-sharded x%d, all-gather of detections" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (features 1.07 GB per step)",
+                       "submission": "eager launches" if args.no_graph else "CUDA graph replay of the step (memset + 12 kernels)",
                        "rois_per_step": r["n"]},
             "clocks": clocks, "gpu_launches": int(launches) * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -436,6 +449,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
     ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
     args = ap.parse_args()

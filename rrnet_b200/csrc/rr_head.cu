@@ -94,8 +94,9 @@ __device__ __forceinline__ void head_load_x(const HeadSrc& src, int n, int sb, i
 #pragma unroll
             for (int p = 0; p < kPix; ++p) v[p] += __ldg(pp + p * 256);
         }
+        const float inv = 1.0f / cnt;               // same rounding as roi_combine_kernel: sum * (1/count)
 #pragma unroll
-        for (int p = 0; p < kPix; ++p) v[p] = v[p] / cnt;
+        for (int p = 0; p < kPix; ++p) v[p] = __fmul_rn(v[p], inv);   // never contracted into the residual add
     }
 }
 

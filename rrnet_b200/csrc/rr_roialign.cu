@@ -685,8 +685,9 @@ roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slo
 #pragma unroll
             for (int q = 0; q < kBins; ++q) acc[q] += __ldg(src + (size_t)q * C);
         }
+        const float inv = 1.0f / rp.count;          // the fused head applies the same sum * (1/count)
 #pragma unroll
-        for (int q = 0; q < kBins; ++q) s_out[c * kBins + q] = acc[q] / rp.count;
+        for (int q = 0; q < kBins; ++q) s_out[c * kBins + q] = acc[q] * inv;
     }
     __syncthreads();
     float* o = out + (size_t)n * C * kBins;

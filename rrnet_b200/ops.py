@@ -279,6 +279,17 @@ class EvalPath:
             _ptr(self.ws), self.ws.numel(), _stream(), ev), "rr_eval_forward")
         return self
 
+    def capture(self, hm, wh, off, feat):
+        """Capture forward() on these (static) input tensors into a CUDA graph; graph.replay() then re-runs
+        the whole path (a memset + 12 kernels) with one launch.  The C entry points never allocate or
+        synchronise, so they are capturable as they are."""
+        self.forward(hm, wh, off, feat)                    # warm-up: function attributes, lazy module load
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(hm, wh, off, feat)
+        return g
+
     def results(self):
         """One host sync: -> dict of tensors sliced to the live row count + per-image counts (python list)."""
         counts = self.counts.tolist()

@@ -406,6 +406,58 @@ def test_eval_path_full_size_properties(ops, oracle_mod):
     np.testing.assert_array_equal(npy(r1["s2"]), npy(r["s2"])[lo:hi])
 
 
+def test_eval_path_config5_dense_scene(ops, oracle_mod):
+    """Config 5 shape (K=5000 proposals per image at 10x272x480; 2 of the 16 images so that the oracle stays
+    within seconds): decode and keep-lists bit-exact, RoI features / head / boxes for a strided subset."""
+    B, C, H, W, K = 2, 10, 272, 480, 5000
+    x = synth.eval_inputs(B, H, W, K, synth.SEED_C5)
+    hp = synth.head_params(synth.SEED_C5)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    path = ops.EvalPath(B, C, H, W, K, folded, keep_roi_feat=True)
+    xd = {k: dev(v) for k, v in x.items()}
+    path.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    r = path.results()
+    dets, inds, _ = oracle_mod.decode(x["hm"].numpy(), x["wh"].numpy(), x["off"].numpy(), K)
+    np.testing.assert_array_equal(npy(path.inds), inds)
+    np.testing.assert_array_equal(npy(path.dets)[..., [0, 1, 2, 3, 5]], dets[..., [0, 1, 2, 3, 5]])
+    rows, sc, cl = [], [], []
+    for b in range(B):
+        kept, _ = oracle_mod.stage1_nms(dets[b], C, 0.7)
+        assert r["counts"][b] == kept.shape[0]
+        rows.append(np.concatenate([np.full((kept.shape[0], 1), b, np.float32), kept[:, :4]], 1))
+        sc.append(kept[:, 4]); cl.append(kept[:, 5])
+    bxyxy = np.concatenate(rows)
+    np.testing.assert_array_equal(npy(r["bxyxy"]), bxyxy)
+    np.testing.assert_array_equal(npy(r["clses"]), np.concatenate(cl))
+    sub = np.arange(0, bxyxy.shape[0], 53)
+    roi = oracle_mod.roi_align(x["feat"].numpy(), bxyxy[sub], relu=True)
+    assert rel_err(npy(path.roi_feat)[sub], roi, floor=1e-3) < TOL
+    reg = oracle_mod.head(roi, {k: v.numpy() for k, v in hp.items()})
+    assert rel_err(npy(r["reg"])[sub], reg, floor=1.0) < TOL
+    sub0 = sub[bxyxy[sub, 0] == 0]
+    s1, s2 = oracle_mod.generate_bbox(bxyxy[sub0], npy(r["reg"])[sub0], np.concatenate(sc)[sub0],
+                                      np.concatenate(cl)[sub0], 0, 4.0)
+    assert rel_err(npy(r["s1"])[sub0], s1) < TOL
+    assert box_rel_err(npy(r["s2"])[sub0], s2) < TOL
+    # final stage at this density: per-class Gaussian soft-NMS of one image's ~4.7k stage-2 boxes vs the oracle
+    n0 = r["counts"][0]
+    s2_img = r["s2"][:n0]
+    order = torch.sort(s2_img[:, 5], stable=True).indices
+    d = s2_img[order]
+    _, cnts = torch.unique_consecutive(d[:, 5], return_counts=True)
+    seg = torch.zeros(cnts.numel() + 1, dtype=torch.int32, device=d.device)
+    seg[1:] = torch.cumsum(cnts, 0).int()
+    b5 = d[:, :5].clone()
+    b5[:, 2:4] += b5[:, 0:2]
+    out, _, kc = ops.soft_nms_batched(b5, seg, 0.5, 0.7, 0.1, 2)
+    out, kc, seg_h = npy(out), npy(kc), npy(seg)
+    for s_i in range(len(kc)):
+        ref = oracle_mod.soft_nms(npy(b5)[seg_h[s_i]:seg_h[s_i + 1]], sigma=0.5, Nt=0.7, threshold=0.1, method=2)
+        assert kc[s_i] == ref.shape[0]
+        np.testing.assert_array_equal(out[seg_h[s_i]:seg_h[s_i] + kc[s_i], :4], ref[:, :4])
+        assert rel_err(out[seg_h[s_i]:seg_h[s_i] + kc[s_i], 4], ref[:, 4]) < TOL
+
+
 # ===================================================================== soft-NMS (a9)
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_soft_nms_golden(ops, method):
