@@ -100,22 +100,40 @@ decode_sample_kernel(const float* __restrict__ hm, int H, int W, int N, int K, i
     // only lowers the threshold slightly, i.e. a few more candidates).  The estimate need not be exact:
     // the select kernel falls back to an exact search when the candidate count leaves [K, kCap].
     unsigned m = 0u;
-#pragma unroll 8
-    for (int it = 0; it < kSamplesPerThread; ++it) {
-        if (it < spt) {
-            unsigned L = (unsigned)(warp * spt + it);
-            unsigned line = (unsigned)(((unsigned long long)L * 2654435761ull + 12345ull) % nlines);
-            unsigned flat = line * 32u + (unsigned)lane;
-            float v = __ldg(img + flat);
-            if (pool == 3) v = pooled_value(img, H, W, HW, flat, v);
-            m = max(m, f2key(v));
+    if (pool != 3) {                                   // all loads of a thread are issued before the first use
+        float v[kSamplesPerThread];
+#pragma unroll
+        for (int it = 0; it < kSamplesPerThread; ++it) {
+            const unsigned L = (unsigned)(warp * spt + min(it, spt - 1));
+            const unsigned line = __umulhi(L * 2654435761u + 12345u, nlines);     // hash -> [0, nlines), no 64-bit modulo
+            v[it] = __ldg(img + line * 32u + (unsigned)lane);
+        }
+#pragma unroll
+        for (int it = 0; it < kSamplesPerThread; ++it) m = max(m, f2key(v[it]));  // it >= spt repeats the last sample
+    } else {
+        for (int it = 0; it < spt; ++it) {
+            const unsigned L = (unsigned)(warp * spt + it);
+            const unsigned line = __umulhi(L * 2654435761u + 12345u, nlines);
+            const unsigned flat = line * 32u + (unsigned)lane;
+            m = max(m, f2key(pooled_value(img, H, W, HW, flat, __ldg(img + flat))));
         }
     }
-    // largest t with #{threads : m >= t} >= r  (MSB-first descent, one counting barrier per bit)
+    // largest t with #{threads : m >= t} >= r: the 1024 maxima go to shared memory and ONE warp runs the
+    // MSB-first descent on 32 values per lane (no block barrier per bit)
+    __shared__ unsigned s_max[kSampleThreads];
+    s_max[tid] = m;
+    __syncthreads();
+    if (warp != 0) return;
+    unsigned mine[kSampleThreads / 32];
+#pragma unroll
+    for (int q = 0; q < kSampleThreads / 32; ++q) mine[q] = s_max[q * 32 + lane];
     unsigned t = 0;
     for (int bit = 31; bit >= 0; --bit) {
         const unsigned trial = t | (1u << bit);
-        if (__syncthreads_count(m >= trial) >= r) t = trial;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < kSampleThreads / 32; ++q) c += (mine[q] >= trial);
+        if (__reduce_add_sync(0xffffffffu, c) >= r) t = trial;
     }
     if (tid == 0) thr_key[b] = t;
 }
@@ -301,19 +319,98 @@ __device__ void exact_select(const float* __restrict__ img, int H, int W, int N,
     }
 }
 
-__device__ void bitonic_sort_desc(unsigned long long* s_e, int P) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += nthr) {
-                int i = 2 * t - (t & (j - 1));          // lower index of the pair
-                int ixj = i + j;
-                bool desc = ((i & k) == 0);
-                unsigned long long a = s_e[i], c = s_e[ixj];
-                if (desc ? (a < c) : (a > c)) { s_e[i] = c; s_e[ixj] = a; }
+// In-place cut of s_e[0..n) to its K largest entries (all entries distinct): MSB-first radix descent, one
+// byte per round (256-bin histogram of the entries that match the prefix so far), then a stable compaction
+// through `tmp`.  Returns K.  Block-wide; s_e and tmp live in shared memory.
+__device__ int select_top_k(unsigned long long* s_e, int n, int K, unsigned long long* tmp) {
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_fill;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_prefix = 0ull; s_need = K; s_fill = 0; }
+    for (int round = 0; round < 8; ++round) {
+        const int shift = 56 - 8 * round;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = round == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int i0 = tid - lane; i0 < n; i0 += nthr) {        // warp-aggregated: one atomic per distinct bin per warp
+            const int i = i0 + lane;
+            const unsigned long long e = i < n ? s_e[i] : 0ull;
+            const bool act = i < n && (e & himask) == prefix;
+            const unsigned bin = act ? (unsigned)((e >> shift) & 255ull) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (act && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int loc[8], tot = 0;                               // lane owns bins [8*lane, 8*lane+8)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * lane + q]; tot += loc[q]; }
+            int suf = tot;                                     // inclusive suffix scan over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += v;
             }
+            const int need = s_need;
+            int run = suf - tot, pick = -1, need_in = 0;       // entries in the bins of higher lanes
+#pragma unroll
+            for (int q = 7; q >= 0; --q) {
+                if (pick < 0 && run < need && run + loc[q] >= need) { pick = 8 * lane + q; need_in = need - run; }
+                run += loc[q];
+            }
+            if (pick >= 0) {                                   // exactly one lane (1 <= need <= matching entries)
+                s_prefix = prefix | ((unsigned long long)pick << shift);
+                s_need = need_in;
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;                   // the K-th largest entry itself
+    for (int i0 = tid - lane; i0 < n; i0 += nthr) {            // order is irrelevant: sorted next
+        const int i = i0 + lane;
+        const unsigned long long e = i < n ? s_e[i] : 0ull;
+        const bool keep = i < n && e >= kth;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_fill, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) tmp[base + __popc(m & ((1u << lane) - 1u))] = e;
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += nthr) s_e[i] = tmp[i];
+    __syncthreads();
+    return K;
+}
+
+// Bitonic sort, descending, P a power of two.  Stages whose partner distance j is <= 32 only touch one
+// aligned 64-element block per warp iteration, so a warp runs them back to back with __syncwarp only; block
+// barriers are needed for the j >= 64 stages (21 instead of 78 barriers at P = 4096).
+__device__ __forceinline__ void bitonic_ce(unsigned long long* s_e, int t, int j, int k) {
+    const int i = 2 * t - (t & (j - 1));                // lower index of the pair
+    const int ixj = i + j;
+    const bool desc = ((i & k) == 0);
+    const unsigned long long a = s_e[i], c = s_e[ixj];
+    if (desc ? (a < c) : (a > c)) { s_e[i] = c; s_e[ixj] = a; }
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* s_e, int P) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int half = P >> 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        int j = k >> 1;
+        for (; j > 32; j >>= 1) {
+            for (int t = tid; t < half; t += nthr) bitonic_ce(s_e, t, j, k);
             __syncthreads();
         }
+        for (int t0 = tid - lane; t0 < half; t0 += nthr) {       // pairs t0..t0+31 <-> elements [2*t0, 2*t0+64)
+            for (int jj = j; jj > 0; jj >>= 1) {
+                if (t0 + lane < half) bitonic_ce(s_e, t0 + lane, jj, k);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -337,8 +434,15 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
         exact_select(img, H, W, N, K, pool, s_e, s_red);
         n = K;
     }
+    // more than 2048 candidates: cut to exactly the K largest first (entries are unique 64-bit values, so an
+    // 8-round byte-wise radix descent finds the K-th one exactly), then sort half as many elements
+    if (n > 2048 && n <= kCap / 2 && K < n) {
+        __syncthreads();
+        n = select_top_k(s_e, n, K, s_e + kCap / 2);
+    }
     int P = 1;
     while (P < n) P <<= 1;
+    __syncthreads();
     for (int i = n + tid; i < P; i += blockDim.x) s_e[i] = 0ull;   // below every real entry
     __syncthreads();
     bitonic_sort_desc(s_e, P);
