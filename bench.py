@@ -224,6 +224,14 @@ def aux_kernels(dev, peak):
     rb = annos.numel() * 4 + n * 4
     out["render_targets_c3"] = {"ms": ms, "algorithmic_bytes": rb, "gbs": rb / ms / 1e6, "frac_of_hbm_peak": rb / ms / 1e6 / peak,
                                 "objects": int(n_obj.sum())}
+    def fused():
+        st = ops.focal_render_forward(z, annos, n_obj, 512, 512)
+        return ops.focal_render_backward(z, annos, n_obj, 512, 512, st)
+    ms = timed(fused)
+    fb = 2 * n * 4 + annos.numel() * 4            # logits read once (second pass from L2) + gradient write
+    out["focal_render_fused_fwd_bwd_c3"] = {"ms": ms, "algorithmic_bytes": fb, "gbs": fb / ms / 1e6,
+                                            "frac_of_hbm_peak": fb / ms / 1e6 / peak,
+                                            "replaces": "render_targets + focal_fwd_bwd (84 MB of traffic)"}
     d = synth.nms_stress_boxes(20000, synth.SEED_C5).to(dev)
     seg = torch.tensor([0, 20000], dtype=torch.int32, device=dev)
     boxes, scores = d[:, :4].contiguous(), d[:, 4].contiguous()

@@ -59,7 +59,7 @@ def _digest(paths, flags):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
+    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(CSRC, "rr_gauss.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
     nvcc = _nvcc()
     ccbin = _host_cc()
     objs, rebuilt = [], False

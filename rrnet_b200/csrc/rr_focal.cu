@@ -10,7 +10,7 @@
 //              (config 3: 42 MB < 126 MB L2), so HBM sees 3 x 4 B/element in total.
 // Sums: fp32 per-thread partials over a few elements, then double precision across the block
 // and across blocks in a fixed order (last-block-done), so the loss is bit-reproducible.
-#include "rr_common.cuh"
+#include "rr_gauss.cuh"
 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -30,10 +30,10 @@ static int focal_grid(long long n) {
     long long cap = (long long)kSMs * 8;
     return (int)max(1LL, min(want, cap));
 }
-static FocalWs carve_focal(void* ws) {
+static FocalWs carve_focal(void* ws, size_t max_grid = (size_t)kSMs * 8) {
     Carver cv(ws);
     FocalWs w;
-    w.partial = cv.take<double>((size_t)kSMs * 8 * 3);
+    w.partial = cv.take<double>(max_grid * 3);
     w.ticket = cv.take<unsigned int>(1);
     w.bytes = cv.off;
     return w;
@@ -200,6 +200,120 @@ focal_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__
     focal_write_grads(logits, gt, n, scale, grad);
 }
 
+// --------------------------------------------------------------------------------------------
+// Fused target render + focal loss: the ground-truth heat-map is never materialised.
+// A CTA owns kFusedPix consecutive pixels of one (image, class) plane.  It filters the image's
+// annotation rows for its class into shared memory (geometry as rr_render.cu), every thread
+// evaluates gt = max over those objects' Gaussians for its 16 pixels in registers and feeds the
+// focal term (forward) or its derivative (backward).  HBM traffic: the logits once per pass
+// (+ the gradient write), B*max_n*32 bytes of annotations -- versus rendering the map (1 write)
+// and reading it back twice in the unfused sequence.
+// --------------------------------------------------------------------------------------------
+constexpr int kFusedPix = 4096;                    // pixels per CTA (16 per thread, four float4)
+constexpr int kFusedObj = 256;                     // objects staged per round
+
+struct FusedObj { float cxi, cyi, denom; int xa, xb, ya, yb; };
+
+template <bool kBackward>
+__device__ __forceinline__ void fused_body(const float* __restrict__ logits, const float* __restrict__ annos,
+                                           const int* __restrict__ n_obj, int max_n, int img_w, int Hh, int Wh,
+                                           float sf, int cls_num, int tiles, float scale, float* __restrict__ grad,
+                                           float* __restrict__ gt_out, float& pos, float& neg, int& npos) {
+    __shared__ FusedObj s_obj[kFusedObj];
+    __shared__ int s_nobj;
+    const int tid = threadIdx.x;
+    const int plane_id = blockIdx.x / tiles, tile = blockIdx.x - plane_id * tiles;     // plane = b * cls_num + c
+    const int b = plane_id / cls_num, c = plane_id - b * cls_num;
+    const int HW = Hh * Wh;
+    const int p0 = tile * kFusedPix + tid * 4;                                        // first of 4 consecutive pixels
+    const int row_lo = (tile * kFusedPix) / Wh, row_hi = min(tile * kFusedPix + kFusedPix - 1, HW - 1) / Wh;
+    float gt[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gt[q][e] = 0.f;
+    const int nb = min(n_obj[b], max_n);
+    for (int base = 0; base < nb; base += kFusedObj) {
+        __syncthreads();
+        if (tid == 0) s_nobj = 0;
+        __syncthreads();
+        const int k = base + tid;
+        if (k < nb) {
+            const ObjGauss o = obj_gauss(annos + ((size_t)b * max_n + k) * 8, img_w, Hh, Wh, sf, cls_num);
+            // keep the objects of this class whose window meets this CTA's rows
+            if (o.cls == c && o.xb > o.xa && o.yb > o.ya && o.yb > row_lo && o.ya <= row_hi) {
+                const int slot = atomicAdd(&s_nobj, 1);
+                s_obj[slot] = {o.cxi, o.cyi, o.denom, o.xa, o.xb, o.ya, o.yb};
+            }
+        }
+        __syncthreads();
+        const int n = s_nobj;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * (kFusedPix / 4);                                   // float4 index stride keeps loads coalesced
+            if (p >= HW) continue;
+            const int y = p / Wh, x0 = p - y * Wh;                                    // Wh % 4 == 0: the 4 pixels share a row
+            for (int j = 0; j < n; ++j) {
+                const FusedObj o = s_obj[j];
+                if (y < o.ya || y >= o.yb || x0 + 3 < o.xa || x0 >= o.xb) continue;   // quick reject for the whole group
+                const float dy = (float)y - o.cyi, dy2 = __fmul_rn(dy, dy);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int x = x0 + e;
+                    if (x >= o.xa && x < o.xb) {
+                        const float dx = (float)x - o.cxi;
+                        gt[q][e] = fmaxf(gt[q][e], expf(-__fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), dy2), o.denom)));
+                    }
+                }
+            }
+        }
+    }
+    const float* zp = logits + (size_t)plane_id * HW;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int p = p0 + q * (kFusedPix / 4);
+        if (p >= HW) continue;                                                        // HW % 4 == 0 (checked by the host)
+        const float4 z = __ldg(reinterpret_cast<const float4*>(zp + p));
+        if (gt_out) *reinterpret_cast<float4*>(gt_out + (size_t)plane_id * HW + p) = make_float4(gt[q][0], gt[q][1], gt[q][2], gt[q][3]);
+        if (kBackward) {
+            float4 o;
+            o.x = focal_grad(z.x, gt[q][0], scale); o.y = focal_grad(z.y, gt[q][1], scale);
+            o.z = focal_grad(z.z, gt[q][2], scale); o.w = focal_grad(z.w, gt[q][3], scale);
+            __stcs(reinterpret_cast<float4*>(grad + (size_t)plane_id * HW + p), o);
+        } else {
+            focal_term(z.x, gt[q][0], pos, neg, npos); focal_term(z.y, gt[q][1], pos, neg, npos);
+            focal_term(z.z, gt[q][2], pos, neg, npos); focal_term(z.w, gt[q][3], pos, neg, npos);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_render_forward_kernel(const float* __restrict__ logits, const float* __restrict__ annos,
+                            const int* __restrict__ n_obj, int max_n, int img_w, int Hh, int Wh, float sf,
+                            int cls_num, int tiles, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                            float* __restrict__ stats, float* __restrict__ gt_out) {
+    float pos = 0.f, neg = 0.f;
+    int npos = 0;
+    fused_body<false>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, 0.f, nullptr, gt_out, pos, neg, npos);
+    if (focal_block_reduce(pos, neg, npos, partial, ticket)) {
+        __threadfence();
+        focal_finish(partial, stats);
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_render_backward_kernel(const float* __restrict__ logits, const float* __restrict__ annos,
+                             const int* __restrict__ n_obj, int max_n, int img_w, int Hh, int Wh, float sf,
+                             int cls_num, int tiles, const float* __restrict__ stats, float upstream,
+                             float* __restrict__ grad) {
+    const float np = stats[3];
+    const float scale = upstream * ((np == 0.f) ? -1.0f : -1.0f / np);
+    float pos = 0.f, neg = 0.f;
+    int npos = 0;
+    fused_body<true>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, scale, grad, nullptr, pos, neg, npos);
+}
+
 }  // namespace rr
 
 using namespace rr;
@@ -264,6 +378,58 @@ RR_API int rr_focal_fwd_bwd(const float* logits, const float* gt, int64_t n, flo
     void* args[] = {(void*)&logits, (void*)&gt, (void*)&n_ll, (void*)&upstream, (void*)&w.partial,
                     (void*)&w.ticket, (void*)&stats, (void*)&grad};
     RR_CUDA(cudaLaunchCooperativeKernel((void*)focal_fwd_bwd_kernel, dim3(grid), dim3(kFocalThreads), args, 0, st), rc);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
+// ------------------------------------------------------------------ fused render + focal
+static int fused_dims(int B, int cls_num, int img_h, int img_w, int sf, int* Hh, int* Wh, int* tiles, long long* grid) {
+    if (B <= 0 || cls_num <= 0 || img_h <= 0 || img_w <= 0 || sf <= 0) return RR_E_BADARG;
+    *Hh = img_h / sf; *Wh = img_w / sf;
+    const long long HW = (long long)*Hh * *Wh;
+    if (HW <= 0 || (*Wh & 3)) return RR_E_RANGE;                     // rows are read as float4 groups
+    *tiles = (int)((HW + kFusedPix - 1) / kFusedPix);
+    *grid = (long long)B * cls_num * *tiles;
+    if (*grid > 0x7fffffffLL) return RR_E_RANGE;
+    return 0;
+}
+
+RR_API size_t rr_focal_render_workspace_bytes(int B, int cls_num, int img_h, int img_w, int scale_factor) {
+    int Hh, Wh, tiles; long long grid;
+    if (fused_dims(B, cls_num, img_h, img_w, scale_factor, &Hh, &Wh, &tiles, &grid)) return 0;
+    return carve_focal(nullptr, (size_t)grid).bytes;
+}
+
+RR_API int rr_focal_render_forward(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
+                                   int img_h, int img_w, int scale_factor, int cls_num,
+                                   float* stats, float* gt_out, void* ws, size_t ws_bytes, void* stream) {
+    int Hh, Wh, tiles; long long grid;
+    int rc = fused_dims(B, cls_num, img_h, img_w, scale_factor, &Hh, &Wh, &tiles, &grid);
+    if (rc) return rc;
+    if (!logits || !stats || !ws || max_n < 0 || (max_n > 0 && (!annos || !n_obj))) return RR_E_BADARG;
+    if (((uintptr_t)logits & 15) || ((uintptr_t)gt_out & 15)) return RR_E_ALIGN;
+    if (ws_bytes < carve_focal(nullptr, (size_t)grid).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    if (max_n == 0 && !n_obj) return RR_E_BADARG;                    // n_obj is always read (may hold zeros)
+    cudaStream_t st = (cudaStream_t)stream;
+    FocalWs w = carve_focal(ws, (size_t)grid);
+    RR_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st), rc);
+    focal_render_forward_kernel<<<(unsigned)grid, kFocalThreads, 0, st>>>(logits, annos, n_obj, max_n, img_w, Hh, Wh,
+                                                                         (float)scale_factor, cls_num, tiles,
+                                                                         w.partial, w.ticket, stats, gt_out);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
+RR_API int rr_focal_render_backward(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
+                                    int img_h, int img_w, int scale_factor, int cls_num,
+                                    const float* stats, float upstream, float* grad, void* stream) {
+    int Hh, Wh, tiles; long long grid;
+    int rc = fused_dims(B, cls_num, img_h, img_w, scale_factor, &Hh, &Wh, &tiles, &grid);
+    if (rc) return rc;
+    if (!logits || !stats || !grad || !n_obj || max_n < 0 || (max_n > 0 && !annos)) return RR_E_BADARG;
+    if (((uintptr_t)logits & 15) || ((uintptr_t)grad & 15)) return RR_E_ALIGN;
+    focal_render_backward_kernel<<<(unsigned)grid, kFocalThreads, 0, (cudaStream_t)stream>>>(
+        logits, annos, n_obj, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num, tiles, stats, upstream, grad);
     RR_LAUNCHED(rc);
     return rc;
 }

@@ -8,28 +8,9 @@
 // hm = max(hm, G).  max is commutative and G >= 0, so atomicMax on the uint bit pattern gives a
 // result that does not depend on the order objects are drawn in: bit-reproducible.
 // Built with --fmad=false; sqrtf and '/' are IEEE (nvcc defaults -prec-sqrt/-prec-div = true).
-#include "rr_common.cuh"
+#include "rr_gauss.cuh"
 
 namespace rr {
-
-// functional.py:177-198 with min_overlap = 0.7; python scalars enter the tensor ops as fp32
-__device__ __forceinline__ float gaussian_radius_f32(float height, float width) {
-    const float c_1m = (float)(1 - 0.7), c_1p = (float)(1 + 0.7);
-    const float b1 = __fadd_rn(height, width);
-    const float c1 = __fdiv_rn(__fmul_rn(__fmul_rn(width, height), c_1m), c_1p);
-    const float sq1 = __fsqrt_rn(__fsub_rn(__fmul_rn(b1, b1), __fmul_rn(4.0f, c1)));
-    const float r1 = __fmul_rn(__fadd_rn(b1, sq1), 0.5f);
-    const float b2 = __fmul_rn(2.0f, __fadd_rn(height, width));
-    const float c2 = __fmul_rn(__fmul_rn(c_1m, width), height);
-    const float sq2 = __fsqrt_rn(__fsub_rn(__fmul_rn(b2, b2), __fmul_rn(16.0f, c2)));
-    const float r2 = __fmul_rn(__fadd_rn(b2, sq2), 0.5f);
-    const float a3x4 = (float)(4 * (4 * 0.7));
-    const float b3 = __fmul_rn((float)(-2 * 0.7), __fadd_rn(height, width));
-    const float c3 = __fmul_rn(__fmul_rn((float)(0.7 - 1), width), height);
-    const float sq3 = __fsqrt_rn(__fsub_rn(__fmul_rn(b3, b3), __fmul_rn(a3x4, c3)));
-    const float r3 = __fmul_rn(__fadd_rn(b3, sq3), 0.5f);
-    return fminf(fminf(r1, r2), r3);
-}
 
 __global__ void __launch_bounds__(256)
 render_kernel(const float* __restrict__ annos, const int* __restrict__ n_obj, int B, int max_n,
@@ -41,45 +22,23 @@ render_kernel(const float* __restrict__ annos, const int* __restrict__ n_obj, in
     if (gw >= B * max_n) return;
     const int b = gw / max_n, k = gw - b * max_n;
     const bool live = k < n_obj[b];
-    const float* a = annos + (size_t)gw * 8;
-    float bw = 0.f, bh = 0.f, ox = 0.f, oy = 0.f, msk = 0.f, idx = 0.f, cxi = 0.f, cyi = 0.f, rad = 0.f;
-    int cls = -1;
-    if (live) {
-        float x1 = a[0], y1 = a[1];
-        float x2 = __fadd_rn(a[2], a[0]), y2 = __fadd_rn(a[3], a[1]);                 // :246-247
-        x1 = __fdiv_rn(x1, sf); y1 = __fdiv_rn(y1, sf); x2 = __fdiv_rn(x2, sf); y2 = __fdiv_rn(y2, sf);
-        bh = __fsub_rn(y2, y1); bw = __fsub_rn(x2, x1);                               // :250
-        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
-        cxi = floorf(cx); cyi = floorf(cy);
-        ox = __fsub_rn(cx, cxi); oy = __fsub_rn(cy, cyi);
-        msk = (bh > 0.f && bw > 0.f) ? 1.f : 0.f;
-        idx = __fadd_rn(__fmul_rn(cyi, (float)(img_w / 4)), cxi);                     // :257 hard-coded 4
-        rad = fmaxf(floorf(gaussian_radius_f32(ceilf(bh), ceilf(bw))), 0.f);          // :258-259
-        cls = (int)__fsub_rn(a[5], 1.f);
-        if (cls < 0) cls += cls_num;                                                  // python negative index
-    }
+    ObjGauss o;
+    o.bw = o.bh = o.ox = o.oy = o.msk = o.idx = 0.f;
+    o.cls = -1;
+    if (live) o = obj_gauss(annos + (size_t)gw * 8, img_w, Hh, Wh, sf, cls_num);
     if (lane == 0) {                               // padded rows are zero, like the reference collate
-        wh[(size_t)gw * 2] = bw; wh[(size_t)gw * 2 + 1] = bh;
-        offset[(size_t)gw * 2] = ox; offset[(size_t)gw * 2 + 1] = oy;
-        reg_mask[gw] = msk;
-        ind[gw] = idx;
+        wh[(size_t)gw * 2] = o.bw; wh[(size_t)gw * 2 + 1] = o.bh;
+        offset[(size_t)gw * 2] = o.ox; offset[(size_t)gw * 2 + 1] = o.oy;
+        reg_mask[gw] = o.msk;
+        ind[gw] = o.idx;
     }
-    if (!live || cls < 0 || cls >= cls_num) return;
+    if (!live || o.cls < 0 || o.xb <= o.xa || o.yb <= o.ya) return;
     // draw_umich_gaussian :212-227
-    const float sigma = __fdiv_rn(__fadd_rn(__fmul_rn(2.f, rad), 1.f), 6.f);
-    const float denom = __fmul_rn(__fmul_rn(2.f, sigma), sigma);
-    const float left = fminf(cxi, rad), right = fminf((float)Wh - cxi, rad + 1.f);
-    const float top = fminf(cyi, rad), bottom = fminf((float)Hh - cyi, rad + 1.f);
-    const int ya = (int)(cyi - top), yb = min((int)(cyi + bottom), Hh);
-    const int xa = (int)(cxi - left), xb = min((int)(cxi + right), Wh);
-    if (ya < 0 || xa < 0 || yb <= ya || xb <= xa) return;
-    unsigned int* plane = reinterpret_cast<unsigned int*>(hm + ((size_t)b * cls_num + cls) * Hh * Wh);
-    const int ww = xb - xa, total = ww * (yb - ya);
+    unsigned int* plane = reinterpret_cast<unsigned int*>(hm + ((size_t)b * cls_num + o.cls) * Hh * Wh);
+    const int ww = o.xb - o.xa, total = ww * (o.yb - o.ya);
     for (int t = lane; t < total; t += 32) {
-        const int y = ya + t / ww, x = xa + t % ww;
-        const float dx = (float)x - cxi, dy = (float)y - cyi;
-        const float g = expf(-__fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), denom));
-        atomicMax(plane + (size_t)y * Wh + x, __float_as_uint(g));
+        const int y = o.ya + t / ww, x = o.xa + t % ww;
+        atomicMax(plane + (size_t)y * Wh + x, __float_as_uint(obj_value(o, y, x)));
     }
 }
 

@@ -36,3 +36,28 @@ def focal_loss_for_hm(pred, gt):
     clamp, which is where the reference itself has non-zero gradient).  Prefer focal_loss_for_hm_logits."""
     p = pred.clamp(1e-4, 1 - 1e-4)
     return focal_loss_for_hm_logits(torch.log(p) - torch.log1p(-p), gt)
+
+
+class _FocalHMFromAnnos(torch.autograd.Function):
+    """Heat-map focal loss from the padded annotations: target render fused into the loss kernels, the
+    [B,cls,h,w] target map is never materialised (rr_focal_render_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, logits, annos, n_obj, img_h, img_w, scale_factor):
+        stats = ops.focal_render_forward(logits.detach(), annos, n_obj, img_h, img_w, scale_factor)
+        ctx.save_for_backward(logits, annos, n_obj, stats)
+        ctx.dims = (img_h, img_w, scale_factor)
+        return stats[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, annos, n_obj, stats = ctx.saved_tensors
+        img_h, img_w, sf = ctx.dims
+        grad = ops.focal_render_backward(logits.detach(), annos, n_obj, img_h, img_w, stats, 1.0, sf)
+        return grad * g, None, None, None, None, None
+
+
+def focal_loss_for_hm_from_annos(logits, annos, n_obj, img_h, img_w, scale_factor=4):
+    """criterion's heat-map term without a rendered target: logits [B,cls,h,w], annos [B,max_n,8] (the
+    collate layout, datasets/drones_det.py:70-94), n_obj [B] int32."""
+    return _FocalHMFromAnnos.apply(logits, annos, n_obj, img_h, img_w, scale_factor)

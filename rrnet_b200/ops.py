@@ -351,3 +351,30 @@ def focal_fwd_bwd(logits, gt, upstream=1.0):
     check(L.rr_focal_fwd_bwd(_ptr(logits), _ptr(gt), logits.numel(), float(upstream), _ptr(stats), _ptr(grad),
                              _ptr(ws), ws.numel(), _stream()), "rr_focal_fwd_bwd")
     return stats, grad
+
+
+def focal_render_forward(logits, annos, n_obj, img_h, img_w, scale_factor=4, want_gt=False):
+    """Heat-map focal loss straight from the padded annotations (the target map is rendered on the fly and
+    never stored).  logits [B,cls,h,w], annos [B,max_n,8], n_obj [B] int32 -> stats [4] (+ gt map if want_gt)."""
+    logits, annos, n_obj = _f32(logits, "logits", 4), _f32(annos, "annos", 3), _i32(n_obj, "n_obj")
+    B, C, h, w = logits.shape
+    if h != img_h // scale_factor or w != img_w // scale_factor or annos.shape[0] != B or annos.shape[2] != 8:
+        raise RRNetB200Error("logits must be [B,cls,img_h/sf,img_w/sf] and annos [B,max_n,8]")
+    L = _lib.lib()
+    stats = torch.empty(4, dtype=torch.float32, device=logits.device)
+    gt = torch.empty_like(logits) if want_gt else None
+    ws = _ws(L.rr_focal_render_workspace_bytes(B, C, int(img_h), int(img_w), int(scale_factor)), logits.device)
+    check(L.rr_focal_render_forward(_ptr(logits), _ptr(annos), _ptr(n_obj), B, annos.shape[1], int(img_h), int(img_w),
+                                    int(scale_factor), C, _ptr(stats), _ptr(gt), _ptr(ws), ws.numel(), _stream()),
+          "rr_focal_render_forward")
+    return (stats, gt) if want_gt else stats
+
+
+def focal_render_backward(logits, annos, n_obj, img_h, img_w, stats, upstream=1.0, scale_factor=4):
+    logits, annos, n_obj = _f32(logits, "logits", 4), _f32(annos, "annos", 3), _i32(n_obj, "n_obj")
+    B, C, h, w = logits.shape
+    grad = torch.empty_like(logits)
+    check(_lib.lib().rr_focal_render_backward(_ptr(logits), _ptr(annos), _ptr(n_obj), B, annos.shape[1], int(img_h),
+                                              int(img_w), int(scale_factor), C, _ptr(_f32(stats, "stats")),
+                                              float(upstream), _ptr(grad), _stream()), "rr_focal_render_backward")
+    return grad

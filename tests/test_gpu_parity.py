@@ -581,3 +581,37 @@ def test_focal_odd_length(ops, oracle_mod):
     # 16-byte alignment is required of the base pointers only
     loss, _, grad = oracle_mod.focal(z.numpy(), gt.numpy(), want_grad=True)
     _check_focal(ops, z.numpy(), gt.numpy(), loss, grad)
+
+
+def test_focal_render_fused_vs_unfused_and_oracle(ops, oracle_mod):
+    """Fused target render + focal loss (config 3 shape): same loss / gradient as render -> focal, the on-the-fly
+    target equals the rendered one bit for bit, and the loss matches the CPU oracle."""
+    B, C, img = 32, 10, 512
+    annos_l = synth.train_annos(B, img, img, synth.SEED_C3)
+    annos, n_obj = synth.pad_annos(annos_l)
+    g = torch.Generator().manual_seed(synth.SEED_C3)
+    z = torch.randn(B, C, img // 4, img // 4, generator=g) * 2.5 - 2.0
+    zd, ad, nd = dev(z), dev(annos), dev(n_obj)
+    gt = ops.render_targets(ad, nd, img, img)[0]
+    stats_u, grad_u = ops.focal_fwd_bwd(zd, gt, 0.5)
+    stats_f, gt_f = ops.focal_render_forward(zd, ad, nd, img, img, want_gt=True)
+    assert torch.equal(gt_f, gt)
+    grad_f = ops.focal_render_backward(zd, ad, nd, img, img, stats_f, 0.5)
+    assert float(stats_f[3]) == float(stats_u[3])                                     # num_pos
+    assert abs(float(stats_f[0]) - float(stats_u[0])) <= 1e-6 * abs(float(stats_u[0]))
+    assert rel_err(npy(grad_f), npy(grad_u), floor=1e-3) < 1e-6
+    gts = np.stack([oracle_mod.render(a.numpy(), img, img)["hm"] for a in annos_l])
+    loss, _, gref = oracle_mod.focal(z.numpy(), gts, want_grad=True)
+    assert abs(float(stats_f[0]) - loss) / abs(loss) < TOL
+    assert rel_err(npy(grad_f) / 0.5, gref, floor=1e-3) < TOL
+
+
+def test_focal_render_no_objects_and_odd_plane(ops):
+    z = torch.randn(2, 3, 10, 12, generator=torch.Generator().manual_seed(5)).cuda()   # 120 pixels per plane, < one CTA
+    annos = torch.zeros(2, 1, 8).cuda()
+    n_obj = torch.zeros(2, dtype=torch.int32).cuda()
+    stats = ops.focal_render_forward(z, annos, n_obj, 40, 48)
+    ref = ops.focal_forward(z, torch.zeros_like(z))
+    assert float(stats[3]) == 0.0 and abs(float(stats[0]) - float(ref[0])) <= 1e-6 * abs(float(ref[0]))
+    with pytest.raises(Exception):
+        ops.focal_render_forward(torch.zeros(1, 1, 4, 5).cuda(), annos[:1], n_obj[:1], 16, 20)   # row length 5: not a multiple of 4

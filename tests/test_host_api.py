@@ -240,6 +240,11 @@ def test_criterion_golden(host):
     hm_l, wh_l, off_l, s2_l = op.criterion(outs, targets)
     got = np.array([float(hm_l), float(wh_l), float(off_l), float(s2_l)])
     assert np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])) < 2e-5, (got, g["losses"])
+    # the fused form of the heat-map term (target rendered on the fly inside the loss) gives the same number
+    from rrnet_b200.host.modules.loss.functional import focal_loss_for_hm_from_annos
+    hm2 = x["hm"].clone().requires_grad_(True)
+    fused = focal_loss_for_hm_from_annos(hm2, torch.from_numpy(g["annos"]).cuda(), n_obj, H * 4, W * 4)
+    assert abs(float(fused) - g["losses"][0]) / g["losses"][0] < 2e-5
     (hm_l + 0.1 * wh_l + off_l + s2_l).backward()
     assert rel_err(npy(hm.grad), g["grad_hm"], floor=1e-3) < 1e-4
     assert rel_err(npy(wh.grad), g["grad_wh"], floor=1e-3) < 1e-4
