@@ -88,24 +88,34 @@ stage1_partition_kernel(const float* __restrict__ dets, int K, int C,
 // Generic API: stable sort by score (desc) inside each segment by rank counting
 // (rank_i = #{j in segment : s_j > s_i or (s_j == s_i and j < i)}), O(n^2) compares, no library.
 // --------------------------------------------------------------------------------------------
+constexpr int kRankSplit = 8;                     // threads that share one element's rank count
+
 __global__ void __launch_bounds__(256)
 rank_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                  const int* __restrict__ seg_offsets, int M, int S,
                  float4* __restrict__ sbox, int* __restrict__ slab, int* __restrict__ ssrc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    int lo = 0, hi = S;                              // largest s with seg_offsets[s] <= i
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (seg_offsets[mid] <= i) lo = mid; else hi = mid;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt / kRankSplit, part = gt % kRankSplit;     // the kRankSplit threads of an element sit in one warp
+    const bool on = i < M;
+    int lo = 0, s0 = 0, s1 = 0;
+    float si = 0.f;
+    if (on) {
+        int hi = S;                                  // largest s with seg_offsets[s] <= i
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (seg_offsets[mid] <= i) lo = mid; else hi = mid;
+        }
+        s0 = seg_offsets[lo]; s1 = seg_offsets[lo + 1];
+        si = scores[i];
     }
-    const int s0 = seg_offsets[lo], s1 = seg_offsets[lo + 1];
-    const float si = scores[i];
     int rank = 0;
-    for (int j = s0; j < s1; ++j) {
+    for (int j = s0 + part; j < s1; j += kRankSplit) {
         float sj = __ldg(scores + j);
         rank += (sj > si) || (sj == si && j < i);
     }
+#pragma unroll
+    for (int o = kRankSplit / 2; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (!on || part != 0) return;
     int pos = s0 + rank;
     const float* bx = boxes + (size_t)i * 4;
     sbox[pos] = make_float4(bx[0], bx[1], bx[2], bx[3]);
@@ -187,7 +197,7 @@ nms_mask_kernel(const float4* __restrict__ sbox, const int* __restrict__ slab,
 // Greedy reduce of one segment (one CTA).  keep_out[g*Kmax + s0 + t] = t-th accepted box of
 // the segment: its list position, or map[position] when `map` is given.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ seg_off,
                 int segs_per_group, int Kmax, int W, const int* __restrict__ map,
                 int* __restrict__ keep_out, int* __restrict__ keep_cnt) {
@@ -239,23 +249,28 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
-        for (int w = t + 1 + tid; w <= t1; w += blockDim.x) {
-            unsigned long long acc = 0ull, kk = kept;
-            while (kk) {                                   // 8 independent loads in flight
-                unsigned long long v[8];
+        // OR the kept rows' mask words into remv for every later tile.  The 64 rows are split in 4 groups of
+        // 16 bits handled by different threads (up to 16 independent loads in flight each) and merged with a
+        // shared-memory atomicOr, so a tile costs one or two L2 round trips instead of eight.
+        const int nw = t1 - t;                               // words t+1 .. t1
+        for (int it = tid; it < nw * 4; it += blockDim.x) {
+            const int w = t + 1 + (it >> 2), grp = it & 3;
+            unsigned long long kk = (kept >> (16 * grp)) & 0xffffull;
+            if (!kk) continue;
+            unsigned long long v[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    v[u] = 0ull;
-                    if (kk) {
-                        int bit = __ffsll((long long)kk) - 1;
-                        kk &= kk - 1ull;
-                        v[u] = m[(size_t)(row0 + bit) * W + w];
-                    }
+            for (int u = 0; u < 16; ++u) {
+                v[u] = 0ull;
+                if (kk) {
+                    int bit = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1ull;
+                    v[u] = m[(size_t)(row0 + 16 * grp + bit) * W + w];
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc |= v[u];
             }
-            s_remv[w] |= acc;
+            unsigned long long acc = 0ull;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc |= v[u];
+            if (acc) atomicOr(&s_remv[w], acc);
         }
         // the next iteration's first barrier orders these s_remv writes before they are read
     }
@@ -326,7 +341,7 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
         if (smem > 200 * 1024) return RR_E_RANGE;
         RR_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     }
-    nms_scan_kernel<<<gs, 256, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, map, keep_out, keep_cnt);
+    nms_scan_kernel<<<gs, 1024, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, map, keep_out, keep_cnt);
     RR_LAUNCHED(rc);
     return rc;
 }
@@ -427,7 +442,7 @@ RR_API int rr_nms_batched(const float* boxes, const float* scores, const int32_t
     if (!boxes || !scores || !keep_idx || !ws) return RR_E_BADARG;
     if (ws_bytes < carve_generic(nullptr, M).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     GenericWs w = carve_generic(ws, M);
-    rank_sort_kernel<<<(M + 255) / 256, 256, 0, st>>>(boxes, scores, seg_offsets, M, S, w.sbox, w.slab, w.ssrc);
+    rank_sort_kernel<<<(int)(((long long)M * kRankSplit + 255) / 256), 256, 0, st>>>(boxes, scores, seg_offsets, M, S, w.sbox, w.slab, w.ssrc);
     RR_LAUNCHED(rc);
     int r2 = launch_mask_scan(w.sbox, w.slab, seg_offsets, 1, S, M, M, thr, pixel_offset, ge_cmp, w.mask,
                               w.ssrc, keep_idx, keep_count, st);
