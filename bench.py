@@ -476,7 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
     ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
