@@ -615,3 +615,60 @@ def test_focal_render_no_objects_and_odd_plane(ops):
     assert float(stats[3]) == 0.0 and abs(float(stats[0]) - float(ref[0])) <= 1e-6 * abs(float(ref[0]))
     with pytest.raises(Exception):
         ops.focal_render_forward(torch.zeros(1, 1, 4, 5).cuda(), annos[:1], n_obj[:1], 16, 20)   # row length 5: not a multiple of 4
+
+
+# ===================================================================== edge cases across the path
+def test_eval_path_tiny_and_degenerate_inputs(ops, oracle_mod):
+    """B=1, K=1 on a 4x4 map; a map of identical logits (massive ties -> exact fallback); wh all negative
+    (every box degenerate: zero area, NaN IoU never suppresses, RoIs of size 0 still sample one point)."""
+    hp = synth.head_params(3)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    g = torch.Generator().manual_seed(8)
+    # (1) tiny
+    hm = torch.randn(1, 3, 4, 4, generator=g)
+    wh = torch.rand(1, 2, 4, 4, generator=g) * 3
+    off = torch.rand(1, 2, 4, 4, generator=g)
+    feat = torch.randn(1, 256, 4, 4, generator=g)
+    path = ops.EvalPath(1, 3, 4, 4, 1, folded, keep_roi_feat=True)
+    path.forward(dev(hm), dev(wh), dev(off), dev(feat))
+    r = path.results()
+    dets, _, _ = oracle_mod.decode(hm.numpy(), wh.numpy(), off.numpy(), 1)
+    assert r["n"] == 1 and np.array_equal(npy(r["bxyxy"])[0, 1:], dets[0, 0, :4])
+    roi = oracle_mod.roi_align(feat.numpy(), npy(r["bxyxy"]), relu=True)
+    assert rel_err(npy(path.roi_feat[:1]), roi, floor=1e-3) < TOL
+    # (2) degenerate boxes: wh < 0 everywhere -> clamp(min=0) -> x1 == x2, y1 == y2
+    B, C, H, W, K = 2, 4, 24, 40, 64
+    x = synth.eval_inputs(B, H, W, K, 77, C=C)
+    x["wh"] = -x["wh"].abs()
+    path = ops.EvalPath(B, C, H, W, K, folded, keep_roi_feat=True)
+    path.forward(*[dev(x[k]) for k in ("hm", "wh", "off", "feat")])
+    r = path.results()
+    dets, _, _ = oracle_mod.decode(x["hm"].numpy(), x["wh"].numpy(), x["off"].numpy(), K)
+    rows = []
+    for b in range(B):
+        kept, _ = oracle_mod.stage1_nms(dets[b], C, 0.7)
+        assert kept.shape[0] == K                       # zero-area boxes never suppress each other
+        rows.append(np.concatenate([np.full((K, 1), b, np.float32), kept[:, :4]], 1))
+    bxyxy = np.concatenate(rows)
+    np.testing.assert_array_equal(npy(r["bxyxy"]), bxyxy)
+    roi = oracle_mod.roi_align(x["feat"].numpy(), bxyxy, relu=True)
+    assert rel_err(npy(path.roi_feat[: r["n"]]), roi, floor=1e-3) < TOL
+    reg = oracle_mod.head(roi, {k: v.numpy() for k, v in hp.items()})
+    assert rel_err(npy(r["reg"]), reg, floor=1.0) < TOL
+    # (3) constant heat-map: every score ties; canonical order = flat index ascending, still K rows per image
+    hm_c = torch.full((1, 2, 8, 8), -1.25)
+    d, inds = ops.decode_topk(dev(hm_c), dev(torch.ones(1, 2, 8, 8)), dev(torch.zeros(1, 2, 8, 8)), 20)
+    assert npy(inds)[0].tolist() == list(range(20)) and float(d[0, :, 5].max()) == 0.0
+
+
+def test_zero_rois_are_a_no_op(ops):
+    feat = torch.randn(1, 32, 8, 8).cuda()
+    assert tuple(ops.roi_align(feat, torch.zeros(0, 5).cuda()).shape) == (0, 32, 3, 3)
+    hp = synth.head_params(1)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    assert tuple(ops.head_forward(torch.zeros(0, 256, 3, 3).cuda(), folded).shape) == (0, 4)
+    n_dev = torch.zeros(1, dtype=torch.int32).cuda()               # capacity 5, live count 0: outputs untouched
+    out = ops.roi_align(feat, torch.rand(5, 5).cuda(), n_dev=n_dev)
+    assert tuple(out.shape) == (5, 32, 3, 3)
+    s1, s2 = ops.generate_bbox(torch.zeros(0, 5).cuda(), torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0).cuda())
+    assert s1.shape[0] == 0 and s2.shape[0] == 0
