@@ -285,7 +285,7 @@ def run_product(args):
     host = {k: v.pin_memory() for k, v in x.items()}           # e2e inputs live in pinned host memory
     d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     folded = ops.head_fold({k: v.to(dev) for k, v in hp.items()})
-    path = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo)
+    path = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo, head_algo=args.head_algo)
     gathered = gathered_cnt = None
     if world > 1:
         gathered = torch.empty(world * B * K, 6, dtype=torch.float32, device=dev)
@@ -479,6 +479,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
+    ap.add_argument("--head-algo", type=int, default=0, help="0 tcgen05 tensor-core head (default), 1 fp32 FFMA head")
     ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -149,18 +149,21 @@ int rr_roi_align(const float* feat, const float* rois, const int32_t* n_rois_dev
  * FasterRCNNDetector.forward -> Bottleneck.forward (models/rrnet.py:155-157,
  * detectors/fasterrcnn_detector.py:13-18, backbones/resnet.py:33-53).
  * rr_head_fold folds the three BatchNorms (running stats, eps 1e-5) into the convolutions
- * once; parameters use the reference's state_dict layouts:
+ * once and also prepares the (hi, lo) tf32 weight tiles of the tensor-core kernel; parameters use
+ * the reference's state_dict layouts:
  *   w1 [64,256]  bn1 [4,64]  (rows gamma,beta,running_mean,running_var)
  *   w2 [64,64,3,3] bn2 [4,64]   w3 [256,64] bn3 [4,256]   wr [4,256]  br [4]
- * folded: rr_head_folded_floats() floats, opaque layout.
+ * folded: rr_head_folded_floats() floats, opaque layout, 16-byte aligned.
  *   roi_feat [n_cap,256,3,3] -> reg [n_cap,4]
+ *   algo: 0 = tcgen05 tensor cores, fp32 accuracy through a 3xTF32 split (default),
+ *         1 = fp32 FFMA kernel.
  * ---------------------------------------------------------------------------------------- */
 size_t rr_head_folded_floats(void);
 int rr_head_fold(const float* w1, const float* bn1, const float* w2, const float* bn2,
                  const float* w3, const float* bn3, const float* wr, const float* br,
                  float* folded, void* stream);
 int rr_head_forward(const float* roi_feat, const int32_t* n_rois_dev, int n_cap,
-                    const float* folded, float* reg, void* stream);
+                    const float* folded, int algo, float* reg, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Box decode of stage 2: replaces RRNetOperator.generate_bbox
@@ -178,7 +181,8 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
  * generate_bbox, i.e. RRNet.forward after forward_stage1 (models/rrnet.py:31-54) plus
  * RRNetOperator.generate_bbox for every image.  All launches go to `stream`, no host sync.
  * Outputs have capacity B*K rows; counts [B+1] as in rr_stage1_nms.
- * roi_feat may be NULL (the workspace then holds it).  roi_algo as in rr_roi_align.
+ * roi_feat may be NULL (the workspace then holds it).  roi_algo: bit 0 as in rr_roi_align (1 = direct
+ * gather), bit 1 selects the head kernel (0 = tcgen05, 2 = fp32 FFMA).
  * stage_events: NULL, or 6 cudaEvent_t handles (as void*) recorded on `stream` before decode and
  * after decode, stage-1 NMS, RoIAlign, head and generate_bbox (a per-stage timing hook; recording
  * an event does not synchronise).

@@ -31,7 +31,7 @@ SIGNATURES = {
     "rr_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
     "rr_head_folded_floats": (c_size_t, []),
     "rr_head_fold": (c_int, [P] * 9 + [P]),
-    "rr_head_forward": (c_int, [P, P, c_int, P, P, P]),
+    "rr_head_forward": (c_int, [P, P, c_int, P, c_int, P, P]),
     "rr_generate_bbox": (c_int, [P, P, P, P, P, c_int, c_float, P, P, P]),
     "rr_eval_workspace_bytes": (c_size_t, [c_int] * 6),
     "rr_eval_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,

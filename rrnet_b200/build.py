@@ -27,6 +27,7 @@ UNITS = {
     "rr_softnms.cu": ["--fmad=false"],
     "rr_roialign.cu": ["--fmad=false"],
     "rr_head.cu": [],
+    "rr_head_tc.cu": [],
     "rr_bbox.cu": ["--fmad=false"],
     "rr_render.cu": ["--fmad=false"],
     "rr_focal.cu": [],
@@ -59,7 +60,7 @@ def _digest(paths, flags):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(CSRC, "rr_gauss.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
+    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(CSRC, "rr_gauss.cuh"), os.path.join(CSRC, "rr_head.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
     nvcc = _nvcc()
     ccbin = _host_cc()
     objs, rebuilt = [], False

@@ -18,9 +18,9 @@ int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, 
                      cudaStream_t);
 void roi_align_ws_views(void*, int, int, int, int, int, const float**, const int**, const int**, const float**);
 int head_forward_launch_partial(const float*, const float*, const int*, const int*, const float*, const int32_t*, int,
-                                const float*, float*, cudaStream_t);
+                                const float*, float*, int, cudaStream_t);
 size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W);
-int head_forward_launch(const float*, const int32_t*, int, const float*, float*, cudaStream_t);
+int head_forward_launch(const float*, const int32_t*, int, const float*, float*, int, cudaStream_t);
 int generate_bbox_launch(const float*, const float*, const float*, const float*, const int32_t*, int, float,
                          float*, float*, cudaStream_t);
 
@@ -76,7 +76,9 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
         return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
     if (feat_ch != RR_HEAD_CH) return RR_E_RANGE;               // the head is 256-channel (fasterrcnn_detector.py:9)
-    if ((pool != 0 && pool != 3) || roi_algo < 0 || roi_algo > 1) return RR_E_BADARG;
+    if ((pool != 0 && pool != 3) || roi_algo < 0 || roi_algo > 3) return RR_E_BADARG;
+    const int head_algo = (roi_algo >> 1) & 1;       // bit 1: fp32 FFMA head instead of the tcgen05 one
+    roi_algo &= 1;                                    // bit 0: direct-gather RoIAlign
     if (C > RR_MAX_CLASSES || K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;
     if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
     if (ws_bytes < carve_eval(nullptr, B, K, C, H, W, feat_ch).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
@@ -106,9 +108,9 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     if (fused) {
         const float* partial; const int* slot; const int* pieces; const float* count;
         roi_align_ws_views(w.roi, n_cap, B, feat_ch, H, W, &partial, &slot, &pieces, &count);
-        rc = head_forward_launch_partial(rf, partial, slot, pieces, count, n_dev, n_cap, head_folded, out_reg, st);
+        rc = head_forward_launch_partial(rf, partial, slot, pieces, count, n_dev, n_cap, head_folded, out_reg, head_algo, st);
     } else {
-        rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, st);
+        rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, head_algo, st);
     }
     if (rc) return rc;
     mark(4);

@@ -8,7 +8,7 @@
 //
 // rr_head_fold folds the eval-mode BatchNorms into the convolutions once:
 //     bn(z) = (z - mean) / sqrt(var + 1e-5) * gamma + beta  ->  W' = W * s, b' = beta - mean * s.
-// Folded block layout (floats):
+// Folded block layout (floats; rr_head.cuh), followed by the tensor-core weight image of rr_head_tc.cu:
 //     [W1 : 256 x 64  (k-major)] [b1 : 64]
 //     [W2 : 64 cin x 9 taps x 64 cout] [b2 : 64]
 //     [W3 : 64 x 256  (k-major)] [b3 : 256]
@@ -17,19 +17,9 @@
 // folded weights per RoI from L2 = 3.2 GB per config-2 step); staging each weight chunk once per CTA in
 // shared memory for 16 RoIs cuts it 16x.  The 3x3 convolution on the zero-padded 3x3 map only issues
 // the 49 valid (tap, pixel) products.
-#include "rr_common.cuh"
+#include "rr_head.cuh"
 
 namespace rr {
-
-constexpr int kOffW1 = 0;
-constexpr int kOffB1 = kOffW1 + 256 * 64;
-constexpr int kOffW2 = kOffB1 + 64;
-constexpr int kOffB2 = kOffW2 + 9 * 64 * 64;
-constexpr int kOffW3 = kOffB2 + 64;
-constexpr int kOffB3 = kOffW3 + 64 * 256;
-constexpr int kOffWr = kOffB3 + 256;
-constexpr int kOffBr = kOffWr + 4 * 256;
-constexpr int kFoldedFloats = kOffBr + 4;
 
 constexpr int kHeadWarps = 16;                   // RoIs per CTA (one warp each); weights are shared by all of them
 constexpr int kHeadThreads = kHeadWarps * 32;
@@ -67,16 +57,6 @@ __global__ void head_fold_kernel(const float* __restrict__ w1, const float* __re
     if (i < 1024) f[kOffWr + i] = wr[i];
     if (i < 4) f[kOffBr + i] = br[i];
 }
-
-// Where a RoI's 256x9 input comes from: the materialised RoIAlign output, or (fused eval path) the
-// partial slots of the tile-centric RoIAlign, summed here in slot order and divided by the sample count.
-struct HeadSrc {
-    const float* roi_feat;     // [n_cap,256,3,3]; read when partial == nullptr or slot[n] < 0 (direct-path RoI)
-    const float* partial;      // [slot][9][256] or nullptr
-    const int* slot;           // [n_cap] first slot, < 0: direct path
-    const int* pieces;         // [n_cap] number of slots (0: all-zero output)
-    const float* count;        // [n_cap] divisor
-};
 
 // x[c][0..8] of RoI n for channel c = 32*j + lane  (9 values per lane)
 __device__ __forceinline__ void head_load_x(const HeadSrc& src, int n, int sb, int pieces, float cnt, int j, int lane,
@@ -288,8 +268,8 @@ head_forward_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     }
 }
 
-int head_forward_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded,
-                            float* reg, cudaStream_t st) {
+int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded,
+                         float* reg, cudaStream_t st) {
     int rc = 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -302,18 +282,21 @@ int head_forward_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, c
     return rc;
 }
 
+// algo: 0 = tcgen05 tensor cores (3xTF32), 1 = fp32 FFMA
 int head_forward_launch(const float* roi_feat, const int32_t* n_rois_dev, int n_cap, const float* folded,
-                        float* reg, cudaStream_t st) {
+                        float* reg, int algo, cudaStream_t st) {
     HeadSrc src = {roi_feat, nullptr, nullptr, nullptr, nullptr};
-    return head_forward_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
+    return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
+                     : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }
 
 // fused eval path: inputs straight from the tile-centric RoIAlign's partial slots
 int head_forward_launch_partial(const float* roi_feat, const float* partial, const int* slot, const int* pieces,
                                 const float* count, const int32_t* n_rois_dev, int n_cap, const float* folded,
-                                float* reg, cudaStream_t st) {
+                                float* reg, int algo, cudaStream_t st) {
     HeadSrc src = {roi_feat, partial, slot, pieces, count};
-    return head_forward_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
+    return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
+                     : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }
 
 }  // namespace rr
@@ -329,13 +312,14 @@ RR_API int rr_head_fold(const float* w1, const float* bn1, const float* w2, cons
     int rc = 0;
     head_fold_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1, bn1, w2, bn2, w3, bn3, wr, br, folded);
     RR_LAUNCHED(rc);
-    return rc;
+    const int r2 = head_fold_tc_launch(folded, (cudaStream_t)stream);     // (hi, lo) tf32 weight tiles for the tensor-core kernel
+    return rc ? rc : r2;
 }
 
 RR_API int rr_head_forward(const float* roi_feat, const int32_t* n_rois_dev, int n_cap,
-                           const float* folded, float* reg, void* stream) {
+                           const float* folded, int algo, float* reg, void* stream) {
     if (n_cap == 0) return 0;
-    if (!roi_feat || !folded || !reg || n_cap < 0) return RR_E_BADARG;
+    if (!roi_feat || !folded || !reg || n_cap < 0 || algo < 0 || algo > 1) return RR_E_BADARG;
     if (((uintptr_t)reg & 15) || ((uintptr_t)folded & 15)) return RR_E_ALIGN;
-    return head_forward_launch(roi_feat, n_rois_dev, n_cap, folded, reg, (cudaStream_t)stream);
+    return head_forward_launch(roi_feat, n_rois_dev, n_cap, folded, reg, algo, (cudaStream_t)stream);
 }

@@ -207,7 +207,9 @@ def head_params_from_module(head_detector):
     }
 
 
-def head_forward(roi_feat, folded, n_dev=None):
+def head_forward(roi_feat, folded, n_dev=None, algo=0):
+    """Re-regression head on [n,256,3,3] RoI features -> [n,4].  algo 0 = tcgen05 tensor cores (3xTF32),
+    1 = fp32 FFMA."""
     roi_feat = _f32(roi_feat, "roi_feat", 4)
     n = roi_feat.shape[0]
     if tuple(roi_feat.shape[1:]) != (256, 3, 3):
@@ -215,7 +217,9 @@ def head_forward(roi_feat, folded, n_dev=None):
     reg = torch.empty(n, 4, dtype=torch.float32, device=roi_feat.device)
     if n_dev is not None:
         n_dev = _i32(n_dev, "n_dev")
-    check(_lib.lib().rr_head_forward(_ptr(roi_feat), _ptr(n_dev), n, _ptr(_f32(folded, "folded")), _ptr(reg),
+    if n == 0:
+        return reg
+    check(_lib.lib().rr_head_forward(_ptr(roi_feat), _ptr(n_dev), n, _ptr(_f32(folded, "folded")), int(algo), _ptr(reg),
                                      _stream()), "rr_head_forward")
     return reg
 
@@ -239,12 +243,12 @@ class EvalPath:
     RoIAlign+ReLU -> head -> generate_bbox in one C-ABI call (rr_eval_forward).  CUDA-graph capturable."""
 
     def __init__(self, B, C, H, W, K, head_folded, feat_ch=256, pool=0, nms_thr=0.7, scale=4.0, device=None,
-                 keep_roi_feat=False, roi_algo=0):
+                 keep_roi_feat=False, roi_algo=0, head_algo=0):
         L = _lib.lib()
         dev = torch.device(device if device is not None else "cuda")
         self.shape = (B, C, H, W, K, feat_ch)
         self.pool, self.nms_thr, self.scale = int(pool), float(nms_thr), float(scale)
-        self.roi_algo = int(roi_algo)
+        self.roi_algo = int(roi_algo) | (int(head_algo) << 1)     # bit 0: direct RoIAlign, bit 1: FFMA head
         self.folded = _f32(head_folded, "head_folded")
         n = B * K
         f32 = dict(dtype=torch.float32, device=dev)

@@ -294,14 +294,15 @@ def test_roi_align_device_count_and_huge_roi(ops, oracle_mod, algo):
 
 
 # ===================================================================== head (a7)
-def test_head_golden_and_oracle(ops, oracle_mod):
+@pytest.mark.parametrize("algo", [0, 1])          # 0 = tcgen05 (3xTF32), 1 = fp32 FFMA
+def test_head_golden_and_oracle(ops, oracle_mod, algo):
     g = load_golden("head")
     hp = synth.head_params(int(g["seed"]))
     folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
-    y = npy(ops.head_forward(dev(g["x"]), folded))
+    y = npy(ops.head_forward(dev(g["x"]), folded, algo=algo))
     assert rel_err(y, g["y"], floor=1.0) < TOL
     x = torch.relu(torch.randn(333, 256, 3, 3, generator=torch.Generator().manual_seed(1))) * 2
-    y = npy(ops.head_forward(dev(x), folded))
+    y = npy(ops.head_forward(dev(x), folded, algo=algo))
     ref = oracle_mod.head(x.numpy(), {k: v.numpy() for k, v in hp.items()})
     assert rel_err(y, ref, floor=1.0) < TOL
 
@@ -390,6 +391,10 @@ def test_eval_path_full_size_properties(ops, oracle_mod):
     assert rf["n"] == r["n"]
     np.testing.assert_array_equal(npy(rf["reg"]), npy(r["reg"]))
     np.testing.assert_array_equal(npy(rf["s2"]), npy(r["s2"]))
+    # the FFMA head agrees with the tensor-core head to rounding
+    ffma = ops.EvalPath(B, C, H, W, K, folded, head_algo=1)
+    ffma.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    assert rel_err(npy(ffma.results()["reg"]), npy(r["reg"]), floor=1.0) < TOL
     # the direct-gather RoIAlign agrees to rounding
     direct = ops.EvalPath(B, C, H, W, K, folded, roi_algo=1)
     direct.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
