@@ -26,7 +26,9 @@
 namespace rr {
 
 constexpr int kTcRois = 14;                      // RoIs per CTA: 126 of the 128 MMA rows
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;
+constexpr int kTcBlock = kTcThreads;
+constexpr int kTcItems = 1024 / kTcThreads;      // (row, 16-byte chunk) items of an A tile per thread
 constexpr int kTcATile = 128 * 128;              // bytes: 128 rows x 32 tf32
 constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
 constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB, two stages
@@ -149,10 +151,19 @@ __device__ __forceinline__ float4 tc_load_x4(const HeadSrc& src, int n, int p, i
     return v;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+#ifdef RR_HEAD_TC_TRACE      // tools/head_trace.py: per-CTA phase time stamps (never defined in the shipped build)
+__device__ unsigned long long g_tc_trace[1024 * 32];
+#define TC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tc_trace[blockIdx.x * 32 + (k)] = t_; } } while (0)
+#else
+#define TC_TRACE(k) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(kTcBlock, 1)
 head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                const float* __restrict__ f, float* __restrict__ reg) {
     extern __shared__ uint8_t s_dyn[];
+    TC_TRACE(0);
     __shared__ __align__(8) unsigned long long s_free[2];      // stage may be overwritten (its MMAs are done)
     __shared__ __align__(8) unsigned long long s_phase;        // all MMAs of a phase are done
     __shared__ uint32_t s_tmem;
@@ -171,7 +182,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     float* s_thi = s_eye + kTcEyeBytes / 4;                                     // t1, then t2: tf32 hi plane [128][kT1Stride]
     float* s_tlo = s_thi + 128 * kT1Stride;                                     //              tf32 lo plane
     float* s_pool = s_tlo + 128 * kT1Stride;                                    // [14][256]
-    for (int i = tid; i < 32 * 32; i += kTcThreads) {                           // I[n][k] in the swizzled tile layout
+    for (int i = tid; i < 32 * 32; i += kTcThreads) {       // I[n][k] in the swizzled tile layout
         const int n = i >> 5, k = i & 31;
         s_eye[n * 32 + ((((k >> 2) ^ (n & 7))) << 2) + (k & 3)] = (n == k) ? 1.0f : 0.0f;
     }
@@ -197,6 +208,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TC_TRACE(1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
     const float* ftc = f + kOffTc;
@@ -208,11 +220,15 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     // weight tile pair of step s -> ring slot s % 4 (16 KB, straight copy); always commits a group so that the
     // group count stays in step with s even past the last step
     auto prefetch_b = [&](int s) {
+#ifdef RR_TC_EXP_NOB
+        if (s < 4) {
+#else
         if (s < kTcSteps) {
+#endif
             const float4* g = reinterpret_cast<const float4*>(ftc + (size_t)s * kTcStepFloats);
             uint8_t* d = ring + (s & (kTcBRing - 1)) * kTcBSlot;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kTcItems; ++q) {
                 const int i = tid + q * kTcThreads;     // 1024 x 16 bytes
                 const unsigned da = smem_addr(d + i * 16);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(g + i) : "memory");
@@ -221,13 +237,15 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // Every step: acquire(s) (the MMAs of step s-2 are done: its A stage and its B slot are free), prefetch the
-    // weights of step s+2 into that slot, fill the A stage, then publish_and_issue(s).
-    auto publish_and_issue = [&](int s, uint32_t d_col, bool first, int residual_chunk = -1) {
+    // weights of step s+2 into that slot, fill the A stage, then publish(s): barrier, and thread 0 issues.
+    auto publish = [&](int s) {
         asm volatile("cp.async.wait_group 2;" ::: "memory");               // groups s+1, s+2 may still be in flight
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_col = s < 8 ? 0u : (s < 26 ? 64u : 128u + 64u * (uint32_t)((s - 26) >> 1));
+            const bool first = s == 0 || s == 8;      // conv3 accumulates onto the residual placed during conv1
             const uint32_t sa = smem_addr(stage[s & 1]), sb = smem_addr(ring + (s & (kTcBRing - 1)) * kTcBSlot);
             const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + kTcATile);
             const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
@@ -237,9 +255,13 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 umma_tf32(tmem + d_col, a_hi + 2 * ks, b_lo + 2 * ks, 1u);
                 umma_tf32(tmem + d_col, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
             }
-            if (residual_chunk >= 0) {              // conv3's accumulator starts as x itself: D3[:, 32c .. 32c+32) = A . I
+#ifdef RR_TC_EXP_NOEYE
+            if (s < 0) {
+#else
+            if (s < 8) {                            // conv3's accumulator starts as x itself: D3[:, 32s .. 32s+32) = A . I
+#endif
                 const uint64_t eye = umma_desc(smem_addr(s_eye));
-                const uint32_t d3 = tmem + 128u + 32u * (uint32_t)residual_chunk;
+                const uint32_t d3 = tmem + 128u + 32u * (uint32_t)s;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     umma_tf32(d3, a_hi + 2 * ks, eye + 2 * ks, ks == 0 ? 0u : 1u, kIdescN32);
@@ -247,24 +269,30 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 }
             }
             umma_commit(&s_free[s & 1]);
+            if (s == 7 || s == 25 || s == kTcSteps - 1) umma_commit(&s_phase);
         }
     };
+    auto stagers_sync = [&]() { __syncthreads(); };
     prefetch_b(0);
     prefetch_b(1);
 
     // ============================== conv1: x [128 x 256] . W1 ==============================
-    // x is prefetched one K chunk ahead into registers.  A row's value is the sum of its RoI's partial slots:
+    // x is prefetched two K chunks ahead into registers.  A row's value is the sum of its RoI's partial slots:
     // the first four slots of all four items are loaded back to back (16 independent 128-bit loads in flight
     // per thread; a load-add-load-add loop would serialise on the in-order issue), the adds happen at use.
-    float4 xp[4][4];
-    auto load_x_chunk = [&](int kc) {
+    float4 xpa[kTcItems][4], xpb[kTcItems][4];      // two chunks in flight (even / odd K chunk)
+    auto load_x_chunk = [&](int kc, float4 (&xp)[kTcItems][4]) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {               // 128 rows x 8 chunks of 4 channels
+        for (int q = 0; q < kTcItems; ++q) {        // 128 rows x 8 chunks of 4 channels
             const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
             const int rl = r / 9, p = r - rl * 9, c0 = 32 * kc + 4 * ch;
 #pragma unroll
             for (int k = 0; k < 4; ++k) xp[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef RR_TC_EXP_NOX
+            if (rl < nroi && kc < 2) {
+#else
             if (rl < nroi) {
+#endif
                 const int sb = s_sb[rl], pc = s_pc[rl];
                 if (sb < 0) {
                     xp[q][0] = tc_load_x4(src, roi0 + rl, p, sb, 0, 1.f, c0);
@@ -277,7 +305,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
         }
     };
-    auto x_value = [&](int kc, int q) {             // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
+    auto x_value = [&](int kc, int q, const float4 (&xp)[kTcItems][4]) {   // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
         const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
         const int rl = r / 9, p = r - rl * 9;
         float4 v = xp[q][0];
@@ -285,7 +313,11 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             const int sb = s_sb[rl], pc = s_pc[rl];
 #pragma unroll
             for (int k = 1; k < 4; ++k) { v.x += xp[q][k].x; v.y += xp[q][k].y; v.z += xp[q][k].z; v.w += xp[q][k].w; }
+#ifdef RR_TC_EXP_NOTAIL
+            for (int k = 4; k < 0; ++k) {
+#else
             for (int k = 4; k < pc; ++k) {          // RoIs cut into more than four pieces are rare
+#endif
                 const float4 t = __ldg(reinterpret_cast<const float4*>(src.partial + (size_t)(sb + k) * 2304 + p * 256 + 32 * kc + 4 * ch));
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
@@ -294,26 +326,34 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         }
         return v;
     };
-    load_x_chunk(0);
-#pragma unroll 1
-    for (int kc = 0; kc < 8; ++kc) {
+    auto conv1_step = [&](int kc, float4 (&xp)[kTcItems][4]) {
         const int s = step++;
         acquire(s);
         prefetch_b(s + 2);
         uint8_t* a_hi = stage[s & 1];
         uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kTcItems; ++q) {
             const int i = tid + q * kTcThreads;
-            store_split(a_hi, a_lo, i >> 3, i & 7, x_value(kc, q));
+            store_split(a_hi, a_lo, i >> 3, i & 7, x_value(kc, q, xp));
         }
-        if (kc + 1 < 8) load_x_chunk(kc + 1);       // in flight across the barrier and the MMAs of this step
-        publish_and_issue(s, 0u, kc == 0, kc);
+        if (kc + 2 < 8) load_x_chunk(kc + 2, xp);   // in flight across two steps
+        publish(s);
+        TC_TRACE(16 + kc);
+    };
+    load_x_chunk(0, xpa);
+    TC_TRACE(2);
+    load_x_chunk(1, xpb);
+#pragma unroll 1
+    for (int kc = 0; kc < 8; kc += 2) {
+        conv1_step(kc, xpa);
+        conv1_step(kc + 1, xpb);
     }
-    if (tid == 0) umma_commit(&s_phase);
+    TC_TRACE(3);
     bar_wait(&s_phase, 0u);
+    TC_TRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {   // t1 = relu(D1 + b1) -> (hi, lo) planes [row][64]
+    if (warp < 8) {   // t1 = relu(D1 + b1) -> (hi, lo) planes [row][64]; eight warps cover 4 lane quarters x 2 column halves
         const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * h), v);
@@ -331,7 +371,8 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    stagers_sync();
+    TC_TRACE(5);
 
     // ============================== conv2: 9 taps, A rows = shifted rows of t1 ==============================
     for (int t = 0; t < 18; ++t) {
@@ -342,7 +383,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         uint8_t* a_hi = stage[s & 1];
         uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kTcItems; ++q) {
             const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
             float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
             const int rl = r / 9, p = r - rl * 9, py = p / 3 + dy, px = p % 3 + dx;
@@ -353,12 +394,13 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
             store_tiles(a_hi, a_lo, r, ch, hi, lo);
         }
-        publish_and_issue(s, 64u, t == 0);
+        publish(s);
     }
-    if (tid == 0) umma_commit(&s_phase);
+    TC_TRACE(6);
     bar_wait(&s_phase, 1u);
+    TC_TRACE(7);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {   // t2 = relu(D2 + b2) -> overwrites t1 (every tap has been staged and consumed)
+    if (warp < 8) {   // t2 = relu(D2 + b2) -> overwrites t1 (every tap has been staged and consumed)
         const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 64u + (uint32_t)(32 * h), v);
@@ -376,7 +418,8 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    stagers_sync();
+    TC_TRACE(8);
 
     // ============================== conv3: t2 [128 x 64] . W3, four N quarters ==============================
     for (int t = 0; t < 8; ++t) {
@@ -388,17 +431,19 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             uint8_t* a_hi = stage[s & 1];
             uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kTcItems; ++q) {
                 const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
                 const int o = r * kT1Stride + 32 * kc + 4 * ch;
                 store_tiles(a_hi, a_lo, r, ch, *reinterpret_cast<const float4*>(s_thi + o),
                             *reinterpret_cast<const float4*>(s_tlo + o));
             }
         }
-        publish_and_issue(s, 128u + 64u * (uint32_t)q4, false);      // accumulates onto the residual placed by conv1
+        publish(s);      // accumulates onto the residual placed by conv1
+        if (t == 0) TC_TRACE(24); if (t == 6) TC_TRACE(25);
     }
-    if (tid == 0) umma_commit(&s_phase);
+    TC_TRACE(9);
     bar_wait(&s_phase, 0u);
+    TC_TRACE(10);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ============================== + b3 + residual, relu, avg-pool over the 9 rows, regressor ==============================
@@ -407,13 +452,15 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     {
         const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
         for (int cb = 0; cb < 4; ++cb) {            // warps 0-3: column blocks 2cb, warps 4-7: 2cb+1 (32 columns each)
-            const int c0 = 32 * (2 * cb + h);
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)c0, v);    // W3.t2 + x (residual already inside)
-            float* dst = s_relu + (h * 128 + row) * 33;
+            if (warp < 8) {
+                const int c0 = 32 * (2 * cb + h);
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)c0, v);    // W3.t2 + x (residual already inside)
+                float* dst = s_relu + (h * 128 + row) * 33;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = fmaxf(v[j] + __ldg(f + kOffB3 + c0 + j), 0.f);   // resnet.py:49-50
-            __syncthreads();
+                for (int j = 0; j < 32; ++j) dst[j] = fmaxf(v[j] + __ldg(f + kOffB3 + c0 + j), 0.f);   // resnet.py:49-50
+            }
+            stagers_sync();
             for (int i = tid; i < 2 * kTcRois * 32; i += kTcThreads) {      // (half, roi, column): mean of 9 rows
                 const int hh = i / (kTcRois * 32), rem = i - hh * (kTcRois * 32), r2 = rem >> 5, c = rem & 31;
                 const float* sp = s_relu + (hh * 128 + r2 * 9) * 33 + c;
@@ -422,7 +469,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 for (int pp = 0; pp < 9; ++pp) acc += sp[pp * 33];
                 s_pool[r2 * 256 + 32 * (2 * cb + hh) + c] = acc / 9.0f;
             }
-            __syncthreads();
+            stagers_sync();
         }
     }
     for (int rl = warp; rl < nroi; rl += kTcThreads / 32) {        // regressor 256 -> 4 (+ bias)
@@ -440,7 +487,8 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                                                                     r2 + __ldg(f + kOffBr + 2), r3 + __ldg(f + kOffBr + 3));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    stagers_sync();
+    TC_TRACE(12);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
@@ -452,9 +500,15 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
         attr_set = true;
     }
     const int grid = (n_cap + kTcRois - 1) / kTcRois;
-    head_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
+    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
     RR_LAUNCHED(rc);
     return rc;
 }
 
 }  // namespace rr
+
+#ifdef RR_HEAD_TC_TRACE
+RR_API int rr_debug_head_trace(unsigned long long* host, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host, rr::g_tc_trace, sizeof(unsigned long long) * (size_t)n_words);
+}
+#endif

@@ -1,0 +1,102 @@
+"""Per-CTA phase timeline of head_tc_kernel on the bench workload (development tool, not shipped).
+
+Builds a second copy of the library with -DRR_HEAD_TC_TRACE (time stamps in a __device__ array), runs the
+eval path once warm, and prints where a CTA spends its time.  Usage on the GPU box: python tools/head_trace.py
+"""
+import ctypes, os, subprocess, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rrnet_b200 import build as B  # noqa: E402
+
+TRACE_LIB = os.path.join(ROOT, "tools", "librrnet_trace.so")
+
+
+VARIANTS = {"": [], "nob": ["-DRR_TC_EXP_NOB"], "nox": ["-DRR_TC_EXP_NOX"], "noeye": ["-DRR_TC_EXP_NOEYE"],
+            "notail": ["-DRR_TC_EXP_NOTAIL"], "nob_nox": ["-DRR_TC_EXP_NOB", "-DRR_TC_EXP_NOX"]}
+
+
+def lib_path(variant):
+    return TRACE_LIB.replace(".so", ("_" + variant if variant else "") + ".so")
+
+
+def build_trace_lib():
+    B.build()
+    for variant, defs in VARIANTS.items():          # timing-only experiments: results are wrong by design
+        obj = os.path.join(ROOT, "tools", "rr_head_tc_trace_%s.o" % variant)
+        subprocess.check_call([B._nvcc()] + B.BASE + ["-DRR_HEAD_TC_TRACE"] + defs +
+                              ["-c", os.path.join(B.CSRC, "rr_head_tc.cu"), "-o", obj])
+        objs = [os.path.join(B.OBJ, u.replace(".cu", ".o")) for u in B.UNITS if u != "rr_head_tc.cu"] + [obj]
+        subprocess.check_call([B._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path(variant)]
+                              + objs + ["-lcudart"])
+
+
+def main():
+    if "--build" in sys.argv or not os.path.exists(TRACE_LIB):
+        build_trace_lib()
+        if "--build" in sys.argv:
+            return
+    variant = ""
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            variant = a.split("=", 1)[1]
+    if variant == "all":
+        for v in VARIANTS:
+            print("================ variant '%s'" % v, flush=True)
+            subprocess.call([sys.executable, os.path.abspath(__file__), "--variant=" + v])
+        return
+    import torch
+    from rrnet_b200 import _lib
+    _lib.LIB_PATH = lib_path(variant)
+    from rrnet_b200 import ops, synth
+    import bench
+    w = bench.WORKLOAD
+    Bn, C, H, W, K = w["B"], w["C"], w["H"], w["W"], w["K"]
+    dev = torch.device("cuda", 0)
+    x = synth.eval_inputs(Bn, H, W, K, synth.SEED_C2)
+    d = {k: v.to(dev) for k, v in x.items()}
+    folded = ops.head_fold({k: v.to(dev) for k, v in synth.head_params(synth.SEED_C2).items()})
+    path = ops.EvalPath(Bn, C, H, W, K, folded, device=dev)
+    for _ in range(3):
+        path.forward(d["hm"], d["wh"], d["off"], d["feat"])
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    n = 1024 * 32
+    buf = (ctypes.c_uint64 * n)()
+    L.rr_debug_head_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    rc = L.rr_debug_head_trace(buf, n)
+    assert rc == 0, rc
+    t = np.frombuffer(buf, dtype=np.uint64).reshape(1024, 32).astype(np.int64)
+    n_cta = (Bn * K + 13) // 14
+    t = t[:min(n_cta, 1024)]
+    t0 = t[:, 0].min()
+    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "conv2 loop", "conv2 mma wait", "epi2",
+             "conv3 loop", "conv3 mma wait", "pool+reg"]
+    marks = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]
+    print("CTAs traced %d; kernel span %.1f us" % (len(t), (t[:, 12].max() - t0) / 1e3))
+    dur = t[:, 12] - t[:, 0]
+    print("CTA duration us: mean %.1f  p10 %.1f  p50 %.1f  p90 %.1f  max %.1f" % (
+        dur.mean() / 1e3, *(np.percentile(dur, q) / 1e3 for q in (10, 50, 90)), dur.max() / 1e3))
+    first = t[:, 0] - t0 < 5000                     # CTAs of the first wave
+    for label, sel in (("all", np.ones(len(t), bool)), ("first wave", first), ("later waves", ~first)):
+        print("--", label, int(sel.sum()), "CTAs, mean us per phase")
+        for i, nm in enumerate(names):
+            seg = (t[sel, marks[i + 1]] - t[sel, marks[i]]) / 1e3
+            print("   %-16s %7.2f" % (nm, seg.mean()))
+    steps = np.diff(np.concatenate([t[:, 2:3], t[:, 16:24]], axis=1), axis=1) / 1e3
+    print("conv1 per-step us (mean over CTAs):", np.round(steps.mean(axis=0), 2))
+    print("conv3 steps 1..6 mean us/step: %.2f" % ((t[:, 25] - t[:, 24]).mean() / 6e3))
+    # how many tile pieces the RoIs of this workload are cut into (approximation of roi_prep_kernel's count)
+    n_live = int(path.counts[-1].item()) if path.counts[-1].item() > 0 else int(path.counts.sum().item())
+    bx = path.bxyxy[:n_live].float().cpu().numpy()
+    ntx = np.floor((bx[:, 3] + 1) / 32) - np.floor(bx[:, 1] / 32) + 1
+    nty = np.floor((bx[:, 4] + 1) / 24) - np.floor(bx[:, 2] / 24) + 1
+    pcs = (ntx * nty).astype(int)
+    print("RoIs %d; pieces histogram:" % n_live, np.bincount(pcs)[:16], " mean %.2f" % pcs.mean())
+    grp = pcs[: (len(pcs) // 14) * 14].reshape(-1, 14)
+    print("CTAs whose 14 RoIs include one with > 4 pieces: %.1f %%" % (100.0 * (grp.max(axis=1) > 4).mean()))
+
+
+if __name__ == "__main__":
+    main()
