@@ -3,42 +3,55 @@
 //
 // Same contract as head_forward_kernel (rr_head.cu): Bottleneck(256,64) -> avg-pool -> 1x1 conv 256->4 on
 // the RoIs' [256,3,3] features (models/rrnet.py:155-157, detectors/fasterrcnn_detector.py:13-18,
-// backbones/resnet.py:33-53), BatchNorms folded.  The three convolutions are GEMMs over M = 128 rows
-// (14 RoIs x 9 pixels + 2 zero rows) per CTA:
-//     conv1  [128 x 256] x [256 x  64]                      8 K-chunks of 32
-//     conv2  9 taps x [128 x 64] x [64 x 64]                the A rows of a tap are the 3x3-shifted rows of t1
-//     conv3  [128 x  64] x [64 x 256]                       4 N-quarters x 2 K-chunks
-// Every MMA is tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8, issued by one thread; the
-// accumulators live in TMEM (conv1: columns 0-63, conv2: 64-127, conv3: 128-383) and come back with
-// tcgen05.ld for the bias / ReLU / pooling epilogues.  The residual x is added by the tensor core too: while
-// a K chunk of x sits in shared memory for conv1, one more MMA against a 32 x 32 identity tile deposits it in
-// conv3's accumulator columns, so x is read from memory exactly once.  An fp32 product a*b is evaluated as
-// a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with hi = tf32(v), lo = tf32(v - hi): three MMAs per K-step,
-// error ~2^-21 relative per product, so the result stays within the 1e-5 parity budget.
+// backbones/resnet.py:33-53), BatchNorms folded.  A CTA takes 8 RoIs.  Their pixels are the rows of one
+// M = 128 tile in a padded list of 16 rows per RoI,
+//     row(roi, py, px) = 16 roi + 4 + 4 py + px          (rows 16 roi + 0..3 and every px = 3 row stay zero)
+// so that the neighbour (py + dy, px + dx) of a pixel is the row 4 dy + dx further down and every neighbour
+// outside the 3x3 map is a zero row.  The three convolutions are GEMMs over that tile:
+//     conv1  [128 x 256] x [256 x  64]              8 K-chunks of 32
+//     conv2  9 taps x [128 x 64] x [64 x 64]        a tap is the SAME t1 tile read through a shared-memory
+//                                                   descriptor whose start address is shifted by 4 dy + dx rows
+//                                                   (the 128-byte swizzle is a function of the address, so a
+//                                                   128-byte-aligned start is legal: tools/tc_shift_probe.cu)
+//     conv3  [128 x  64] x [64 x 256]               4 N-quarters x 2 K-chunks
+// Nothing is restaged between the taps: after conv1 the only data movement is the weight stream.
+// Every MMA is tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8; the accumulators live in TMEM
+// (conv1: columns 0-63, conv2: 64-127, conv3: 128-383) and come back with tcgen05.ld for the epilogues.  The
+// residual x is added by the tensor core too: while a K chunk of x sits in shared memory for conv1, one more
+// MMA against a 32 x 32 identity tile deposits it in conv3's accumulator columns, so x is read exactly once.
+// An fp32 product a*b is evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with hi = tf32(v), lo = tf32(v - hi):
+// three MMAs per K-step, error ~2^-21 relative per product, inside the 1e-5 parity budget.
 //
-// Operands are K-major tiles of 32 tf32 per row (128 bytes) with the 128-byte swizzle, written by ordinary
-// stores: A tiles (activations, split on the fly) by all threads into two alternating stages, B tiles
-// (weights) copied with cp.async from a pre-split, pre-swizzled image made once by rr_head_fold into a
-// ring of four slots, two steps ahead of their use.  While the tensor core works on one step the threads
-// fill the next; a tcgen05.commit on a per-stage mbarrier tells when a stage / slot may be overwritten.
+// Warp roles (no block-wide barrier after the prologue; mbarriers connect the roles):
+//   warps 0-8   workers: sum the RoIs' partial slots (x), split, fill the three conv1 A stages; epilogues
+//   warp  9     lane 0 issues every tcgen05.mma and the tcgen05.commit that frees a stage / ring slot
+//   warp  10    lane 0 streams the 34 pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
+//               rr_head_fold) through a ring of six slots with cp.async.bulk (TMA) + complete_tx; the warp
+//               also prefetches into L2 the x slots of the CTA that will follow this one on the SM
+// The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
 namespace rr {
 
-constexpr int kTcRois = 14;                      // RoIs per CTA: 126 of the 128 MMA rows
-constexpr int kTcThreads = 512;
-constexpr int kTcBlock = kTcThreads;
-constexpr int kTcItems = 1024 / kTcThreads;      // (row, 16-byte chunk) items of an A tile per thread
+constexpr int kTcRois = 8;                       // RoIs per CTA
+constexpr int kRoiRows = 16;                     // tile rows per RoI: 3 x (3 pixels + 1 zero) + 4 zero rows in front
+constexpr int kWorkerWarps = 9;
+constexpr int kWorkers = 32 * kWorkerWarps;      // 288 threads x 2 items = the 576 live (row, 16-byte chunk) items of an x tile
+constexpr int kTcItems = 2;
+constexpr int kTcSlotsInReg = 6;                 // partial slots of an item held in registers per K chunk
+constexpr int kTcBlock = kWorkers + 64;          // + the MMA issuer warp + the weight stream warp
 constexpr int kTcATile = 128 * 128;              // bytes: 128 rows x 32 tf32
 constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
-constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB, two stages
-constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB, ring of four (weights are prefetched 2 steps ahead)
-constexpr int kTcBRing = 4;
-constexpr int kT1Stride = 68;                    // floats per row of the plain t1 / t2 array (conflict-free 128-bit rows)
-constexpr int kTcT1Bytes = 2 * 128 * kT1Stride * 4;   // t1 / t2 as (hi, lo) tf32 planes
+constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB
+constexpr int kAStages = 3;
+constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one step of the weight image
+constexpr int kTcBRing = 6;
+constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
+constexpr int kPlaneBytes = (128 + 2 * kMargin) * 128;
+static_assert(4 * kPlaneBytes <= kAStages * kTcAStage, "the t planes reuse the conv1 stages");
+static_assert(kTcBSlot == kTcStepFloats * 4, "a ring slot is one step of the folded image");
 constexpr int kTcEyeBytes = 32 * 128;                // 32 x 32 identity tile (residual through the tensor core)
-constexpr int kTcPoolBytes = kTcRois * 256 * 4;
-constexpr int kTcSmem = 2 * kTcAStage + kTcBRing * kTcBSlot + kTcEyeBytes + kTcT1Bytes + kTcPoolBytes + 1024;   // + slack for the 1024-byte alignment
+constexpr int kTcSmem = kAStages * kTcAStage + kTcBRing * kTcBSlot + kTcEyeBytes + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 //                          D = f32      A = tf32     B = tf32      N = 64               M = 128      (both K-major)
@@ -67,6 +80,25 @@ __device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parit
                      : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+// A whole warp waits, one lane polls (with back-off): 300 threads spinning on try_wait would compete with the
+// tensor core for the shared-memory port its operands come through.
+__device__ __forceinline__ void bar_wait_warp(unsigned long long* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t ok;
+        for (;;) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+            if (ok) break;
+            __nanosleep(64);
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ bool elect_one() {        // one lane of a converged warp
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -89,21 +121,6 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
     hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
     lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
 }
-// 16-byte stores of an already split value into the swizzled A tiles: row r, 16-byte chunk ch
-__device__ __forceinline__ void store_tiles(uint8_t* a_hi, uint8_t* a_lo, int r, int ch, float4 hi, float4 lo) {
-    const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-    *reinterpret_cast<float4*>(a_hi + off) = hi;
-    *reinterpret_cast<float4*>(a_lo + off) = lo;
-}
-// (hi, lo) split of four values and their stores into the swizzled A tiles
-__device__ __forceinline__ void store_split(uint8_t* a_hi, uint8_t* a_lo, int r, int ch, float4 v) {
-    float4 hi, lo;
-    split4(v, hi, lo);
-    const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-    *reinterpret_cast<float4*>(a_hi + off) = hi;
-    *reinterpret_cast<float4*>(a_lo + off) = lo;
-}
-
 // ---- weight image: (hi, lo) tf32 tiles in the swizzled shared-memory layout, made once per fold ----
 __global__ void head_fold_tc_kernel(float* __restrict__ f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,41 +151,38 @@ int head_fold_tc_launch(float* folded, cudaStream_t st) {
     return rc;
 }
 
-// x[row][c0 .. c0+3] of the CTA's RoI tile: row = roi_local * 9 + pixel
-__device__ __forceinline__ float4 tc_load_x4(const HeadSrc& src, int n, int p, int sb, int pieces, float inv, int c0) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sb < 0) {
-        const float* xn = src.roi_feat + (size_t)n * 2304 + p;
-        v.x = __ldg(xn + (c0 + 0) * 9); v.y = __ldg(xn + (c0 + 1) * 9);
-        v.z = __ldg(xn + (c0 + 2) * 9); v.w = __ldg(xn + (c0 + 3) * 9);
-    } else {
-        for (int k = 0; k < pieces; ++k) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src.partial + (size_t)(sb + k) * 2304 + p * 256 + c0));
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        }
-        v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
-    }
-    return v;
-}
 
 #ifdef RR_HEAD_TC_TRACE      // tools/head_trace.py: per-CTA phase time stamps (never defined in the shipped build)
-__device__ unsigned long long g_tc_trace[1024 * 32];
-#define TC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned long long t_; \
+__device__ unsigned long long g_tc_trace[2048 * 32];
+#define TC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tc_trace[blockIdx.x * 32 + (k)] = t_; } } while (0)
+#define TC_TRACE_VAL(k, v) do { if (blockIdx.x < 2048) g_tc_trace[blockIdx.x * 32 + (k)] = (unsigned long long)(v); } while (0)
+#define TC_CLOCK() clock64()
 #else
 #define TC_TRACE(k) do { } while (0)
+#define TC_TRACE_VAL(k, v) do { } while (0)
+#define TC_CLOCK() 0ll
 #endif
+
+__device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(kTcBlock, 1)
 head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
-               const float* __restrict__ f, float* __restrict__ reg) {
+               const float* __restrict__ f, float* __restrict__ reg, int wave) {
     extern __shared__ uint8_t s_dyn[];
-    TC_TRACE(0);
-    __shared__ __align__(8) unsigned long long s_free[2];      // stage may be overwritten (its MMAs are done)
-    __shared__ __align__(8) unsigned long long s_phase;        // all MMAs of a phase are done
+    __shared__ __align__(8) unsigned long long s_full_a[kAStages];   // conv1 A stage filled (one arrival per worker warp)
+    __shared__ __align__(8) unsigned long long s_free_a[kAStages];   // ... consumed (tcgen05.commit)
+    __shared__ __align__(8) unsigned long long s_full_b[kTcBRing];   // weight slot landed (complete_tx)
+    __shared__ __align__(8) unsigned long long s_free_b[kTcBRing];   // ... consumed (tcgen05.commit)
+    __shared__ __align__(8) unsigned long long s_phase[3];           // all MMAs of conv1 / conv2 / conv3 are done
+    __shared__ __align__(8) unsigned long long s_tready;             // t1 (then t2) tiles written by the epilogue
     __shared__ uint32_t s_tmem;
-    __shared__ int s_sb[kTcRois], s_pc[kTcRois];
-    __shared__ float s_inv[kTcRois];
+    __shared__ float s_b1[64], s_b2[64], s_b3[256];
+    __shared__ float4 s_wr[256];                                     // regressor weights, one float4 per channel
+    __shared__ float4 s_part[2][kTcRois];
+    TC_TRACE(0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     const int roi0 = blockIdx.x * kTcRois;
@@ -176,320 +190,334 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     const int nroi = min(kTcRois, live - roi0);
 
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)s_dyn + 1023) & ~(uintptr_t)1023);
-    uint8_t* stage[2] = {base, base + kTcAStage};                               // A_hi | A_lo
-    uint8_t* ring = base + 2 * kTcAStage;                                       // kTcBRing x (B_hi | B_lo)
+    // [0, 96 KB): three conv1 A stages (A_hi | A_lo); after conv1 the same bytes hold the t1 / t2 tiles:
+    // plane (hi|lo, kc) at base + (2*lo + kc) * kPlaneBytes, 8 zero rows, the 128 tile rows, 8 zero rows
+    uint8_t* ring = base + kAStages * kTcAStage;                                // kTcBRing x (B_hi | B_lo)
     float* s_eye = reinterpret_cast<float*>(ring + kTcBRing * kTcBSlot);        // identity B tile, 32 x 32
-    float* s_thi = s_eye + kTcEyeBytes / 4;                                     // t1, then t2: tf32 hi plane [128][kT1Stride]
-    float* s_tlo = s_thi + 128 * kT1Stride;                                     //              tf32 lo plane
-    float* s_pool = s_tlo + 128 * kT1Stride;                                    // [14][256]
-    for (int i = tid; i < 32 * 32; i += kTcThreads) {       // I[n][k] in the swizzled tile layout
+
+    // ------------------------------ prologue (all warps) ------------------------------
+    for (int i = tid; i < 32 * 32; i += kTcBlock) {         // I[n][k] in the swizzled tile layout
         const int n = i >> 5, k = i & 31;
         s_eye[n * 32 + ((((k >> 2) ^ (n & 7))) << 2) + (k & 3)] = (n == k) ? 1.0f : 0.0f;
     }
-
-    if (tid < kTcRois) {
-        int sb = 0, pc = 0;
-        float cnt = 1.f;
-        if (tid < nroi) {
-            const int n = roi0 + tid;
-            if (src.partial) { sb = src.slot[n]; pc = src.pieces[n]; cnt = src.count[n]; }
-            else sb = -1;
-        }
-        s_sb[tid] = sb; s_pc[tid] = pc; s_inv[tid] = 1.0f / cnt;
+    for (int i = tid; i < kAStages * kTcAStage / 16; i += kTcBlock)             // pad rows of the A stages stay zero
+        reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 64; i += kTcBlock) { s_b1[i] = __ldg(f + kOffB1 + i); s_b2[i] = __ldg(f + kOffB2 + i); }
+    for (int i = tid; i < 256; i += kTcBlock) {
+        s_b3[i] = __ldg(f + kOffB3 + i);
+        s_wr[i] = make_float4(__ldg(f + kOffWr + i), __ldg(f + kOffWr + 256 + i), __ldg(f + kOffWr + 512 + i),
+                              __ldg(f + kOffWr + 768 + i));
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_free[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_free[1])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_phase)) : "memory");
+    if (tid == 32) {
+        auto init = [](unsigned long long* b, int count) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+        };
+        for (int i = 0; i < kAStages; ++i) { init(&s_full_a[i], kWorkerWarps); init(&s_free_a[i], 1); }
+        for (int i = 0; i < kTcBRing; ++i) { init(&s_full_b[i], 1); init(&s_free_b[i], 1); }
+        for (int i = 0; i < 3; ++i) init(&s_phase[i], 1);
+        init(&s_tready, kWorkerWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // identity tile + zero fill -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    TC_TRACE(1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TC_TRACE(1);
     const uint32_t tmem = s_tmem;
     const float* ftc = f + kOffTc;
 
-    int step = 0;                                   // ring position over all 34 weight steps
-    auto acquire = [&](int s) {                     // stage s&1 was last used by step s-2
-        if (s >= 2) bar_wait(&s_free[s & 1], (uint32_t)(((s >> 1) - 1) & 1));
-    };
-    // weight tile pair of step s -> ring slot s % 4 (16 KB, straight copy); always commits a group so that the
-    // group count stays in step with s even past the last step
-    auto prefetch_b = [&](int s) {
-#ifdef RR_TC_EXP_NOB
-        if (s < 4) {
-#else
-        if (s < kTcSteps) {
-#endif
-            const float4* g = reinterpret_cast<const float4*>(ftc + (size_t)s * kTcStepFloats);
-            uint8_t* d = ring + (s & (kTcBRing - 1)) * kTcBSlot;
-#pragma unroll
-            for (int q = 0; q < kTcItems; ++q) {
-                const int i = tid + q * kTcThreads;     // 1024 x 16 bytes
-                const unsigned da = smem_addr(d + i * 16);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(g + i) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // Every step: acquire(s) (the MMAs of step s-2 are done: its A stage and its B slot are free), prefetch the
-    // weights of step s+2 into that slot, fill the A stage, then publish(s): barrier, and thread 0 issues.
-    auto publish = [&](int s) {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");               // groups s+1, s+2 may still be in flight
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d_col = s < 8 ? 0u : (s < 26 ? 64u : 128u + 64u * (uint32_t)((s - 26) >> 1));
-            const bool first = s == 0 || s == 8;      // conv3 accumulates onto the residual placed during conv1
-            const uint32_t sa = smem_addr(stage[s & 1]), sb = smem_addr(ring + (s & (kTcBRing - 1)) * kTcBSlot);
-            const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + kTcATile);
-            const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {        // K = 32 per stage: four K = 8 instructions, 32 bytes apart
-                umma_tf32(tmem + d_col, a_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
-                umma_tf32(tmem + d_col, a_hi + 2 * ks, b_lo + 2 * ks, 1u);
-                umma_tf32(tmem + d_col, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
-            }
-#ifdef RR_TC_EXP_NOEYE
-            if (s < 0) {
-#else
-            if (s < 8) {                            // conv3's accumulator starts as x itself: D3[:, 32s .. 32s+32) = A . I
-#endif
-                const uint64_t eye = umma_desc(smem_addr(s_eye));
-                const uint32_t d3 = tmem + 128u + 32u * (uint32_t)s;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    umma_tf32(d3, a_hi + 2 * ks, eye + 2 * ks, ks == 0 ? 0u : 1u, kIdescN32);
-                    umma_tf32(d3, a_lo + 2 * ks, eye + 2 * ks, 1u, kIdescN32);
+    // ------------------------------ warp 10: the weight stream ------------------------------
+    if (warp == kWorkerWarps + 1) {
+        auto load_b = [&](int s) {
+            const uint32_t bar = smem_addr(&s_full_b[s % kTcBRing]);
+            const uint32_t dst = smem_addr(ring + (s % kTcBRing) * kTcBSlot);
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(kTcBSlot) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(ftc + (size_t)s * kTcStepFloats), "r"(kTcBSlot), "r"(bar) : "memory");
+        };
+        if (lane == 0)
+            for (int s = 0; s < kTcBRing; ++s) load_b(s);
+        __syncwarp();
+        if (lane < kTcRois) {       // L2 prefetch for the CTA one wave later: its x is in L2 when it starts
+            const int n = (blockIdx.x + wave) * kTcRois + lane;
+            if (n < live) {
+                const float* p0 = src.roi_feat + (size_t)n * 2304;
+                int pc = 1;
+                if (src.partial) {
+                    const int sb = __ldg(src.slot + n);
+                    if (sb >= 0) { p0 = src.partial + (size_t)sb * 2304; pc = __ldg(src.pieces + n); }
                 }
+                for (int k = 0; k < pc; ++k)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0 + (size_t)k * 2304), "r"(2304 * 4) : "memory");
             }
-            umma_commit(&s_free[s & 1]);
-            if (s == 7 || s == 25 || s == kTcSteps - 1) umma_commit(&s_phase);
         }
-    };
-    auto stagers_sync = [&]() { __syncthreads(); };
-    prefetch_b(0);
-    prefetch_b(1);
+        __syncwarp();
+        if (lane == 0)
+            for (int s = kTcBRing; s < kTcSteps; ++s) {
+                bar_wait(&s_free_b[s % kTcBRing], (uint32_t)((s / kTcBRing - 1) & 1));
+                load_b(s);
+            }
+        return;
+    }
 
-    // ============================== conv1: x [128 x 256] . W1 ==============================
-    // x is prefetched two K chunks ahead into registers.  A row's value is the sum of its RoI's partial slots:
-    // the first four slots of all four items are loaded back to back (16 independent 128-bit loads in flight
-    // per thread; a load-add-load-add loop would serialise on the in-order issue), the adds happen at use.
-    float4 xpa[kTcItems][4], xpb[kTcItems][4];      // two chunks in flight (even / odd K chunk)
-    auto load_x_chunk = [&](int kc, float4 (&xp)[kTcItems][4]) {
+    // ------------------------------ warp 9: the MMA issuer ------------------------------
+    // The warp stays converged and one elected lane issues: the compiler then keeps the descriptors in uniform
+    // registers and emits the MMAs back to back (a `lane == 0` branch wraps every tcgen05.mma in an
+    // ELECT / BRA.U.ANY loop, and with the per-step index arithmetic the single issuing thread, not the tensor
+    // core, set the pace: 95 cycles per MMA instead of the 48 that tools/tc_rate_probe.cu measures).  The 34
+    // steps are unrolled, so ring slots, parities, accumulator columns and tap shifts are immediates.
+    if (warp == kWorkerWarps) {
+        const uint32_t sbase = smem_addr(base), sring = smem_addr(ring);
+        const uint64_t eye = umma_desc(smem_addr(s_eye));
+        long long w_a = 0, w_b = 0, w_t = 0, t_c2 = 0, t_c3 = 0;      // trace build only: cycles waiting for A / B / t, conv2 / conv3 spans
 #pragma unroll
-        for (int q = 0; q < kTcItems; ++q) {        // 128 rows x 8 chunks of 4 channels
-            const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
-            const int rl = r / 9, p = r - rl * 9, c0 = 32 * kc + 4 * ch;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xp[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef RR_TC_EXP_NOX
-            if (rl < nroi && kc < 2) {
-#else
-            if (rl < nroi) {
-#endif
-                const int sb = s_sb[rl], pc = s_pc[rl];
-                if (sb < 0) {
-                    xp[q][0] = tc_load_x4(src, roi0 + rl, p, sb, 0, 1.f, c0);
+        for (int s = 0; s < kTcSteps; ++s) {
+            const long long c0 = TC_CLOCK();
+            if (s == 8) t_c2 = c0;
+            if (s == 26) { t_c2 = c0 - t_c2; t_c3 = c0; }
+            uint32_t sa_hi, sa_lo, d_col;
+            if (s < 8) {                                    // conv1: A = stage s % 3
+                bar_wait(&s_full_a[s % kAStages], (uint32_t)((s / kAStages) & 1));
+                sa_hi = sbase + (uint32_t)((s % kAStages) * kTcAStage);
+                sa_lo = sa_hi + kTcATile;
+                d_col = 0u;
+            } else {
+                const int kc = s & 1;                       // steps 8.. are (tap, kc) then (quarter, kc): kc = parity of s
+                int shift = 0;
+                if (s < 26) {
+                    if (s == 8) bar_wait(&s_tready, 0u);
+                    const int tap = (s - 8) >> 1;
+                    shift = 4 * (tap / 3 - 1) + (tap % 3 - 1);
+                    d_col = 64u;
                 } else {
-                    const float* pp = src.partial + (size_t)sb * 2304 + p * 256 + c0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < pc) xp[q][k] = __ldg(reinterpret_cast<const float4*>(pp + (size_t)k * 2304));
+                    if (s == 26) bar_wait(&s_tready, 1u);
+                    d_col = 128u + 64u * (uint32_t)((s - 26) >> 1);
                 }
+                sa_hi = sbase + (uint32_t)(kc * kPlaneBytes + (kMargin + shift) * 128);
+                sa_lo = sa_hi + 2 * kPlaneBytes;
+            }
+            const long long c1 = TC_CLOCK();
+            bar_wait(&s_full_b[s % kTcBRing], (uint32_t)((s / kTcBRing) & 1));
+            const long long c2 = TC_CLOCK();
+            if (s < 8) w_a += c1 - c0; else w_t += c1 - c0;
+            w_b += c2 - c1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const bool first = s == 0 || s == 8;        // conv3 accumulates onto the residual placed during conv1
+                const uint32_t sb = sring + (uint32_t)((s % kTcBRing) * kTcBSlot);
+                const uint64_t a_hi = umma_desc(sa_hi), a_lo = umma_desc(sa_lo);
+                const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {            // K = 32 per step: four K = 8 instructions, 32 bytes apart
+                    umma_tf32(tmem + d_col, a_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
+                    umma_tf32(tmem + d_col, a_hi + 2 * ks, b_lo + 2 * ks, 1u);
+                    umma_tf32(tmem + d_col, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
+                }
+#ifdef RR_TC_EXP_NOEYE
+                if (s < 0) {
+#else
+                if (s < 8) {                                // conv3's accumulator starts as x itself: D3[:, 32s .. 32s+32) = A . I
+#endif
+                    const uint32_t d3 = tmem + 128u + 32u * (uint32_t)s;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_tf32(d3, a_hi + 2 * ks, eye + 2 * ks, ks == 0 ? 0u : 1u, kIdescN32);
+                        umma_tf32(d3, a_lo + 2 * ks, eye + 2 * ks, 1u, kIdescN32);
+                    }
+                }
+                umma_commit(&s_free_b[s % kTcBRing]);
+                if (s < 8) umma_commit(&s_free_a[s % kAStages]);
+                if (s == 7) umma_commit(&s_phase[0]);
+                if (s == 25) umma_commit(&s_phase[1]);
+                if (s == kTcSteps - 1) umma_commit(&s_phase[2]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            TC_TRACE_VAL(26, w_a); TC_TRACE_VAL(27, w_b); TC_TRACE_VAL(28, w_t);
+            TC_TRACE_VAL(29, t_c2); TC_TRACE_VAL(30, TC_CLOCK() - t_c3);
+        }
+        return;
+    }
+
+    // ------------------------------ warps 0-8: workers ------------------------------
+    // conv1 A tile: 72 live rows x eight 16-byte chunks = 576 items, two per thread, the same two for all 8 K chunks
+    const float* xptr[kTcItems];
+    int xpc[kTcItems], xoff[kTcItems];
+    float xinv[kTcItems];
+    bool xdirect[kTcItems];
+#pragma unroll
+    for (int q = 0; q < kTcItems; ++q) {
+        const int i = tid + q * kWorkers, r72 = i >> 3, ch = i & 7;
+        const int rl = r72 / 9, p = r72 - rl * 9, m = kRoiRows * rl + 4 + 4 * (p / 3) + p % 3;
+        xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
+        xptr[q] = src.roi_feat; xpc[q] = 0; xinv[q] = 1.f; xdirect[q] = false;
+        if (rl < nroi) {
+            const int n = roi0 + rl;
+            const int sb = src.partial ? __ldg(src.slot + n) : -1;
+            if (sb < 0) {                                       // finished feature [256][9] (direct RoIAlign path / plain API)
+                xdirect[q] = true;
+                xptr[q] = src.roi_feat + (size_t)n * 2304 + p + 36 * ch;
+            } else {                                            // partial slots [pieces][9][256], to be summed and scaled
+                xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
+                xpc[q] = __ldg(src.pieces + n);
+                xinv[q] = 1.0f / __ldg(src.count + n);
+            }
+        }
+    }
+    // x is prefetched two K chunks ahead into registers, up to six slots per item, every load issued before the
+    // first add (a load-add-load-add loop would serialise on the in-order issue); the slots are L2 hits after
+    // the first wave thanks to the previous CTA's bulk prefetch.
+    float4 xpa[kTcItems][kTcSlotsInReg], xpb[kTcItems][kTcSlotsInReg];
+    auto load_x_chunk = [&](int kc, float4 (&xp)[kTcItems][kTcSlotsInReg]) {
+#pragma unroll
+        for (int q = 0; q < kTcItems; ++q) {
+            xp[q][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xdirect[q]) {
+                const float* g = xptr[q] + 288 * kc;
+                xp[q][0] = make_float4(__ldg(g), __ldg(g + 9), __ldg(g + 18), __ldg(g + 27));
+            } else {
+#pragma unroll
+                for (int k = 0; k < kTcSlotsInReg; ++k)
+                    if (k < xpc[q]) xp[q][k] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
             }
         }
     };
-    auto x_value = [&](int kc, int q, const float4 (&xp)[kTcItems][4]) {   // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
-        const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
-        const int rl = r / 9, p = r - rl * 9;
+    auto x_value = [&](int kc, int q, const float4 (&xp)[kTcItems][kTcSlotsInReg]) {   // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
         float4 v = xp[q][0];
-        if (rl < nroi && s_sb[rl] >= 0) {
-            const int sb = s_sb[rl], pc = s_pc[rl];
+        if (!xdirect[q]) {
 #pragma unroll
-            for (int k = 1; k < 4; ++k) { v.x += xp[q][k].x; v.y += xp[q][k].y; v.z += xp[q][k].z; v.w += xp[q][k].w; }
-#ifdef RR_TC_EXP_NOTAIL
-            for (int k = 4; k < 0; ++k) {
-#else
-            for (int k = 4; k < pc; ++k) {          // RoIs cut into more than four pieces are rare
-#endif
-                const float4 t = __ldg(reinterpret_cast<const float4*>(src.partial + (size_t)(sb + k) * 2304 + p * 256 + 32 * kc + 4 * ch));
+            for (int k = 1; k < kTcSlotsInReg; ++k)
+                if (k < xpc[q]) { v.x += xp[q][k].x; v.y += xp[q][k].y; v.z += xp[q][k].z; v.w += xp[q][k].w; }
+            for (int k = kTcSlotsInReg; k < xpc[q]; ++k) {      // RoIs cut into more than six pieces are rare
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
-            const float inv = s_inv[rl];
+            const float inv = xinv[q];
             v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
         }
         return v;
     };
-    auto conv1_step = [&](int kc, float4 (&xp)[kTcItems][4]) {
-        const int s = step++;
-        acquire(s);
-        prefetch_b(s + 2);
-        uint8_t* a_hi = stage[s & 1];
+    auto conv1_step = [&](int kc, float4 (&xp)[kTcItems][kTcSlotsInReg]) {
+        const int st = kc % kAStages;
+        if (kc >= kAStages) bar_wait_warp(&s_free_a[st], (uint32_t)((kc / kAStages - 1) & 1));
+        uint8_t* a_hi = base + st * kTcAStage;
         uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
         for (int q = 0; q < kTcItems; ++q) {
-            const int i = tid + q * kTcThreads;
-            store_split(a_hi, a_lo, i >> 3, i & 7, x_value(kc, q, xp));
+            float4 hi, lo;
+            split4(x_value(kc, q, xp), hi, lo);
+            *reinterpret_cast<float4*>(a_hi + xoff[q]) = hi;
+            *reinterpret_cast<float4*>(a_lo + xoff[q]) = lo;
         }
         if (kc + 2 < 8) load_x_chunk(kc + 2, xp);   // in flight across two steps
-        publish(s);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) bar_arrive(&s_full_a[st]);
         TC_TRACE(16 + kc);
     };
     load_x_chunk(0, xpa);
-    TC_TRACE(2);
     load_x_chunk(1, xpb);
+    TC_TRACE(2);
 #pragma unroll 1
     for (int kc = 0; kc < 8; kc += 2) {
         conv1_step(kc, xpa);
         conv1_step(kc + 1, xpb);
     }
     TC_TRACE(3);
-    bar_wait(&s_phase, 0u);
+
+    // t = relu(D + b) of conv1 / conv2 -> (hi, lo) tf32 planes in the MMA tile layout.  Eight warps cover the
+    // 4 TMEM lane quarters x 2 column halves (= K chunks of the next GEMM); the ninth zeroes the plane margins.
+    auto epilogue_t = [&](uint32_t col0, const float* bias, bool mask_pad) {
+        if (warp < 8) {
+            const int q = warp & 3, h = warp >> 2, m = 32 * q + lane;
+            const bool keep = !mask_pad || ((m & 15) >= 4 && (m & 3) != 3);     // conv2 reads the pad rows as zeros
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + col0 + (uint32_t)(32 * h), v);
+            uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + m) * 128;
+            uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 o;
+                o.x = keep ? fmaxf(v[4 * c] + bias[32 * h + 4 * c], 0.f) : 0.f;
+                o.y = keep ? fmaxf(v[4 * c + 1] + bias[32 * h + 4 * c + 1], 0.f) : 0.f;
+                o.z = keep ? fmaxf(v[4 * c + 2] + bias[32 * h + 4 * c + 2], 0.f) : 0.f;
+                o.w = keep ? fmaxf(v[4 * c + 3] + bias[32 * h + 4 * c + 3], 0.f) : 0.f;
+                float4 hi, lo;
+                split4(o, hi, lo);
+                const int off = (c ^ (m & 7)) << 4;
+                *reinterpret_cast<float4*>(p_hi + off) = hi;
+                *reinterpret_cast<float4*>(p_lo + off) = lo;
+            }
+        } else if (mask_pad) {
+            for (int i = lane; i < 4 * 16 * 8; i += 32) {       // 4 planes x (8 + 8) margin rows x 8 chunks
+                const int pl = i >> 7, r = (i >> 3) & 15, c = i & 7;
+                const int row = r < 8 ? r : kMargin + 128 + (r - 8);
+                *reinterpret_cast<float4*>(base + pl * kPlaneBytes + row * 128 + c * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(&s_tready);
+    };
+    bar_wait_warp(&s_phase[0], 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_TRACE(4);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp < 8) {   // t1 = relu(D1 + b1) -> (hi, lo) planes [row][64]; eight warps cover 4 lane quarters x 2 column halves
-        const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * h), v);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = fmaxf(v[j] + __ldg(f + kOffB1 + 32 * h + j), 0.f);
-            o.y = fmaxf(v[j + 1] + __ldg(f + kOffB1 + 32 * h + j + 1), 0.f);
-            o.z = fmaxf(v[j + 2] + __ldg(f + kOffB1 + 32 * h + j + 2), 0.f);
-            o.w = fmaxf(v[j + 3] + __ldg(f + kOffB1 + 32 * h + j + 3), 0.f);
-            float4 hi, lo;
-            split4(o, hi, lo);
-            *reinterpret_cast<float4*>(s_thi + row * kT1Stride + 32 * h + j) = hi;
-            *reinterpret_cast<float4*>(s_tlo + row * kT1Stride + 32 * h + j) = lo;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    stagers_sync();
+    epilogue_t(0u, s_b1, true);
     TC_TRACE(5);
-
-    // ============================== conv2: 9 taps, A rows = shifted rows of t1 ==============================
-    for (int t = 0; t < 18; ++t) {
-        const int s = step++;
-        const int tap = t >> 1, kc = t & 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
-        acquire(s);
-        prefetch_b(s + 2);
-        uint8_t* a_hi = stage[s & 1];
-        uint8_t* a_lo = a_hi + kTcATile;
-#pragma unroll
-        for (int q = 0; q < kTcItems; ++q) {
-            const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
-            float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-            const int rl = r / 9, p = r - rl * 9, py = p / 3 + dy, px = p % 3 + dx;
-            if (rl < kTcRois && py >= 0 && py < 3 && px >= 0 && px < 3) {     // zero padding of the 3x3 map
-                const int o = (r + dy * 3 + dx) * kT1Stride + 32 * kc + 4 * ch;
-                hi = *reinterpret_cast<const float4*>(s_thi + o);
-                lo = *reinterpret_cast<const float4*>(s_tlo + o);
-            }
-            store_tiles(a_hi, a_lo, r, ch, hi, lo);
-        }
-        publish(s);
-    }
     TC_TRACE(6);
-    bar_wait(&s_phase, 1u);
+    bar_wait_warp(&s_phase[1], 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_TRACE(7);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp < 8) {   // t2 = relu(D2 + b2) -> overwrites t1 (every tap has been staged and consumed)
-        const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 64u + (uint32_t)(32 * h), v);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = fmaxf(v[j] + __ldg(f + kOffB2 + 32 * h + j), 0.f);
-            o.y = fmaxf(v[j + 1] + __ldg(f + kOffB2 + 32 * h + j + 1), 0.f);
-            o.z = fmaxf(v[j + 2] + __ldg(f + kOffB2 + 32 * h + j + 2), 0.f);
-            o.w = fmaxf(v[j + 3] + __ldg(f + kOffB2 + 32 * h + j + 3), 0.f);
-            float4 hi, lo;
-            split4(o, hi, lo);
-            *reinterpret_cast<float4*>(s_thi + row * kT1Stride + 32 * h + j) = hi;
-            *reinterpret_cast<float4*>(s_tlo + row * kT1Stride + 32 * h + j) = lo;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    stagers_sync();
+    epilogue_t(64u, s_b2, false);
     TC_TRACE(8);
-
-    // ============================== conv3: t2 [128 x 64] . W3, four N quarters ==============================
-    for (int t = 0; t < 8; ++t) {
-        const int s = step++;                       // s & 1 == kc: the A chunk kc stays in stage kc for all quarters
-        const int q4 = t >> 1, kc = t & 1;
-        acquire(s);
-        prefetch_b(s + 2);
-        if (q4 == 0) {
-            uint8_t* a_hi = stage[s & 1];
-            uint8_t* a_lo = a_hi + kTcATile;
-#pragma unroll
-            for (int q = 0; q < kTcItems; ++q) {
-                const int i = tid + q * kTcThreads, r = i >> 3, ch = i & 7;
-                const int o = r * kT1Stride + 32 * kc + 4 * ch;
-                store_tiles(a_hi, a_lo, r, ch, *reinterpret_cast<const float4*>(s_thi + o),
-                            *reinterpret_cast<const float4*>(s_tlo + o));
-            }
-        }
-        publish(s);      // accumulates onto the residual placed by conv1
-        if (t == 0) TC_TRACE(24); if (t == 6) TC_TRACE(25);
-    }
     TC_TRACE(9);
-    bar_wait(&s_phase, 0u);
-    TC_TRACE(10);
+    bar_wait_warp(&s_phase[2], 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TC_TRACE(10);
 
-    // ============================== + b3 + residual, relu, avg-pool over the 9 rows, regressor ==============================
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    float* s_relu = reinterpret_cast<float*>(stage[0]);            // [2][128][33] = 33 KB over both A stages, idle now
-    {
-        const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
-        for (int cb = 0; cb < 4; ++cb) {            // warps 0-3: column blocks 2cb, warps 4-7: 2cb+1 (32 columns each)
-            if (warp < 8) {
-                const int c0 = 32 * (2 * cb + h);
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)c0, v);    // W3.t2 + x (residual already inside)
-                float* dst = s_relu + (h * 128 + row) * 33;
+    // ============================== + b3 (+ residual, already inside), relu, regressor per row, mean over the 9 rows ==============================
+    if (warp < 8) {
+        const int q = warp & 3, g = warp >> 2, m = 32 * q + lane;
+        const bool keep = (m & 15) >= 4 && (m & 3) != 3;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) {
+            const int c0 = 32 * (4 * g + j);
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dst[j] = fmaxf(v[j] + __ldg(f + kOffB3 + c0 + j), 0.f);   // resnet.py:49-50
+            for (int e = 0; e < 32; ++e) {
+                const float y = fmaxf(v[e] + s_b3[c0 + e], 0.f);            // resnet.py:49-50
+                const float4 w = s_wr[c0 + e];
+                acc.x = fmaf(y, w.x, acc.x); acc.y = fmaf(y, w.y, acc.y); acc.z = fmaf(y, w.z, acc.z); acc.w = fmaf(y, w.w, acc.w);
             }
-            stagers_sync();
-            for (int i = tid; i < 2 * kTcRois * 32; i += kTcThreads) {      // (half, roi, column): mean of 9 rows
-                const int hh = i / (kTcRois * 32), rem = i - hh * (kTcRois * 32), r2 = rem >> 5, c = rem & 31;
-                const float* sp = s_relu + (hh * 128 + r2 * 9) * 33 + c;
-                float acc = 0.f;
+        }
+        if (!keep) acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int pp = 0; pp < 9; ++pp) acc += sp[pp * 33];
-                s_pool[r2 * 256 + 32 * (2 * cb + hh) + c] = acc / 9.0f;
-            }
-            stagers_sync();
+        for (int o = 8; o > 0; o >>= 1) {                       // the 16 rows of a RoI sit in one half warp
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
-    }
-    for (int rl = warp; rl < nroi; rl += kTcThreads / 32) {        // regressor 256 -> 4 (+ bias)
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-        for (int o = lane; o < 256; o += 32) {
-            const float pv = s_pool[rl * 256 + o];
-            r0 = fmaf(__ldg(f + kOffWr + o), pv, r0);
-            r1 = fmaf(__ldg(f + kOffWr + 256 + o), pv, r1);
-            r2 = fmaf(__ldg(f + kOffWr + 512 + o), pv, r2);
-            r3 = fmaf(__ldg(f + kOffWr + 768 + o), pv, r3);
-        }
-        r0 = warp_sum(r0); r1 = warp_sum(r1); r2 = warp_sum(r2); r3 = warp_sum(r3);
-        if (lane == 0)
-            reinterpret_cast<float4*>(reg)[roi0 + rl] = make_float4(r0 + __ldg(f + kOffBr), r1 + __ldg(f + kOffBr + 1),
-                                                                    r2 + __ldg(f + kOffBr + 2), r3 + __ldg(f + kOffBr + 3));
+        if ((lane & 15) == 0) s_part[g][2 * q + (lane >> 4)] = acc;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    stagers_sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+    if (tid < nroi) {
+        const float4 a = s_part[0][tid], b = s_part[1][tid];
+        reinterpret_cast<float4*>(reg)[roi0 + tid] =
+            make_float4((a.x + b.x) / 9.0f + __ldg(f + kOffBr), (a.y + b.y) / 9.0f + __ldg(f + kOffBr + 1),
+                        (a.z + b.z) / 9.0f + __ldg(f + kOffBr + 2), (a.w + b.w) / 9.0f + __ldg(f + kOffBr + 3));
+    }
     TC_TRACE(12);
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    }
 }
 
 int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded, float* reg, cudaStream_t st) {
@@ -499,8 +527,9 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
         RR_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem), rc);
         attr_set = true;
     }
+    if (((uintptr_t)folded & 15) != 0) return RR_E_BADARG;     // the weight stream is copied in 16-byte units
     const int grid = (n_cap + kTcRois - 1) / kTcRois;
-    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
+    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg, kSMs);
     RR_LAUNCHED(rc);
     return rc;
 }

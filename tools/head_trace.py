@@ -13,8 +13,7 @@ from rrnet_b200 import build as B  # noqa: E402
 TRACE_LIB = os.path.join(ROOT, "tools", "librrnet_trace.so")
 
 
-VARIANTS = {"": [], "nob": ["-DRR_TC_EXP_NOB"], "nox": ["-DRR_TC_EXP_NOX"], "noeye": ["-DRR_TC_EXP_NOEYE"],
-            "notail": ["-DRR_TC_EXP_NOTAIL"], "nob_nox": ["-DRR_TC_EXP_NOB", "-DRR_TC_EXP_NOX"]}
+VARIANTS = {"": [], "noeye": ["-DRR_TC_EXP_NOEYE"]}
 
 
 def lib_path(variant):
@@ -62,17 +61,18 @@ def main():
         path.forward(d["hm"], d["wh"], d["off"], d["feat"])
     torch.cuda.synchronize()
     L = _lib.lib()
-    n = 1024 * 32
+    n = 2048 * 32
     buf = (ctypes.c_uint64 * n)()
     L.rr_debug_head_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     rc = L.rr_debug_head_trace(buf, n)
     assert rc == 0, rc
-    t = np.frombuffer(buf, dtype=np.uint64).reshape(1024, 32).astype(np.int64)
-    n_cta = (Bn * K + 13) // 14
-    t = t[:min(n_cta, 1024)]
+    t = np.frombuffer(buf, dtype=np.uint64).reshape(2048, 32).astype(np.int64)
+    n_live = int(path.counts[-1].item())
+    n_cta = (n_live + 7) // 8
+    t = t[:min(n_cta, 2048)]
     t0 = t[:, 0].min()
-    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "conv2 loop", "conv2 mma wait", "epi2",
-             "conv3 loop", "conv3 mma wait", "pool+reg"]
+    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "-", "conv2 mma wait", "epi2",
+             "-", "conv3 mma wait", "regress"]
     marks = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]
     print("CTAs traced %d; kernel span %.1f us" % (len(t), (t[:, 12].max() - t0) / 1e3))
     dur = t[:, 12] - t[:, 0]
@@ -86,16 +86,16 @@ def main():
             print("   %-16s %7.2f" % (nm, seg.mean()))
     steps = np.diff(np.concatenate([t[:, 2:3], t[:, 16:24]], axis=1), axis=1) / 1e3
     print("conv1 per-step us (mean over CTAs):", np.round(steps.mean(axis=0), 2))
-    print("conv3 steps 1..6 mean us/step: %.2f" % ((t[:, 25] - t[:, 24]).mean() / 6e3))
+    print("issuer thread, mean cycles per CTA: wait A %.0f  wait B %.0f  wait t1/t2 %.0f | conv2 issue span %.0f  conv3 issue span %.0f" % tuple(
+        t[:, k].mean() for k in (26, 27, 28, 29, 30)))
     # how many tile pieces the RoIs of this workload are cut into (approximation of roi_prep_kernel's count)
-    n_live = int(path.counts[-1].item()) if path.counts[-1].item() > 0 else int(path.counts.sum().item())
     bx = path.bxyxy[:n_live].float().cpu().numpy()
     ntx = np.floor((bx[:, 3] + 1) / 32) - np.floor(bx[:, 1] / 32) + 1
     nty = np.floor((bx[:, 4] + 1) / 24) - np.floor(bx[:, 2] / 24) + 1
     pcs = (ntx * nty).astype(int)
     print("RoIs %d; pieces histogram:" % n_live, np.bincount(pcs)[:16], " mean %.2f" % pcs.mean())
-    grp = pcs[: (len(pcs) // 14) * 14].reshape(-1, 14)
-    print("CTAs whose 14 RoIs include one with > 4 pieces: %.1f %%" % (100.0 * (grp.max(axis=1) > 4).mean()))
+    grp = pcs[: (len(pcs) // 8) * 8].reshape(-1, 8)
+    print("CTAs whose 8 RoIs include one with > 6 pieces: %.1f %%" % (100.0 * (grp.max(axis=1) > 6).mean()))
 
 
 if __name__ == "__main__":
