@@ -17,7 +17,7 @@ size_t stage1_nms_ws_bytes(int B, int K, int C);
 int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, int, int, float*, void*,
                      cudaStream_t);
 void roi_align_ws_views(void*, int, int, int, int, int, const float**, const int**, const int**, const float**);
-int head_forward_launch_partial(const float*, const float*, const int*, const int*, const float*, const int32_t*, int,
+int head_forward_launch_partial(float*, const float*, const int*, const int*, const float*, const int32_t*, int,
                                 const float*, float*, int, cudaStream_t);
 size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W);
 int head_forward_launch(const float*, const int32_t*, int, const float*, float*, int, cudaStream_t);

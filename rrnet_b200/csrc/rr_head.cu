@@ -285,16 +285,18 @@ int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, cons
 // algo: 0 = tcgen05 tensor cores (3xTF32), 1 = fp32 FFMA
 int head_forward_launch(const float* roi_feat, const int32_t* n_rois_dev, int n_cap, const float* folded,
                         float* reg, int algo, cudaStream_t st) {
-    HeadSrc src = {roi_feat, nullptr, nullptr, nullptr, nullptr};
+    HeadSrc src = {roi_feat, nullptr, nullptr, nullptr, nullptr, nullptr};
     return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
                      : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }
 
 // fused eval path: inputs straight from the tile-centric RoIAlign's partial slots
-int head_forward_launch_partial(const float* roi_feat, const float* partial, const int* slot, const int* pieces,
+// roi_feat is the eval workspace's own feature buffer here: the rows of tile-path RoIs are unused by RoIAlign
+// (combine == 0), so the tensor-core head keeps its residual copy of x there
+int head_forward_launch_partial(float* roi_feat, const float* partial, const int* slot, const int* pieces,
                                 const float* count, const int32_t* n_rois_dev, int n_cap, const float* folded,
                                 float* reg, int algo, cudaStream_t st) {
-    HeadSrc src = {roi_feat, partial, slot, pieces, count};
+    HeadSrc src = {roi_feat, partial, slot, pieces, count, roi_feat};
     return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
                      : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }

@@ -40,6 +40,7 @@ struct HeadSrc {
     const int* slot;           // [n_cap] first slot, < 0: direct path
     const int* pieces;         // [n_cap] number of slots (0: all-zero output)
     const float* count;        // [n_cap] divisor
+    float* scratch;            // [n_cap,9,256] workspace for the tensor-core head's residual copy of x (tile-path RoIs), with partial
 };
 
 int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded, float* reg, cudaStream_t st);

@@ -13,21 +13,26 @@
 //                                                   descriptor whose start address is shifted by 4 dy + dx rows
 //                                                   (the 128-byte swizzle is a function of the address, so a
 //                                                   128-byte-aligned start is legal: tools/tc_shift_probe.cu)
-//     conv3  [128 x  64] x [64 x 256]               4 N-quarters x 2 K-chunks
+//     conv3  [128 x  64] x [64 x 256]               2 halves of 2 N-quarters x 2 K-chunks
 // Nothing is restaged between the taps: after conv1 the only data movement is the weight stream.
-// Every MMA is tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8; the accumulators live in TMEM
-// (conv1: columns 0-63, conv2: 64-127, conv3: 128-383) and come back with tcgen05.ld for the epilogues.  The
-// residual x is added by the tensor core too: while a K chunk of x sits in shared memory for conv1, one more
-// MMA against a 32 x 32 identity tile deposits it in conv3's accumulator columns, so x is read exactly once.
-// An fp32 product a*b is evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with hi = tf32(v), lo = tf32(v - hi):
-// three MMAs per K-step, error ~2^-21 relative per product, inside the 1e-5 parity budget.
+// Every MMA is tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8, both operands in shared memory:
+// 48 cycles each, bound by the 6 KB of operands it reads (tools/tc_rate_probe.cu), not by the 32 cycles of
+// math.  An fp32 product a*b is evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with hi = tf32(v),
+// lo = tf32(v - hi): three MMAs per K-step, error ~2^-21 relative per product, inside the 1e-5 parity budget.
+//
+// The tensor pipe idles while a tile is loaded and during its epilogues, and the workers idle during conv2 /
+// conv3, so TWO CTAs share an SM and fill each other's gaps.  That sets the budget of one CTA: 256 TMEM columns
+// (conv1 and conv2 share columns 0-63, a conv3 half has 64-191, the two halves run one after the other),
+// <= 113 KB of shared memory (the t1 / t2 tiles reuse the conv1 stages, the weight ring has two slots) and
+// <= 88 registers per thread.  The residual x is added in the last epilogue from a per-RoI fp32 copy the workers
+// leave in global memory (L2) while they stage conv1.
 //
 // Warp roles (no block-wide barrier after the prologue; mbarriers connect the roles):
-//   warps 0-8   workers: sum the RoIs' partial slots (x), split, fill the three conv1 A stages; epilogues
-//   warp  9     lane 0 issues every tcgen05.mma and the tcgen05.commit that frees a stage / ring slot
+//   warps 0-8   workers: sum the RoIs' partial slots (x), split, fill the two conv1 A stages; epilogues
+//   warp  9     one elected lane issues every tcgen05.mma and the tcgen05.commit that frees a stage / ring slot
 //   warp  10    lane 0 streams the 34 pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
-//               rr_head_fold) through a ring of six slots with cp.async.bulk (TMA) + complete_tx; the warp
-//               also prefetches into L2 the x slots of the CTA that will follow this one on the SM
+//               rr_head_fold) with cp.async.bulk (TMA) + complete_tx; the warp also prefetches into L2 the x
+//               slots of the CTA that will follow this one on the SM
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
@@ -39,23 +44,26 @@ constexpr int kWorkerWarps = 9;
 constexpr int kWorkers = 32 * kWorkerWarps;      // 288 threads x 2 items = the 576 live (row, 16-byte chunk) items of an x tile
 constexpr int kTcItems = 2;
 constexpr int kTcSlotsInReg = 6;                 // partial slots of an item held in registers per K chunk
-constexpr int kTcBlock = kWorkers + 64;          // + the MMA issuer warp + the weight stream warp
+constexpr int kTcTiles = 2;                      // M = 128 tiles per CTA, in lockstep: every weight slot serves both
+constexpr int kTcBlock = kTcTiles * kWorkers + 64;   // + the MMA issuer warp + the weight stream warp
+constexpr int kTcCtasPerSm = 1;
 constexpr int kTcATile = 128 * 128;              // bytes: 128 rows x 32 tf32
 constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
 constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB
-constexpr int kAStages = 3;
+constexpr int kAStages = 2;
 constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one step of the weight image
-constexpr int kTcBRing = 6;
+constexpr int kTcBRing = 4;
 constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
 constexpr int kPlaneBytes = (128 + 2 * kMargin) * 128;
-static_assert(4 * kPlaneBytes <= kAStages * kTcAStage, "the t planes reuse the conv1 stages");
+constexpr int kRegion0 = 4 * kPlaneBytes;        // 72 KB: the conv1 stages (64 KB), then the four t planes
+static_assert(kRegion0 >= kAStages * kTcAStage, "the t planes reuse the conv1 stages");
 static_assert(kTcBSlot == kTcStepFloats * 4, "a ring slot is one step of the folded image");
-constexpr int kTcEyeBytes = 32 * 128;                // 32 x 32 identity tile (residual through the tensor core)
-constexpr int kTcSmem = kAStages * kTcAStage + kTcBRing * kTcBSlot + kTcEyeBytes + 1024;   // + slack for the 1024-byte alignment
+constexpr int kTcSmem = kTcTiles * kRegion0 + kTcBRing * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
+constexpr uint32_t kTileCols = 192;               // TMEM columns of one tile
+constexpr uint32_t kColD12 = 0, kColD3 = 64;     // conv1 / conv2 accumulator, conv3 half accumulator (128 columns)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 //                          D = f32      A = tf32     B = tf32      N = 64               M = 128      (both K-major)
-constexpr uint32_t kIdescN32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -89,7 +97,9 @@ __device__ __forceinline__ void bar_wait_warp(unsigned long long* bar, uint32_t 
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
             if (ok) break;
+#ifndef RR_TC_EXP_NOSLEEP
             __nanosleep(64);
+#endif
         }
     }
     __syncwarp();
@@ -167,8 +177,13 @@ __device__ unsigned long long g_tc_trace[2048 * 32];
 __device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ float4 ld_global_f4(const float* p) {      // coherent load: the data was written by this kernel
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 
-__global__ void __launch_bounds__(kTcBlock, 1)
+__global__ void __launch_bounds__(kTcBlock, kTcCtasPerSm)
 head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                const float* __restrict__ f, float* __restrict__ reg, int wave) {
     extern __shared__ uint8_t s_dyn[];
@@ -176,37 +191,36 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     __shared__ __align__(8) unsigned long long s_free_a[kAStages];   // ... consumed (tcgen05.commit)
     __shared__ __align__(8) unsigned long long s_full_b[kTcBRing];   // weight slot landed (complete_tx)
     __shared__ __align__(8) unsigned long long s_free_b[kTcBRing];   // ... consumed (tcgen05.commit)
-    __shared__ __align__(8) unsigned long long s_phase[3];           // all MMAs of conv1 / conv2 / conv3 are done
+    __shared__ __align__(8) unsigned long long s_phase[4];           // all MMAs of conv1 / conv2 / conv3 half 0 / half 1 are done
     __shared__ __align__(8) unsigned long long s_tready;             // t1 (then t2) tiles written by the epilogue
+    __shared__ __align__(8) unsigned long long s_d3free;             // conv3 half 0 has been read out of TMEM
     __shared__ uint32_t s_tmem;
+    __shared__ int s_sb[kTcTiles][kTcRois];
     __shared__ float s_b1[64], s_b2[64], s_b3[256];
     __shared__ float4 s_wr[256];                                     // regressor weights, one float4 per channel
-    __shared__ float4 s_part[2][kTcRois];
+    __shared__ float4 s_part[kTcTiles][2][kTcRois];
     TC_TRACE(0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
-    const int roi0 = blockIdx.x * kTcRois;
-    if (roi0 >= live) return;
-    const int nroi = min(kTcRois, live - roi0);
+    if (blockIdx.x * (kTcTiles * kTcRois) >= live) return;
 
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)s_dyn + 1023) & ~(uintptr_t)1023);
-    // [0, 96 KB): three conv1 A stages (A_hi | A_lo); after conv1 the same bytes hold the t1 / t2 tiles:
+    // [0, 72 KB): two conv1 A stages (A_hi | A_lo); after conv1 the same bytes hold the t1 / t2 tiles:
     // plane (hi|lo, kc) at base + (2*lo + kc) * kPlaneBytes, 8 zero rows, the 128 tile rows, 8 zero rows
-    uint8_t* ring = base + kAStages * kTcAStage;                                // kTcBRing x (B_hi | B_lo)
-    float* s_eye = reinterpret_cast<float*>(ring + kTcBRing * kTcBSlot);        // identity B tile, 32 x 32
+    uint8_t* ring = base + kTcTiles * kRegion0;                                            // kTcBRing x (B_hi | B_lo)
 
     // ------------------------------ prologue (all warps) ------------------------------
-    for (int i = tid; i < 32 * 32; i += kTcBlock) {         // I[n][k] in the swizzled tile layout
-        const int n = i >> 5, k = i & 31;
-        s_eye[n * 32 + ((((k >> 2) ^ (n & 7))) << 2) + (k & 3)] = (n == k) ? 1.0f : 0.0f;
-    }
-    for (int i = tid; i < kAStages * kTcAStage / 16; i += kTcBlock)             // pad rows of the A stages stay zero
+    for (int i = tid; i < kTcTiles * kRegion0 / 16; i += kTcBlock)              // pad rows of the A stages stay zero
         reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < 64; i += kTcBlock) { s_b1[i] = __ldg(f + kOffB1 + i); s_b2[i] = __ldg(f + kOffB2 + i); }
     for (int i = tid; i < 256; i += kTcBlock) {
         s_b3[i] = __ldg(f + kOffB3 + i);
         s_wr[i] = make_float4(__ldg(f + kOffWr + i), __ldg(f + kOffWr + 256 + i), __ldg(f + kOffWr + 512 + i),
                               __ldg(f + kOffWr + 768 + i));
+    }
+    if (tid >= 64 && tid < 64 + kTcTiles * kTcRois) {
+        const int n = blockIdx.x * (kTcTiles * kTcRois) + (tid - 64);
+        (&s_sb[0][0])[tid - 64] = (n < live && src.partial) ? __ldg(src.slot + n) : -1;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "n"(kTmemCols) : "memory");
@@ -216,13 +230,14 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         auto init = [](unsigned long long* b, int count) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
         };
-        for (int i = 0; i < kAStages; ++i) { init(&s_full_a[i], kWorkerWarps); init(&s_free_a[i], 1); }
+        for (int i = 0; i < kAStages; ++i) { init(&s_full_a[i], kTcTiles * kWorkerWarps); init(&s_free_a[i], 1); }
         for (int i = 0; i < kTcBRing; ++i) { init(&s_full_b[i], 1); init(&s_free_b[i], 1); }
-        for (int i = 0; i < 3; ++i) init(&s_phase[i], 1);
-        init(&s_tready, kWorkerWarps);
+        for (int i = 0; i < 4; ++i) init(&s_phase[i], 1);
+        init(&s_tready, kTcTiles * kWorkerWarps);
+        init(&s_d3free, kTcTiles * 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // identity tile + zero fill -> visible to the MMA
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // zero fill -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -231,7 +246,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     const float* ftc = f + kOffTc;
 
     // ------------------------------ warp 10: the weight stream ------------------------------
-    if (warp == kWorkerWarps + 1) {
+    if (warp == kTcTiles * kWorkerWarps + 1) {
         auto load_b = [&](int s) {
             const uint32_t bar = smem_addr(&s_full_b[s % kTcBRing]);
             const uint32_t dst = smem_addr(ring + (s % kTcBRing) * kTcBSlot);
@@ -241,20 +256,6 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         };
         if (lane == 0)
             for (int s = 0; s < kTcBRing; ++s) load_b(s);
-        __syncwarp();
-        if (lane < kTcRois) {       // L2 prefetch for the CTA one wave later: its x is in L2 when it starts
-            const int n = (blockIdx.x + wave) * kTcRois + lane;
-            if (n < live) {
-                const float* p0 = src.roi_feat + (size_t)n * 2304;
-                int pc = 1;
-                if (src.partial) {
-                    const int sb = __ldg(src.slot + n);
-                    if (sb >= 0) { p0 = src.partial + (size_t)sb * 2304; pc = __ldg(src.pieces + n); }
-                }
-                for (int k = 0; k < pc; ++k)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0 + (size_t)k * 2304), "r"(2304 * 4) : "memory");
-            }
-        }
         __syncwarp();
         if (lane == 0)
             for (int s = kTcBRing; s < kTcSteps; ++s) {
@@ -268,128 +269,123 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     // The warp stays converged and one elected lane issues: the compiler then keeps the descriptors in uniform
     // registers and emits the MMAs back to back (a `lane == 0` branch wraps every tcgen05.mma in an
     // ELECT / BRA.U.ANY loop, and with the per-step index arithmetic the single issuing thread, not the tensor
-    // core, set the pace: 95 cycles per MMA instead of the 48 that tools/tc_rate_probe.cu measures).  The 34
-    // steps are unrolled, so ring slots, parities, accumulator columns and tap shifts are immediates.
-    if (warp == kWorkerWarps) {
+    // core, set the pace).  The 34 steps are unrolled: ring slots, parities, columns and tap shifts are immediates.
+    if (warp == kTcTiles * kWorkerWarps) {
         const uint32_t sbase = smem_addr(base), sring = smem_addr(ring);
-        const uint64_t eye = umma_desc(smem_addr(s_eye));
-        long long w_a = 0, w_b = 0, w_t = 0, t_c2 = 0, t_c3 = 0;      // trace build only: cycles waiting for A / B / t, conv2 / conv3 spans
 #pragma unroll
         for (int s = 0; s < kTcSteps; ++s) {
-            const long long c0 = TC_CLOCK();
-            if (s == 8) t_c2 = c0;
-            if (s == 26) { t_c2 = c0 - t_c2; t_c3 = c0; }
             uint32_t sa_hi, sa_lo, d_col;
-            if (s < 8) {                                    // conv1: A = stage s % 3
+            if (s < 8) {                                    // conv1: A = stage s % 2
                 bar_wait(&s_full_a[s % kAStages], (uint32_t)((s / kAStages) & 1));
                 sa_hi = sbase + (uint32_t)((s % kAStages) * kTcAStage);
                 sa_lo = sa_hi + kTcATile;
-                d_col = 0u;
+                d_col = kColD12;
             } else {
                 const int kc = s & 1;                       // steps 8.. are (tap, kc) then (quarter, kc): kc = parity of s
                 int shift = 0;
                 if (s < 26) {
-                    if (s == 8) bar_wait(&s_tready, 0u);
+                    if (s == 8) bar_wait(&s_tready, 0u);    // t1 is in place (and D1 has been read: conv2 reuses its columns)
                     const int tap = (s - 8) >> 1;
                     shift = 4 * (tap / 3 - 1) + (tap % 3 - 1);
-                    d_col = 64u;
+                    d_col = kColD12;
                 } else {
                     if (s == 26) bar_wait(&s_tready, 1u);
-                    d_col = 128u + 64u * (uint32_t)((s - 26) >> 1);
+                    if (s == 30) bar_wait(&s_d3free, 0u);   // the first half has left TMEM
+                    d_col = kColD3 + 64u * (uint32_t)(((s - 26) >> 1) & 1);
                 }
                 sa_hi = sbase + (uint32_t)(kc * kPlaneBytes + (kMargin + shift) * 128);
                 sa_lo = sa_hi + 2 * kPlaneBytes;
             }
-            const long long c1 = TC_CLOCK();
             bar_wait(&s_full_b[s % kTcBRing], (uint32_t)((s / kTcBRing) & 1));
-            const long long c2 = TC_CLOCK();
-            if (s < 8) w_a += c1 - c0; else w_t += c1 - c0;
-            w_b += c2 - c1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                const bool first = s == 0 || s == 8;        // conv3 accumulates onto the residual placed during conv1
+                const bool first = s == 0 || s == 8 || (s >= 26 && (s & 1) == 0);   // first K chunk of an accumulator
                 const uint32_t sb = sring + (uint32_t)((s % kTcBRing) * kTcBSlot);
                 const uint64_t a_hi = umma_desc(sa_hi), a_lo = umma_desc(sa_lo);
                 const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {            // K = 32 per step: four K = 8 instructions, 32 bytes apart
-                    umma_tf32(tmem + d_col, a_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
-                    umma_tf32(tmem + d_col, a_hi + 2 * ks, b_lo + 2 * ks, 1u);
-                    umma_tf32(tmem + d_col, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
-                }
-#ifdef RR_TC_EXP_NOEYE
-                if (s < 0) {
-#else
-                if (s < 8) {                                // conv3's accumulator starts as x itself: D3[:, 32s .. 32s+32) = A . I
-#endif
-                    const uint32_t d3 = tmem + 128u + 32u * (uint32_t)s;
+                for (int t = 0; t < kTcTiles; ++t) {
+                    const uint64_t ta_hi = a_hi + (uint64_t)(t * (kRegion0 >> 4)), ta_lo = a_lo + (uint64_t)(t * (kRegion0 >> 4));
+                    const uint32_t d = tmem + (uint32_t)t * kTileCols + d_col;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        umma_tf32(d3, a_hi + 2 * ks, eye + 2 * ks, ks == 0 ? 0u : 1u, kIdescN32);
-                        umma_tf32(d3, a_lo + 2 * ks, eye + 2 * ks, 1u, kIdescN32);
+                    for (int ks = 0; ks < 4; ++ks) {        // K = 32 per step: four K = 8 instructions, 32 bytes apart
+                        umma_tf32(d, ta_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
+                        umma_tf32(d, ta_hi + 2 * ks, b_lo + 2 * ks, 1u);
+                        umma_tf32(d, ta_lo + 2 * ks, b_hi + 2 * ks, 1u);
                     }
                 }
                 umma_commit(&s_free_b[s % kTcBRing]);
                 if (s < 8) umma_commit(&s_free_a[s % kAStages]);
                 if (s == 7) umma_commit(&s_phase[0]);
                 if (s == 25) umma_commit(&s_phase[1]);
-                if (s == kTcSteps - 1) umma_commit(&s_phase[2]);
+                if (s == 29) umma_commit(&s_phase[2]);
+                if (s == kTcSteps - 1) umma_commit(&s_phase[3]);
             }
             __syncwarp();
-        }
-        if (lane == 0) {
-            TC_TRACE_VAL(26, w_a); TC_TRACE_VAL(27, w_b); TC_TRACE_VAL(28, w_t);
-            TC_TRACE_VAL(29, t_c2); TC_TRACE_VAL(30, TC_CLOCK() - t_c3);
         }
         return;
     }
 
-    // ------------------------------ warps 0-8: workers ------------------------------
+    // ------------------------------ warps 0-17: two groups of nine worker warps, one tile each ------------------------------
+    const int grp = warp / kWorkerWarps;
+    const int roi0 = (blockIdx.x * kTcTiles + grp) * kTcRois;
+    const int nroi = max(0, min(kTcRois, live - roi0));        // 0: the last CTA's second tile may be empty (it still keeps step)
+    const int wtid = tid - grp * kWorkers, wwarp = warp - grp * kWorkerWarps;
+    base += grp * kRegion0;
+    const uint32_t tmem_t = tmem + (uint32_t)grp * kTileCols;
     // conv1 A tile: 72 live rows x eight 16-byte chunks = 576 items, two per thread, the same two for all 8 K chunks
     const float* xptr[kTcItems];
+    float* xscr[kTcItems];                                      // fp32 copy of x for the residual (tile-path RoIs)
     int xpc[kTcItems], xoff[kTcItems];
     float xinv[kTcItems];
-    bool xdirect[kTcItems];
 #pragma unroll
     for (int q = 0; q < kTcItems; ++q) {
-        const int i = tid + q * kWorkers, r72 = i >> 3, ch = i & 7;
+        const int i = wtid + q * kWorkers, r72 = i >> 3, ch = i & 7;
         const int rl = r72 / 9, p = r72 - rl * 9, m = kRoiRows * rl + 4 + 4 * (p / 3) + p % 3;
         xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
-        xptr[q] = src.roi_feat; xpc[q] = 0; xinv[q] = 1.f; xdirect[q] = false;
+        xptr[q] = src.roi_feat; xscr[q] = nullptr; xpc[q] = 0; xinv[q] = 1.f;
         if (rl < nroi) {
             const int n = roi0 + rl;
-            const int sb = src.partial ? __ldg(src.slot + n) : -1;
+            int sb = -1, pcs = 0;
+            float cnt = 1.f;
+            if (src.partial) { sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n); }
             if (sb < 0) {                                       // finished feature [256][9] (direct RoIAlign path / plain API)
-                xdirect[q] = true;
+                xpc[q] = -1;
                 xptr[q] = src.roi_feat + (size_t)n * 2304 + p + 36 * ch;
             } else {                                            // partial slots [pieces][9][256], to be summed and scaled
                 xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
-                xpc[q] = __ldg(src.pieces + n);
-                xinv[q] = 1.0f / __ldg(src.count + n);
+                xscr[q] = src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
+                xpc[q] = pcs;
+                xinv[q] = 1.0f / cnt;
             }
         }
     }
-    // x is prefetched two K chunks ahead into registers, up to six slots per item, every load issued before the
+    // x is prefetched one K chunk ahead into registers, up to six slots per item, every load issued before the
     // first add (a load-add-load-add loop would serialise on the in-order issue); the slots are L2 hits after
-    // the first wave thanks to the previous CTA's bulk prefetch.
-    float4 xpa[kTcItems][kTcSlotsInReg], xpb[kTcItems][kTcSlotsInReg];
-    auto load_x_chunk = [&](int kc, float4 (&xp)[kTcItems][kTcSlotsInReg]) {
+    // the first wave thanks to the previous CTA's bulk prefetch, and the other CTA of the SM covers the rest.
+    float4 xp[kTcItems][kTcSlotsInReg];
+    auto load_x_chunk = [&](int kc) {
 #pragma unroll
         for (int q = 0; q < kTcItems; ++q) {
             xp[q][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (xdirect[q]) {
+            if (xpc[q] < 0) {
                 const float* g = xptr[q] + 288 * kc;
                 xp[q][0] = make_float4(__ldg(g), __ldg(g + 9), __ldg(g + 18), __ldg(g + 27));
             } else {
 #pragma unroll
                 for (int k = 0; k < kTcSlotsInReg; ++k)
-                    if (k < xpc[q]) xp[q][k] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
+#ifdef RR_TC_EXP_NOX
+                    if (k < xpc[q] && kc < 1)
+#else
+                    if (k < xpc[q])
+#endif
+                        xp[q][k] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
             }
         }
     };
-    auto x_value = [&](int kc, int q, const float4 (&xp)[kTcItems][kTcSlotsInReg]) {   // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
+    auto x_value = [&](int kc, int q) {             // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
         float4 v = xp[q][0];
-        if (!xdirect[q]) {
+        if (xpc[q] >= 0) {
 #pragma unroll
             for (int k = 1; k < kTcSlotsInReg; ++k)
                 if (k < xpc[q]) { v.x += xp[q][k].x; v.y += xp[q][k].y; v.z += xp[q][k].z; v.w += xp[q][k].w; }
@@ -402,42 +398,39 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         }
         return v;
     };
-    auto conv1_step = [&](int kc, float4 (&xp)[kTcItems][kTcSlotsInReg]) {
+    load_x_chunk(0);
+    TC_TRACE(2);
+#pragma unroll 1
+    for (int kc = 0; kc < 8; ++kc) {
         const int st = kc % kAStages;
         if (kc >= kAStages) bar_wait_warp(&s_free_a[st], (uint32_t)((kc / kAStages - 1) & 1));
         uint8_t* a_hi = base + st * kTcAStage;
         uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
         for (int q = 0; q < kTcItems; ++q) {
+            const float4 v = x_value(kc, q);
             float4 hi, lo;
-            split4(x_value(kc, q, xp), hi, lo);
+            split4(v, hi, lo);
             *reinterpret_cast<float4*>(a_hi + xoff[q]) = hi;
             *reinterpret_cast<float4*>(a_lo + xoff[q]) = lo;
+            if (xscr[q]) *reinterpret_cast<float4*>(xscr[q] + 32 * kc) = v;
         }
-        if (kc + 2 < 8) load_x_chunk(kc + 2, xp);   // in flight across two steps
+        if (kc + 1 < 8) load_x_chunk(kc + 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
         __syncwarp();
         if (lane == 0) bar_arrive(&s_full_a[st]);
         TC_TRACE(16 + kc);
-    };
-    load_x_chunk(0, xpa);
-    load_x_chunk(1, xpb);
-    TC_TRACE(2);
-#pragma unroll 1
-    for (int kc = 0; kc < 8; kc += 2) {
-        conv1_step(kc, xpa);
-        conv1_step(kc + 1, xpb);
     }
     TC_TRACE(3);
 
     // t = relu(D + b) of conv1 / conv2 -> (hi, lo) tf32 planes in the MMA tile layout.  Eight warps cover the
     // 4 TMEM lane quarters x 2 column halves (= K chunks of the next GEMM); the ninth zeroes the plane margins.
-    auto epilogue_t = [&](uint32_t col0, const float* bias, bool mask_pad) {
-        if (warp < 8) {
-            const int q = warp & 3, h = warp >> 2, m = 32 * q + lane;
+    auto epilogue_t = [&](const float* bias, bool mask_pad) {
+        if (wwarp < 8) {                                    // a warp reaches the TMEM lane quarter warp % 4 of the CTA
+            const int q = warp & 3, h = wwarp >> 2, m = 32 * q + lane;
             const bool keep = !mask_pad || ((m & 15) >= 4 && (m & 3) != 3);     // conv2 reads the pad rows as zeros
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + col0 + (uint32_t)(32 * h), v);
+            tmem_ld32(tmem_t + ((uint32_t)(32 * q) << 16) + kColD12 + (uint32_t)(32 * h), v);
             uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + m) * 128;
             uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
 #pragma unroll
@@ -468,52 +461,85 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     bar_wait_warp(&s_phase[0], 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_TRACE(4);
-    epilogue_t(0u, s_b1, true);
+    epilogue_t(s_b1, true);
     TC_TRACE(5);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kWorkers) : "memory");   // every worker's copy of x is visible to the others
     TC_TRACE(6);
     bar_wait_warp(&s_phase[1], 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TC_TRACE(7);
-    epilogue_t(64u, s_b2, false);
+    epilogue_t(s_b2, false);
     TC_TRACE(8);
-    TC_TRACE(9);
-    bar_wait_warp(&s_phase[2], 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    TC_TRACE(10);
 
-    // ============================== + b3 (+ residual, already inside), relu, regressor per row, mean over the 9 rows ==============================
-    if (warp < 8) {
-        const int q = warp & 3, g = warp >> 2, m = 32 * q + lane;
-        const bool keep = (m & 15) >= 4 && (m & 3) != 3;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < 4; ++j) {
-            const int c0 = 32 * (4 * g + j);
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)c0, v);
+    // ======== y = D3 + b3 + x, relu (resnet.py:49-50), regressor per row, mean over the 9 rows; two halves of 128 channels ========
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int eq = warp & 3, eg = (wwarp >> 2) & 1, em = 32 * eq + lane;
+    const bool ekeep = wwarp < 8 && (em & 15) >= 4 && (em & 3) != 3 && (em >> 4) < nroi;
+    const float* res = nullptr;                                  // residual source of this thread's row
+    bool res_rows = false;                                       // true: [9][256] copy, false: [256][9] feature
+    if (ekeep) {
+        const int rl = em >> 4, rr = em & 15, p = 3 * ((rr - 4) >> 2) + (rr & 3), n = roi0 + rl;
+        res_rows = s_sb[grp][rl] >= 0;
+        res = res_rows ? src.scratch + (size_t)n * 2304 + p * 256 : src.roi_feat + (size_t)n * 2304 + p;
+    }
+    for (int half = 0; half < 2; ++half) {
+        bar_wait_warp(&s_phase[2 + half], 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (half == 0) TC_TRACE(9); else TC_TRACE(10);
+        if (wwarp < 8) {
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const int c0 = 128 * half + 64 * eg + 32 * j;
+                float x[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float y = fmaxf(v[e] + s_b3[c0 + e], 0.f);            // resnet.py:49-50
-                const float4 w = s_wr[c0 + e];
-                acc.x = fmaf(y, w.x, acc.x); acc.y = fmaf(y, w.y, acc.y); acc.z = fmaf(y, w.z, acc.z); acc.w = fmaf(y, w.w, acc.w);
+                for (int e = 0; e < 32; ++e) x[e] = 0.f;
+                if (ekeep) {
+                    if (res_rows) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 t = ld_global_f4(res + c0 + 4 * e);
+                            x[4 * e] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) x[e] = __ldg(res + (c0 + e) * 9);
+                    }
+                }
+                float v[32];
+                tmem_ld32(tmem_t + ((uint32_t)(32 * eq) << 16) + kColD3 + (uint32_t)(64 * eg + 32 * j), v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float y = fmaxf(v[e] + s_b3[c0 + e] + x[e], 0.f);
+                    const float4 w = s_wr[c0 + e];
+                    acc.x = fmaf(y, w.x, acc.x); acc.y = fmaf(y, w.y, acc.y); acc.z = fmaf(y, w.z, acc.z); acc.w = fmaf(y, w.w, acc.w);
+                }
+            }
+            if (half == 0) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) bar_arrive(&s_d3free);
             }
         }
-        if (!keep) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (wwarp < 8) {
+        if (!ekeep) acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {                       // the 16 rows of a RoI sit in one half warp
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
             acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
         }
-        if ((lane & 15) == 0) s_part[g][2 * q + (lane >> 4)] = acc;
+        if ((lane & 15) == 0) s_part[grp][eg][2 * eq + (lane >> 4)] = acc;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
-    if (tid < nroi) {
-        const float4 a = s_part[0][tid], b = s_part[1][tid];
-        reinterpret_cast<float4*>(reg)[roi0 + tid] =
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kWorkers) : "memory");
+    if (wtid < nroi) {
+        const float4 a = s_part[grp][0][wtid], b = s_part[grp][1][wtid];
+        reinterpret_cast<float4*>(reg)[roi0 + wtid] =
             make_float4((a.x + b.x) / 9.0f + __ldg(f + kOffBr), (a.y + b.y) / 9.0f + __ldg(f + kOffBr + 1),
                         (a.z + b.z) / 9.0f + __ldg(f + kOffBr + 2), (a.w + b.w) / 9.0f + __ldg(f + kOffBr + 3));
     }
     TC_TRACE(12);
+    asm volatile("bar.sync 3, %0;" ::"n"(kTcTiles * kWorkers) : "memory");      // both tiles are out of TMEM
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -528,8 +554,9 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
         attr_set = true;
     }
     if (((uintptr_t)folded & 15) != 0) return RR_E_BADARG;     // the weight stream is copied in 16-byte units
-    const int grid = (n_cap + kTcRois - 1) / kTcRois;
-    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg, kSMs);
+    if (src.partial && !src.scratch) return RR_E_BADARG;
+    const int grid = (n_cap + kTcTiles * kTcRois - 1) / (kTcTiles * kTcRois);
+    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg, kTcCtasPerSm * kSMs);
     RR_LAUNCHED(rc);
     return rc;
 }

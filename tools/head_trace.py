@@ -13,7 +13,7 @@ from rrnet_b200 import build as B  # noqa: E402
 TRACE_LIB = os.path.join(ROOT, "tools", "librrnet_trace.so")
 
 
-VARIANTS = {"": [], "noeye": ["-DRR_TC_EXP_NOEYE"]}
+VARIANTS = {"": [], "nox": ["-DRR_TC_EXP_NOX"]}
 
 
 def lib_path(variant):
@@ -68,11 +68,11 @@ def main():
     assert rc == 0, rc
     t = np.frombuffer(buf, dtype=np.uint64).reshape(2048, 32).astype(np.int64)
     n_live = int(path.counts[-1].item())
-    n_cta = (n_live + 7) // 8
+    n_cta = (n_live + 15) // 16
     t = t[:min(n_cta, 2048)]
     t0 = t[:, 0].min()
-    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "-", "conv2 mma wait", "epi2",
-             "-", "conv3 mma wait", "regress"]
+    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "worker sync", "conv2 mma wait", "epi2",
+             "conv3a mma wait", "epi3a + conv3b", "epi3b + regress"]
     marks = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]
     print("CTAs traced %d; kernel span %.1f us" % (len(t), (t[:, 12].max() - t0) / 1e3))
     dur = t[:, 12] - t[:, 0]
@@ -86,8 +86,6 @@ def main():
             print("   %-16s %7.2f" % (nm, seg.mean()))
     steps = np.diff(np.concatenate([t[:, 2:3], t[:, 16:24]], axis=1), axis=1) / 1e3
     print("conv1 per-step us (mean over CTAs):", np.round(steps.mean(axis=0), 2))
-    print("issuer thread, mean cycles per CTA: wait A %.0f  wait B %.0f  wait t1/t2 %.0f | conv2 issue span %.0f  conv3 issue span %.0f" % tuple(
-        t[:, k].mean() for k in (26, 27, 28, 29, 30)))
     # how many tile pieces the RoIs of this workload are cut into (approximation of roi_prep_kernel's count)
     bx = path.bxyxy[:n_live].float().cpu().numpy()
     ntx = np.floor((bx[:, 3] + 1) / 32) - np.floor(bx[:, 1] / 32) + 1
