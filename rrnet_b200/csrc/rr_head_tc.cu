@@ -3,8 +3,8 @@
 //
 // Same contract as head_forward_kernel (rr_head.cu): Bottleneck(256,64) -> avg-pool -> 1x1 conv 256->4 on
 // the RoIs' [256,3,3] features (models/rrnet.py:155-157, detectors/fasterrcnn_detector.py:13-18,
-// backbones/resnet.py:33-53), BatchNorms folded.  A CTA takes 8 RoIs.  Their pixels are the rows of one
-// M = 128 tile in a padded list of 16 rows per RoI,
+// backbones/resnet.py:33-53), BatchNorms folded.  A tile is 8 RoIs.  Their pixels are the rows of one
+// M = 128 MMA tile in a padded list of 16 rows per RoI,
 //     row(roi, py, px) = 16 roi + 4 + 4 py + px          (rows 16 roi + 0..3 and every px = 3 row stay zero)
 // so that the neighbour (py + dy, px + dx) of a pixel is the row 4 dy + dx further down and every neighbour
 // outside the 3x3 map is a zero row.  The three convolutions are GEMMs over that tile:
@@ -13,55 +13,55 @@
 //                                                   descriptor whose start address is shifted by 4 dy + dx rows
 //                                                   (the 128-byte swizzle is a function of the address, so a
 //                                                   128-byte-aligned start is legal: tools/tc_shift_probe.cu)
-//     conv3  [128 x  64] x [64 x 256]               2 halves of 2 N-quarters x 2 K-chunks
+//     conv3  [128 x  64] x [64 x 256]               4 N-quarters x 2 K-chunks
 // Nothing is restaged between the taps: after conv1 the only data movement is the weight stream.
 // Every MMA is tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64, K = 8, both operands in shared memory:
 // 48 cycles each, bound by the 6 KB of operands it reads (tools/tc_rate_probe.cu), not by the 32 cycles of
 // math.  An fp32 product a*b is evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with hi = tf32(v),
 // lo = tf32(v - hi): three MMAs per K-step, error ~2^-21 relative per product, inside the 1e-5 parity budget.
 //
-// The tensor pipe idles while a tile is loaded and during its epilogues, and the workers idle during conv2 /
-// conv3, so TWO CTAs share an SM and fill each other's gaps.  That sets the budget of one CTA: 256 TMEM columns
-// (conv1 and conv2 share columns 0-63, a conv3 half has 64-191, the two halves run one after the other),
-// <= 113 KB of shared memory (the t1 / t2 tiles reuse the conv1 stages, the weight ring has two slots) and
-// <= 88 registers per thread.  The residual x is added in the last epilogue from a per-RoI fp32 copy the workers
-// leave in global memory (L2) while they stage conv1.
-//
-// Warp roles (no block-wide barrier after the prologue; mbarriers connect the roles):
-//   warps 0-8   workers: sum the RoIs' partial slots (x), split, fill the two conv1 A stages; epilogues
-//   warp  9     one elected lane issues every tcgen05.mma and the tcgen05.commit that frees a stage / ring slot
-//   warp  10    lane 0 streams the 34 pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
-//               rr_head_fold) with cp.async.bulk (TMA) + complete_tx; the warp also prefetches into L2 the x
-//               slots of the CTA that will follow this one on the SM
+// The kernel is persistent (one CTA per SM walks over the tiles) and software-pipelined across tiles, because
+// inside one tile the tensor pipe and the ordinary warps only take turns (conv1 -> epilogue -> conv2 ->
+// epilogue -> conv3 -> epilogue).  While the tensor core runs conv2 / conv3 of tile i the workers already sum,
+// split and stage x of tile i+1, and its conv1 MMAs are slotted between the conv2 / conv3 steps of tile i:
+//   warps 0-8   workers: E1(i) [t1 = relu(conv1 + b1) -> smem tiles], W(i+1) [x of the next tile -> conv1 A
+//               stages + fp32 copy for the residual], E2(i) [t2], E3(i) [y = conv3 + b3 + x, relu, regressor]
+//   warp  9     one elected lane issues every tcgen05.mma; two instruction streams (conv1 of tile i+1 / conv2
+//               and conv3 of tile i), whichever has its operands ready goes next
+//   warp  10    lane 0 streams the pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
+//               rr_head_fold) with cp.async.bulk (TMA) + complete_tx into one ring per stream
+// mbarriers connect the roles; there is no block-wide barrier after the prologue.  TMEM: conv1 / conv2
+// accumulator double-buffered by tile parity (columns 0-63 / 64-127), conv3 in columns 128-383.
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
 namespace rr {
 
-constexpr int kTcRois = 8;                       // RoIs per CTA
+constexpr int kTcRois = 8;                       // RoIs per tile
 constexpr int kRoiRows = 16;                     // tile rows per RoI: 3 x (3 pixels + 1 zero) + 4 zero rows in front
-constexpr int kWorkerWarps = 9;
-constexpr int kWorkers = 32 * kWorkerWarps;      // 288 threads x 2 items = the 576 live (row, 16-byte chunk) items of an x tile
+constexpr int kEpiWarps = 8;                     // epilogue warps: 4 TMEM lane quarters x 2 column halves
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kLoadWarps = 9;
+constexpr int kLoaders = 32 * kLoadWarps;        // 288 threads x 2 items = the 576 live (row, 16-byte chunk) items of an x tile
 constexpr int kTcItems = 2;
 constexpr int kTcSlotsInReg = 6;                 // partial slots of an item held in registers per K chunk
-constexpr int kTcTiles = 2;                      // M = 128 tiles per CTA, in lockstep: every weight slot serves both
-constexpr int kTcBlock = kTcTiles * kWorkers + 64;   // + the MMA issuer warp + the weight stream warp
-constexpr int kTcCtasPerSm = 1;
+constexpr int kWarpIssuer = kEpiWarps + kLoadWarps, kWarpWeights = kWarpIssuer + 1;
+constexpr int kTcBlock = 32 * (kWarpWeights + 1);
 constexpr int kTcATile = 128 * 128;              // bytes: 128 rows x 32 tf32
 constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
 constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB
-constexpr int kAStages = 2;
+constexpr int kAStages = 2;                      // conv1 A stages; ring 1 (conv1 weights) has one slot per stage
 constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one step of the weight image
-constexpr int kTcBRing = 4;
+constexpr int kRing2 = 3;                        // slots of ring 2 (conv2 / conv3 weights)
+constexpr int kSteps1 = 8, kSteps2 = 26;         // weight steps of stream 1 (conv1) and stream 2 (conv2, conv3)
 constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
 constexpr int kPlaneBytes = (128 + 2 * kMargin) * 128;
-constexpr int kRegion0 = 4 * kPlaneBytes;        // 72 KB: the conv1 stages (64 KB), then the four t planes
-static_assert(kRegion0 >= kAStages * kTcAStage, "the t planes reuse the conv1 stages");
+constexpr int kTBytes = 4 * kPlaneBytes;         // t planes (hi | lo) x (kc 0 | 1): 72 KB
 static_assert(kTcBSlot == kTcStepFloats * 4, "a ring slot is one step of the folded image");
-constexpr int kTcSmem = kTcTiles * kRegion0 + kTcBRing * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
+static_assert(kSteps1 + kSteps2 == kTcSteps, "the two streams cover the folded image");
+constexpr int kTcSmem = kTBytes + kAStages * kTcAStage + (kAStages + kRing2) * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
-constexpr uint32_t kTileCols = 192;               // TMEM columns of one tile
-constexpr uint32_t kColD12 = 0, kColD3 = 64;     // conv1 / conv2 accumulator, conv3 half accumulator (128 columns)
+constexpr uint32_t kColD12 = 0, kColD3 = 128;    // conv1 / conv2 accumulator (+64 for odd tiles), conv3 accumulator (256 columns)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 //                          D = f32      A = tf32     B = tf32      N = 64               M = 128      (both K-major)
 
@@ -97,9 +97,7 @@ __device__ __forceinline__ void bar_wait_warp(unsigned long long* bar, uint32_t 
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
             if (ok) break;
-#ifndef RR_TC_EXP_NOSLEEP
-            __nanosleep(64);
-#endif
+            __nanosleep(32);
         }
     }
     __syncwarp();
@@ -121,6 +119,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
@@ -162,20 +171,29 @@ int head_fold_tc_launch(float* folded, cudaStream_t st) {
 }
 
 
-#ifdef RR_HEAD_TC_TRACE      // tools/head_trace.py: per-CTA phase time stamps (never defined in the shipped build)
+#ifdef RR_HEAD_TC_TRACE      // tools/head_trace.py: per-CTA time stamps (never defined in the shipped build)
 __device__ unsigned long long g_tc_trace[2048 * 32];
 #define TC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_tc_trace[blockIdx.x * 32 + (k)] = t_; } } while (0)
 #define TC_TRACE_VAL(k, v) do { if (blockIdx.x < 2048) g_tc_trace[blockIdx.x * 32 + (k)] = (unsigned long long)(v); } while (0)
-#define TC_CLOCK() clock64()
+__device__ __forceinline__ long long tc_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_LAP(acc) do { const long long n_ = tc_now(); (acc) += n_ - lap_; lap_ = n_; } while (0)
+#define TC_TIMED(acc, stmt) do { const long long a_ = tc_now(); stmt; (acc) += tc_now() - a_; } while (0)
 #else
+#define TC_TIMED(acc, stmt) do { stmt; } while (0)
+#define TC_LAP(acc) do { } while (0)
 #define TC_TRACE(k) do { } while (0)
 #define TC_TRACE_VAL(k, v) do { } while (0)
-#define TC_CLOCK() 0ll
 #endif
 
 __device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool bar_test(unsigned long long* bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ float4 ld_global_f4(const float* p) {      // coherent load: the data was written by this kernel
     float4 v;
@@ -183,44 +201,45 @@ __device__ __forceinline__ float4 ld_global_f4(const float* p) {      // coheren
     return v;
 }
 
-__global__ void __launch_bounds__(kTcBlock, kTcCtasPerSm)
+__global__ void __launch_bounds__(kTcBlock, 1)
 head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
-               const float* __restrict__ f, float* __restrict__ reg, int wave) {
+               const float* __restrict__ f, float* __restrict__ reg) {
     extern __shared__ uint8_t s_dyn[];
     __shared__ __align__(8) unsigned long long s_full_a[kAStages];   // conv1 A stage filled (one arrival per worker warp)
     __shared__ __align__(8) unsigned long long s_free_a[kAStages];   // ... consumed (tcgen05.commit)
-    __shared__ __align__(8) unsigned long long s_full_b[kTcBRing];   // weight slot landed (complete_tx)
-    __shared__ __align__(8) unsigned long long s_free_b[kTcBRing];   // ... consumed (tcgen05.commit)
-    __shared__ __align__(8) unsigned long long s_phase[4];           // all MMAs of conv1 / conv2 / conv3 half 0 / half 1 are done
-    __shared__ __align__(8) unsigned long long s_tready;             // t1 (then t2) tiles written by the epilogue
-    __shared__ __align__(8) unsigned long long s_d3free;             // conv3 half 0 has been read out of TMEM
+    __shared__ __align__(8) unsigned long long s_full_b1[kAStages];  // ring 1 slot landed (complete_tx)
+    __shared__ __align__(8) unsigned long long s_free_b1[kAStages];  // ... consumed (tcgen05.commit)
+    __shared__ __align__(8) unsigned long long s_full_b2[kRing2];
+    __shared__ __align__(8) unsigned long long s_free_b2[kRing2];
+    __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of conv1 / conv2 / conv3 first half / second half are done
+    __shared__ __align__(8) unsigned long long s_tready;             // t1, then t2 written by the epilogue (two phases per tile)
+    __shared__ __align__(8) unsigned long long s_d3free;             // conv3's accumulator has been read out (one phase per tile)
     __shared__ uint32_t s_tmem;
-    __shared__ int s_sb[kTcTiles][kTcRois];
+    __shared__ __align__(8) unsigned long long s_xdone[2];           // fp32 copy of x (and s_sb) of a tile written, by tile parity
+    __shared__ int s_sb[4][kTcRois];                                 // first slot of the tile's RoIs, ring of four tiles
     __shared__ float s_b1[64], s_b2[64], s_b3[256];
     __shared__ float4 s_wr[256];                                     // regressor weights, one float4 per channel
-    __shared__ float4 s_part[kTcTiles][2][kTcRois];
     TC_TRACE(0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
-    if (blockIdx.x * (kTcTiles * kTcRois) >= live) return;
+    const int n_tiles = (live + kTcRois - 1) / kTcRois;
+    if ((int)blockIdx.x >= n_tiles) return;
+    const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;       // tiles blockIdx.x + k * gridDim.x
 
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)s_dyn + 1023) & ~(uintptr_t)1023);
-    // [0, 72 KB): two conv1 A stages (A_hi | A_lo); after conv1 the same bytes hold the t1 / t2 tiles:
-    // plane (hi|lo, kc) at base + (2*lo + kc) * kPlaneBytes, 8 zero rows, the 128 tile rows, 8 zero rows
-    uint8_t* ring = base + kTcTiles * kRegion0;                                            // kTcBRing x (B_hi | B_lo)
+    // t planes: plane (hi|lo, kc) at base + (2*lo + kc) * kPlaneBytes: 8 zero rows, the 128 tile rows, 8 zero rows
+    uint8_t* stages = base + kTBytes;                           // conv1 A stages (A_hi | A_lo)
+    uint8_t* ring1 = stages + kAStages * kTcAStage;             // conv1 weights, slot = stage
+    uint8_t* ring2 = ring1 + kAStages * kTcBSlot;               // conv2 / conv3 weights
 
     // ------------------------------ prologue (all warps) ------------------------------
-    for (int i = tid; i < kTcTiles * kRegion0 / 16; i += kTcBlock)              // pad rows of the A stages stay zero
+    for (int i = tid; i < (kTBytes + kAStages * kTcAStage) / 16; i += kTcBlock)   // margins and pad rows stay zero for good
         reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < 64; i += kTcBlock) { s_b1[i] = __ldg(f + kOffB1 + i); s_b2[i] = __ldg(f + kOffB2 + i); }
     for (int i = tid; i < 256; i += kTcBlock) {
         s_b3[i] = __ldg(f + kOffB3 + i);
         s_wr[i] = make_float4(__ldg(f + kOffWr + i), __ldg(f + kOffWr + 256 + i), __ldg(f + kOffWr + 512 + i),
                               __ldg(f + kOffWr + 768 + i));
-    }
-    if (tid >= 64 && tid < 64 + kTcTiles * kTcRois) {
-        const int n = blockIdx.x * (kTcTiles * kTcRois) + (tid - 64);
-        (&s_sb[0][0])[tid - 64] = (n < live && src.partial) ? __ldg(src.slot + n) : -1;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "n"(kTmemCols) : "memory");
@@ -230,11 +249,14 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         auto init = [](unsigned long long* b, int count) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
         };
-        for (int i = 0; i < kAStages; ++i) { init(&s_full_a[i], kTcTiles * kWorkerWarps); init(&s_free_a[i], 1); }
-        for (int i = 0; i < kTcBRing; ++i) { init(&s_full_b[i], 1); init(&s_free_b[i], 1); }
+        for (int i = 0; i < kAStages; ++i) {
+            init(&s_full_a[i], kLoadWarps); init(&s_free_a[i], 1); init(&s_full_b1[i], 1); init(&s_free_b1[i], 1);
+            init(&s_xdone[i], kLoadWarps);
+        }
+        for (int i = 0; i < kRing2; ++i) { init(&s_full_b2[i], 1); init(&s_free_b2[i], 1); }
         for (int i = 0; i < 4; ++i) init(&s_phase[i], 1);
-        init(&s_tready, kTcTiles * kWorkerWarps);
-        init(&s_d3free, kTcTiles * 8);
+        init(&s_tready, 4);
+        init(&s_d3free, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // zero fill -> visible to the MMA
@@ -245,301 +267,361 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     const uint32_t tmem = s_tmem;
     const float* ftc = f + kOffTc;
 
-    // ------------------------------ warp 10: the weight stream ------------------------------
-    if (warp == kTcTiles * kWorkerWarps + 1) {
-        auto load_b = [&](int s) {
-            const uint32_t bar = smem_addr(&s_full_b[s % kTcBRing]);
-            const uint32_t dst = smem_addr(ring + (s % kTcBRing) * kTcBSlot);
-            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(kTcBSlot) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(ftc + (size_t)s * kTcStepFloats), "r"(kTcBSlot), "r"(bar) : "memory");
-        };
-        if (lane == 0)
-            for (int s = 0; s < kTcBRing; ++s) load_b(s);
-        __syncwarp();
-        if (lane == 0)
-            for (int s = kTcBRing; s < kTcSteps; ++s) {
-                bar_wait(&s_free_b[s % kTcBRing], (uint32_t)((s / kTcBRing - 1) & 1));
-                load_b(s);
+    // ------------------------------ warp 10: the weight streams ------------------------------
+    if (warp == kWarpWeights) {
+        if (lane == 0) {
+            auto load_b = [&](unsigned long long* full, uint8_t* slot, int image_step) {
+                const uint32_t bar = smem_addr(full);
+                asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(kTcBSlot) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr(slot)), "l"(ftc + (size_t)image_step * kTcStepFloats), "r"(kTcBSlot), "r"(bar) : "memory");
+            };
+            const int total1 = n_my * kSteps1, total2 = n_my * kSteps2;
+            int c1 = 0, c2 = 0, s2 = 0, slot2 = 0, use2 = 0;           // loads issued; step inside the tile / slot / use count of ring 2
+            while (c1 < total1 || c2 < total2) {
+                if (c2 < total2 && (use2 == 0 || bar_test(&s_free_b2[slot2], (uint32_t)((use2 - 1) & 1)))) {
+                    load_b(&s_full_b2[slot2], ring2 + slot2 * kTcBSlot, kSteps1 + s2);
+                    ++c2;
+                    if (++s2 == kSteps2) s2 = 0;
+                    if (++slot2 == kRing2) { slot2 = 0; ++use2; }
+                }
+                if (c1 < total1) {
+                    const int slot = c1 & 1, use = c1 >> 1;
+                    if (use == 0 || bar_test(&s_free_b1[slot], (uint32_t)((use - 1) & 1))) {
+                        load_b(&s_full_b1[slot], ring1 + slot * kTcBSlot, c1 & 7);
+                        ++c1;
+                    }
+                }
             }
+        }
         return;
     }
 
     // ------------------------------ warp 9: the MMA issuer ------------------------------
-    // The warp stays converged and one elected lane issues: the compiler then keeps the descriptors in uniform
-    // registers and emits the MMAs back to back (a `lane == 0` branch wraps every tcgen05.mma in an
-    // ELECT / BRA.U.ANY loop, and with the per-step index arithmetic the single issuing thread, not the tensor
-    // core, set the pace).  The 34 steps are unrolled: ring slots, parities, columns and tap shifts are immediates.
-    if (warp == kTcTiles * kWorkerWarps) {
-        const uint32_t sbase = smem_addr(base), sring = smem_addr(ring);
+    // The warp stays converged (every lane tests the barriers, they all see the same answer) and one elected
+    // lane issues, so the compiler keeps descriptors in uniform registers and emits the MMAs back to back.
+    if (warp == kWarpIssuer) {
+        const uint32_t sT = smem_addr(base), sA = smem_addr(stages), sB1 = smem_addr(ring1), sB2 = smem_addr(ring2);
+        auto issue12 = [&](uint32_t sa_hi, uint32_t sa_lo, uint32_t sb, uint32_t d, bool first) {
+            const uint64_t a_hi = umma_desc(sa_hi), a_lo = umma_desc(sa_lo);
+            const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
 #pragma unroll
-        for (int s = 0; s < kTcSteps; ++s) {
-            uint32_t sa_hi, sa_lo, d_col;
-            if (s < 8) {                                    // conv1: A = stage s % 2
-                bar_wait(&s_full_a[s % kAStages], (uint32_t)((s / kAStages) & 1));
-                sa_hi = sbase + (uint32_t)((s % kAStages) * kTcAStage);
-                sa_lo = sa_hi + kTcATile;
-                d_col = kColD12;
-            } else {
-                const int kc = s & 1;                       // steps 8.. are (tap, kc) then (quarter, kc): kc = parity of s
-                int shift = 0;
-                if (s < 26) {
-                    if (s == 8) bar_wait(&s_tready, 0u);    // t1 is in place (and D1 has been read: conv2 reuses its columns)
-                    const int tap = (s - 8) >> 1;
-                    shift = 4 * (tap / 3 - 1) + (tap % 3 - 1);
-                    d_col = kColD12;
-                } else {
-                    if (s == 26) bar_wait(&s_tready, 1u);
-                    if (s == 30) bar_wait(&s_d3free, 0u);   // the first half has left TMEM
-                    d_col = kColD3 + 64u * (uint32_t)(((s - 26) >> 1) & 1);
-                }
-                sa_hi = sbase + (uint32_t)(kc * kPlaneBytes + (kMargin + shift) * 128);
-                sa_lo = sa_hi + 2 * kPlaneBytes;
+            for (int ks = 0; ks < 4; ++ks) {                    // K = 32 per step: four K = 8 instructions, 32 bytes apart
+                umma_tf32(d, a_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
+                umma_tf32(d, a_hi + 2 * ks, b_lo + 2 * ks, 1u);
+                umma_tf32(d, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
             }
-            bar_wait(&s_full_b[s % kTcBRing], (uint32_t)((s / kTcBRing) & 1));
+        };
+        uint32_t c1 = 0;                                        // conv1 steps issued: stage = c1 & 1, its use = c1 >> 1
+        uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % 3, its use c2 / 3
+        int s1 = 0;                                             // conv1 steps of the next tile issued in this period
+        uint32_t d12_next = tmem + kColD12;
+        // one conv1 step of the next tile; `block`: wait for its operands, else only take it if they are there
+        auto conv1_step = [&](bool block) {
+            const uint32_t st = c1 & 1u, par = (c1 >> 1) & 1u;
+            if (block) { bar_wait(&s_full_a[st], par); bar_wait(&s_full_b1[st], par); }
+            else if (!(bar_test(&s_full_a[st], par) && bar_test(&s_full_b1[st], par))) return;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                const bool first = s == 0 || s == 8 || (s >= 26 && (s & 1) == 0);   // first K chunk of an accumulator
-                const uint32_t sb = sring + (uint32_t)((s % kTcBRing) * kTcBSlot);
-                const uint64_t a_hi = umma_desc(sa_hi), a_lo = umma_desc(sa_lo);
-                const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
-#pragma unroll
-                for (int t = 0; t < kTcTiles; ++t) {
-                    const uint64_t ta_hi = a_hi + (uint64_t)(t * (kRegion0 >> 4)), ta_lo = a_lo + (uint64_t)(t * (kRegion0 >> 4));
-                    const uint32_t d = tmem + (uint32_t)t * kTileCols + d_col;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {        // K = 32 per step: four K = 8 instructions, 32 bytes apart
-                        umma_tf32(d, ta_hi + 2 * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
-                        umma_tf32(d, ta_hi + 2 * ks, b_lo + 2 * ks, 1u);
-                        umma_tf32(d, ta_lo + 2 * ks, b_hi + 2 * ks, 1u);
-                    }
-                }
-                umma_commit(&s_free_b[s % kTcBRing]);
-                if (s < 8) umma_commit(&s_free_a[s % kAStages]);
-                if (s == 7) umma_commit(&s_phase[0]);
-                if (s == 25) umma_commit(&s_phase[1]);
-                if (s == 29) umma_commit(&s_phase[2]);
-                if (s == kTcSteps - 1) umma_commit(&s_phase[3]);
+                if (st == 0) issue12(sA, sA + kTcATile, sB1, d12_next, s1 == 0);
+                else issue12(sA + kTcAStage, sA + kTcAStage + kTcATile, sB1 + kTcBSlot, d12_next, s1 == 0);
+                umma_commit(&s_free_a[st]);
+                umma_commit(&s_free_b1[st]);
+                if (s1 == kSteps1 - 1) umma_commit(&s_phase[0]);
             }
             __syncwarp();
+            ++s1;
+            ++c1;
+        };
+        long long w_b2 = 0, w_t = 0, w_c1 = 0;                   // trace build: ns blocked on ring 2 / on t1, t2 / in blocking conv1 steps
+        while (s1 < kSteps1) conv1_step(true);                  // conv1 of the first tile
+        for (int it = 0; it < n_my; ++it) {
+            // period `it`: conv2 / conv3 of tile it in program order (steps unrolled: shifts, columns and flags are
+            // immediates), a conv1 step of tile it + 1 slotted in after each of them whenever its operands are ready
+            const bool has_next = it + 1 < n_my;
+            s1 = has_next ? 0 : kSteps1;
+            const uint32_t d12_cur = tmem + kColD12 + 64u * (uint32_t)(it & 1);
+            d12_next = tmem + kColD12 + 64u * (uint32_t)((it + 1) & 1);
+            uint32_t slot2 = c2 % kRing2, par2 = (c2 / kRing2) & 1u;
+#pragma unroll
+            for (int s2 = 0; s2 < kSteps2; ++s2) {
+                if (s2 == 0) TC_TIMED(w_t, bar_wait(&s_tready, 0u));           // t1 in place
+                if (s2 == 18) {
+                    TC_TIMED(w_c1, while (s1 < kSteps1) conv1_step(true));      // every conv1 stage of the next tile, then t2
+                    TC_TIMED(w_t, bar_wait(&s_tready, 1u));                    // t2 in place
+                    if (it > 0) bar_wait(&s_d3free, (uint32_t)((it - 1) & 1));  // the previous tile has left conv3's accumulator
+                }
+                TC_TIMED(w_b2, bar_wait(&s_full_b2[slot2], par2));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int kc = s2 & 1;
+                int shift = 0;
+                if (s2 < 18) { const int tap = s2 >> 1; shift = 4 * (tap / 3 - 1) + (tap % 3 - 1); }
+                const uint32_t sa_hi = sT + (uint32_t)(kc * kPlaneBytes + (kMargin + shift) * 128);
+                const uint32_t d = s2 < 18 ? d12_cur : tmem + kColD3 + 64u * (uint32_t)((s2 - 18) >> 1);
+                if (elect_one()) {
+                    issue12(sa_hi, sa_hi + 2 * kPlaneBytes, sB2 + slot2 * (uint32_t)kTcBSlot, d, s2 < 18 ? s2 == 0 : kc == 0);
+                    umma_commit(&s_free_b2[slot2]);
+                    if (s2 == 17) umma_commit(&s_phase[1]);
+                    if (s2 == 21) umma_commit(&s_phase[2]);
+                    if (s2 == 25) umma_commit(&s_phase[3]);
+                }
+                __syncwarp();
+                if (++slot2 == kRing2) { slot2 = 0; par2 ^= 1u; }
+                if (s1 < kSteps1) conv1_step(false);
+            }
+            c2 += kSteps2;
+        }
+#ifdef RR_HEAD_TC_TRACE
+        if (lane == 0) { TC_TRACE_VAL(22, w_b2); TC_TRACE_VAL(23, w_t); TC_TRACE_VAL(24, w_c1); }
+#endif
+        return;
+    }
+
+    // ------------------------------ warps 8-16: x loaders ------------------------------
+    // x of tile k -> conv1 A stages (tf32 hi | lo) + fp32 copy for the residual, one tile after the other, as far
+    // ahead of the tensor core as the two A stages allow.  The 316 MB of partial slots come from DRAM in 128-byte
+    // pieces (about half of the HBM bandwidth is reachable that way): ~10 us per tile, which is why this runs in
+    // its own warps next to the MMAs and the epilogues instead of in front of them.
+    if (warp >= kEpiWarps) {
+        const int ltid = tid - kEpiThreads;
+        int it_row[kTcItems], it_p[kTcItems], it_ch[kTcItems], xoff[kTcItems];
+#pragma unroll
+        for (int q = 0; q < kTcItems; ++q) {
+            const int i = ltid + q * kLoaders, r72 = i >> 3, ch = i & 7;
+            const int rl = r72 / 9, p = r72 - rl * 9, m = kRoiRows * rl + 4 + 4 * (p / 3) + p % 3;
+            it_row[q] = rl; it_p[q] = p; it_ch[q] = ch;
+            xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
+        }
+        uint32_t cw = 0;                                        // conv1 chunks staged so far (all tiles)
+        for (int k = 0; k < n_my; ++k) {
+            const int roi0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTcRois;
+            const int nroi = min(kTcRois, live - roi0);
+            const float* xptr[kTcItems];
+            float* xscr[kTcItems];
+            int xpc[kTcItems];
+            float xinv[kTcItems];
+#pragma unroll
+            for (int q = 0; q < kTcItems; ++q) {
+                const int rl = it_row[q], p = it_p[q], ch = it_ch[q];
+                xptr[q] = src.roi_feat; xscr[q] = nullptr; xpc[q] = 0; xinv[q] = 1.f;
+                if (rl < nroi) {
+                    const int n = roi0 + rl;
+                    int sb = -1, pcs = 0;
+                    float cnt = 1.f;
+                    if (src.partial) { sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n); }
+                    if (sb < 0) {                               // finished feature [256][9] (direct RoIAlign path / plain API)
+                        xpc[q] = -1;
+                        xptr[q] = src.roi_feat + (size_t)n * 2304 + p + 36 * ch;
+                    } else {                                    // partial slots [pieces][9][256], to be summed and scaled
+                        xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
+                        xscr[q] = src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
+                        xpc[q] = pcs;
+                        xinv[q] = 1.0f / cnt;
+                    }
+                }
+            }
+            if (ltid < kTcRois) s_sb[k & 3][ltid] = (ltid < nroi && src.partial) ? __ldg(src.slot + roi0 + ltid) : -1;
+            // one K chunk ahead in registers, up to six slots per item, every load issued before the first add
+            float4 xp[kTcItems][kTcSlotsInReg];
+            auto load_x_chunk = [&](int kc) {
+#pragma unroll
+                for (int q = 0; q < kTcItems; ++q) {
+                    xp[q][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (xpc[q] < 0) {
+                        const float* g = xptr[q] + 288 * kc;
+                        xp[q][0] = make_float4(__ldg(g), __ldg(g + 9), __ldg(g + 18), __ldg(g + 27));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kTcSlotsInReg; ++j)
+#ifdef RR_TC_EXP_NOX
+                            if (j < xpc[q] && kc < 0)
+#else
+                            if (j < xpc[q])
+#endif
+                                xp[q][j] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)j * 2304 + 32 * kc));
+                    }
+                }
+            };
+            load_x_chunk(0);
+#pragma unroll 1
+            for (int kc = 0; kc < 8; ++kc) {
+                float4 v[kTcItems];
+#pragma unroll
+                for (int q = 0; q < kTcItems; ++q) {            // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
+                    v[q] = xp[q][0];
+                    if (xpc[q] >= 0) {
+#pragma unroll
+                        for (int j = 1; j < kTcSlotsInReg; ++j)
+                            if (j < xpc[q]) { v[q].x += xp[q][j].x; v[q].y += xp[q][j].y; v[q].z += xp[q][j].z; v[q].w += xp[q][j].w; }
+                        for (int j = kTcSlotsInReg; j < xpc[q]; ++j) {   // RoIs cut into more than six pieces are rare
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)j * 2304 + 32 * kc));
+                            v[q].x += t.x; v[q].y += t.y; v[q].z += t.z; v[q].w += t.w;
+                        }
+                        const float inv = xinv[q];
+                        v[q].x = __fmul_rn(v[q].x, inv); v[q].y = __fmul_rn(v[q].y, inv);
+                        v[q].z = __fmul_rn(v[q].z, inv); v[q].w = __fmul_rn(v[q].w, inv);
+                    }
+                }
+                if (kc + 1 < 8) load_x_chunk(kc + 1);           // in flight while this chunk is split and stored
+                const uint32_t st = cw & 1u, use = cw >> 1;
+                if (use > 0) bar_wait_warp(&s_free_a[st], (use - 1) & 1u);
+                uint8_t* a_hi = stages + st * kTcAStage;
+                uint8_t* a_lo = a_hi + kTcATile;
+#pragma unroll
+                for (int q = 0; q < kTcItems; ++q) {
+                    float4 hi, lo;
+                    split4(v[q], hi, lo);
+                    *reinterpret_cast<float4*>(a_hi + xoff[q]) = hi;
+                    *reinterpret_cast<float4*>(a_lo + xoff[q]) = lo;
+                    if (xscr[q]) *reinterpret_cast<float4*>(xscr[q] + 32 * kc) = v[q];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) bar_arrive(&s_full_a[st]);
+                ++cw;
+            }
+            __threadfence_block();                              // the fp32 copy and s_sb, before the epilogue warps are told
+            __syncwarp();
+            if (lane == 0) bar_arrive(&s_xdone[k & 1]);
         }
         return;
     }
 
-    // ------------------------------ warps 0-17: two groups of nine worker warps, one tile each ------------------------------
-    const int grp = warp / kWorkerWarps;
-    const int roi0 = (blockIdx.x * kTcTiles + grp) * kTcRois;
-    const int nroi = max(0, min(kTcRois, live - roi0));        // 0: the last CTA's second tile may be empty (it still keeps step)
-    const int wtid = tid - grp * kWorkers, wwarp = warp - grp * kWorkerWarps;
-    base += grp * kRegion0;
-    const uint32_t tmem_t = tmem + (uint32_t)grp * kTileCols;
-    // conv1 A tile: 72 live rows x eight 16-byte chunks = 576 items, two per thread, the same two for all 8 K chunks
-    const float* xptr[kTcItems];
-    float* xscr[kTcItems];                                      // fp32 copy of x for the residual (tile-path RoIs)
-    int xpc[kTcItems], xoff[kTcItems];
-    float xinv[kTcItems];
+    // ------------------------------ warps 0-3: t epilogues, warps 4-7: output epilogue ------------------------------
+    // A warp reaches the TMEM lane quarter warp % 4, so each group of four covers the 128 rows.  Two groups, because
+    // the output epilogue of tile k (the long one) must not sit between the tensor core and t1 of tile k + 1.
+    const int eq = warp & 3, em = 32 * eq + lane;
+    const bool pixel_row = (em & 15) >= 4 && (em & 3) != 3;
+    if (warp < 4) {
+        // E1 / E2: t = relu(D + b) of conv1 / conv2 -> (hi, lo) tf32 planes in the MMA tile layout; the two column
+        // halves of the accumulator are the two K chunks of the next GEMM
+        auto epilogue_t = [&](uint32_t d12, const float* bias, bool mask_pad) {
+            const bool keep = !mask_pad || pixel_row;           // conv2 reads the pad rows as zeros
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tmem_ld32(d12 + ((uint32_t)(32 * eq) << 16) + (uint32_t)(32 * h), v);
+                uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + em) * 128;
+                uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
 #pragma unroll
-    for (int q = 0; q < kTcItems; ++q) {
-        const int i = wtid + q * kWorkers, r72 = i >> 3, ch = i & 7;
-        const int rl = r72 / 9, p = r72 - rl * 9, m = kRoiRows * rl + 4 + 4 * (p / 3) + p % 3;
-        xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
-        xptr[q] = src.roi_feat; xscr[q] = nullptr; xpc[q] = 0; xinv[q] = 1.f;
-        if (rl < nroi) {
-            const int n = roi0 + rl;
-            int sb = -1, pcs = 0;
-            float cnt = 1.f;
-            if (src.partial) { sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n); }
-            if (sb < 0) {                                       // finished feature [256][9] (direct RoIAlign path / plain API)
-                xpc[q] = -1;
-                xptr[q] = src.roi_feat + (size_t)n * 2304 + p + 36 * ch;
-            } else {                                            // partial slots [pieces][9][256], to be summed and scaled
-                xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
-                xscr[q] = src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
-                xpc[q] = pcs;
-                xinv[q] = 1.0f / cnt;
+                for (int c = 0; c < 8; ++c) {
+                    float4 o;
+                    o.x = keep ? fmaxf(v[4 * c] + bias[32 * h + 4 * c], 0.f) : 0.f;
+                    o.y = keep ? fmaxf(v[4 * c + 1] + bias[32 * h + 4 * c + 1], 0.f) : 0.f;
+                    o.z = keep ? fmaxf(v[4 * c + 2] + bias[32 * h + 4 * c + 2], 0.f) : 0.f;
+                    o.w = keep ? fmaxf(v[4 * c + 3] + bias[32 * h + 4 * c + 3], 0.f) : 0.f;
+                    float4 hi, lo;
+                    split4(o, hi, lo);
+                    const int off = (c ^ (em & 7)) << 4;
+                    *reinterpret_cast<float4*>(p_hi + off) = hi;
+                    *reinterpret_cast<float4*>(p_lo + off) = lo;
+                }
             }
-        }
-    }
-    // x is prefetched one K chunk ahead into registers, up to six slots per item, every load issued before the
-    // first add (a load-add-load-add loop would serialise on the in-order issue); the slots are L2 hits after
-    // the first wave thanks to the previous CTA's bulk prefetch, and the other CTA of the SM covers the rest.
-    float4 xp[kTcItems][kTcSlotsInReg];
-    auto load_x_chunk = [&](int kc) {
-#pragma unroll
-        for (int q = 0; q < kTcItems; ++q) {
-            xp[q][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (xpc[q] < 0) {
-                const float* g = xptr[q] + 288 * kc;
-                xp[q][0] = make_float4(__ldg(g), __ldg(g + 9), __ldg(g + 18), __ldg(g + 27));
-            } else {
-#pragma unroll
-                for (int k = 0; k < kTcSlotsInReg; ++k)
-#ifdef RR_TC_EXP_NOX
-                    if (k < xpc[q] && kc < 1)
-#else
-                    if (k < xpc[q])
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(&s_tready);
+        };
+        TC_TRACE(2);
+#ifdef RR_HEAD_TC_TRACE
+        long long lap_ = tc_now(), w_p0 = 0, w_e1 = 0, w_x = 0, w_p1 = 0, w_e2 = 0, w_e3 = 0;
 #endif
-                        xp[q][k] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
-            }
+        for (int k = 0; k < n_my; ++k) {
+            const uint32_t par = (uint32_t)(k & 1);
+            const uint32_t d12 = tmem + kColD12 + 64u * par;
+            if (k > 0) bar_wait_warp(&s_phase[3], par ^ 1u);    // conv3(k-1) has finished reading the t planes
+            TC_LAP(w_e3);
+            bar_wait_warp(&s_phase[0], par);                    // conv1(k) done
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TC_LAP(w_p0);
+            epilogue_t(d12, s_b1, true);
+            TC_LAP(w_e1);
+            bar_wait_warp(&s_phase[1], par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TC_LAP(w_p1);
+            epilogue_t(d12, s_b2, false);
+            TC_LAP(w_e2);
         }
-    };
-    auto x_value = [&](int kc, int q) {             // same summation order as roi_combine_kernel: slot 0, 1, 2, ...
-        float4 v = xp[q][0];
-        if (xpc[q] >= 0) {
-#pragma unroll
-            for (int k = 1; k < kTcSlotsInReg; ++k)
-                if (k < xpc[q]) { v.x += xp[q][k].x; v.y += xp[q][k].y; v.z += xp[q][k].z; v.w += xp[q][k].w; }
-            for (int k = kTcSlotsInReg; k < xpc[q]; ++k) {      // RoIs cut into more than six pieces are rare
-                const float4 t = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)k * 2304 + 32 * kc));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+#ifdef RR_HEAD_TC_TRACE
+        if (tid == 0) { TC_TRACE_VAL(16, w_p0); TC_TRACE_VAL(17, w_e1); TC_TRACE_VAL(18, w_x); TC_TRACE_VAL(19, w_p1); TC_TRACE_VAL(20, w_e2); TC_TRACE_VAL(21, w_e3); }
+#endif
+    } else {
+        // E3: y = D3 + b3 + x, relu (resnet.py:49-50), regressor per row, mean over the 9 rows.  One warp owns its 32
+        // rows (two RoIs) over all 256 channels, 16 at a time; the residual of the next 16 is in flight meanwhile.
+        for (int k = 0; k < n_my; ++k) {
+            const int roi0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTcRois;
+            const int nroi = min(kTcRois, live - roi0);
+            const uint32_t par = (uint32_t)(k & 1);
+            const bool ekeep = pixel_row && (em >> 4) < nroi;
+            bar_wait_warp(&s_xdone[k & 1], (uint32_t)((k >> 1) & 1));     // the loaders' copy of x and s_sb are complete
+            const float* res = src.roi_feat;                    // residual source of this thread's row
+            bool res_rows = false;                              // true: [9][256] copy, false: [256][9] feature
+            if (ekeep) {
+                const int rl = em >> 4, rr = em & 15, p = 3 * ((rr - 4) >> 2) + (rr & 3), n = roi0 + rl;
+                res_rows = s_sb[k & 3][rl] >= 0;
+                res = res_rows ? src.scratch + (size_t)n * 2304 + p * 256 : src.roi_feat + (size_t)n * 2304 + p;
             }
-            const float inv = xinv[q];
-            v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
-        }
-        return v;
-    };
-    load_x_chunk(0);
-    TC_TRACE(2);
-#pragma unroll 1
-    for (int kc = 0; kc < 8; ++kc) {
-        const int st = kc % kAStages;
-        if (kc >= kAStages) bar_wait_warp(&s_free_a[st], (uint32_t)((kc / kAStages - 1) & 1));
-        uint8_t* a_hi = base + st * kTcAStage;
-        uint8_t* a_lo = a_hi + kTcATile;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float xa[16], xb[16];
+            auto load_res = [&](int c0, float (&x)[16]) {
 #pragma unroll
-        for (int q = 0; q < kTcItems; ++q) {
-            const float4 v = x_value(kc, q);
-            float4 hi, lo;
-            split4(v, hi, lo);
-            *reinterpret_cast<float4*>(a_hi + xoff[q]) = hi;
-            *reinterpret_cast<float4*>(a_lo + xoff[q]) = lo;
-            if (xscr[q]) *reinterpret_cast<float4*>(xscr[q] + 32 * kc) = v;
-        }
-        if (kc + 1 < 8) load_x_chunk(kc + 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
-        __syncwarp();
-        if (lane == 0) bar_arrive(&s_full_a[st]);
-        TC_TRACE(16 + kc);
-    }
-    TC_TRACE(3);
-
-    // t = relu(D + b) of conv1 / conv2 -> (hi, lo) tf32 planes in the MMA tile layout.  Eight warps cover the
-    // 4 TMEM lane quarters x 2 column halves (= K chunks of the next GEMM); the ninth zeroes the plane margins.
-    auto epilogue_t = [&](const float* bias, bool mask_pad) {
-        if (wwarp < 8) {                                    // a warp reaches the TMEM lane quarter warp % 4 of the CTA
-            const int q = warp & 3, h = wwarp >> 2, m = 32 * q + lane;
-            const bool keep = !mask_pad || ((m & 15) >= 4 && (m & 3) != 3);     // conv2 reads the pad rows as zeros
-            float v[32];
-            tmem_ld32(tmem_t + ((uint32_t)(32 * q) << 16) + kColD12 + (uint32_t)(32 * h), v);
-            uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + m) * 128;
-            uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 o;
-                o.x = keep ? fmaxf(v[4 * c] + bias[32 * h + 4 * c], 0.f) : 0.f;
-                o.y = keep ? fmaxf(v[4 * c + 1] + bias[32 * h + 4 * c + 1], 0.f) : 0.f;
-                o.z = keep ? fmaxf(v[4 * c + 2] + bias[32 * h + 4 * c + 2], 0.f) : 0.f;
-                o.w = keep ? fmaxf(v[4 * c + 3] + bias[32 * h + 4 * c + 3], 0.f) : 0.f;
-                float4 hi, lo;
-                split4(o, hi, lo);
-                const int off = (c ^ (m & 7)) << 4;
-                *reinterpret_cast<float4*>(p_hi + off) = hi;
-                *reinterpret_cast<float4*>(p_lo + off) = lo;
-            }
-        } else if (mask_pad) {
-            for (int i = lane; i < 4 * 16 * 8; i += 32) {       // 4 planes x (8 + 8) margin rows x 8 chunks
-                const int pl = i >> 7, r = (i >> 3) & 15, c = i & 7;
-                const int row = r < 8 ? r : kMargin + 128 + (r - 8);
-                *reinterpret_cast<float4*>(base + pl * kPlaneBytes + row * 128 + c * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) bar_arrive(&s_tready);
-    };
-    bar_wait_warp(&s_phase[0], 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    TC_TRACE(4);
-    epilogue_t(s_b1, true);
-    TC_TRACE(5);
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kWorkers) : "memory");   // every worker's copy of x is visible to the others
-    TC_TRACE(6);
-    bar_wait_warp(&s_phase[1], 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    TC_TRACE(7);
-    epilogue_t(s_b2, false);
-    TC_TRACE(8);
-
-    // ======== y = D3 + b3 + x, relu (resnet.py:49-50), regressor per row, mean over the 9 rows; two halves of 128 channels ========
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int eq = warp & 3, eg = (wwarp >> 2) & 1, em = 32 * eq + lane;
-    const bool ekeep = wwarp < 8 && (em & 15) >= 4 && (em & 3) != 3 && (em >> 4) < nroi;
-    const float* res = nullptr;                                  // residual source of this thread's row
-    bool res_rows = false;                                       // true: [9][256] copy, false: [256][9] feature
-    if (ekeep) {
-        const int rl = em >> 4, rr = em & 15, p = 3 * ((rr - 4) >> 2) + (rr & 3), n = roi0 + rl;
-        res_rows = s_sb[grp][rl] >= 0;
-        res = res_rows ? src.scratch + (size_t)n * 2304 + p * 256 : src.roi_feat + (size_t)n * 2304 + p;
-    }
-    for (int half = 0; half < 2; ++half) {
-        bar_wait_warp(&s_phase[2 + half], 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (half == 0) TC_TRACE(9); else TC_TRACE(10);
-        if (wwarp < 8) {
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int c0 = 128 * half + 64 * eg + 32 * j;
-                float x[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[e] = 0.f;
+                for (int e = 0; e < 16; ++e) x[e] = 0.f;
                 if (ekeep) {
                     if (res_rows) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
+                        for (int e = 0; e < 4; ++e) {
                             const float4 t = ld_global_f4(res + c0 + 4 * e);
                             x[4 * e] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
                         }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) x[e] = __ldg(res + (c0 + e) * 9);
+                        for (int e = 0; e < 16; ++e) x[e] = __ldg(res + (c0 + e) * 9);
                     }
                 }
-                float v[32];
-                tmem_ld32(tmem_t + ((uint32_t)(32 * eq) << 16) + kColD3 + (uint32_t)(64 * eg + 32 * j), v);
+            };
+            auto block = [&](int c0, const float (&x)[16]) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(32 * eq) << 16) + kColD3 + (uint32_t)c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
+                for (int e = 0; e < 16; ++e) {
                     const float y = fmaxf(v[e] + s_b3[c0 + e] + x[e], 0.f);
                     const float4 w = s_wr[c0 + e];
                     acc.x = fmaf(y, w.x, acc.x); acc.y = fmaf(y, w.y, acc.y); acc.z = fmaf(y, w.z, acc.z); acc.w = fmaf(y, w.w, acc.w);
                 }
+            };
+            load_res(0, xa);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                bar_wait_warp(&s_phase[2 + half], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c0 = 128 * half; c0 < 128 * half + 128; c0 += 32) {
+                    load_res(c0 + 16, xb);
+                    block(c0, xa);
+                    if (c0 + 32 < 256) load_res(c0 + 32, xa);
+                    block(c0 + 16, xb);
+                }
             }
-            if (half == 0) {
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) bar_arrive(&s_d3free);
-            }
-        }
-    }
-    if (wwarp < 8) {
-        if (!ekeep) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(&s_d3free);
+            if (!ekeep) acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {                       // the 16 rows of a RoI sit in one half warp
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            for (int o = 8; o > 0; o >>= 1) {                   // the 16 rows of a RoI sit in one half warp
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            const int rl = 2 * eq + (lane >> 4);
+            if ((lane & 15) == 0 && rl < nroi)
+                reinterpret_cast<float4*>(reg)[roi0 + rl] =
+                    make_float4(acc.x / 9.0f + __ldg(f + kOffBr), acc.y / 9.0f + __ldg(f + kOffBr + 1),
+                                acc.z / 9.0f + __ldg(f + kOffBr + 2), acc.w / 9.0f + __ldg(f + kOffBr + 3));
         }
-        if ((lane & 15) == 0) s_part[grp][eg][2 * eq + (lane >> 4)] = acc;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kWorkers) : "memory");
-    if (wtid < nroi) {
-        const float4 a = s_part[grp][0][wtid], b = s_part[grp][1][wtid];
-        reinterpret_cast<float4*>(reg)[roi0 + wtid] =
-            make_float4((a.x + b.x) / 9.0f + __ldg(f + kOffBr), (a.y + b.y) / 9.0f + __ldg(f + kOffBr + 1),
-                        (a.z + b.z) / 9.0f + __ldg(f + kOffBr + 2), (a.w + b.w) / 9.0f + __ldg(f + kOffBr + 3));
     }
     TC_TRACE(12);
-    asm volatile("bar.sync 3, %0;" ::"n"(kTcTiles * kWorkers) : "memory");      // both tiles are out of TMEM
+    TC_TRACE_VAL(13, n_my);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");      // both epilogue groups are out of TMEM
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -555,8 +637,8 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
     }
     if (((uintptr_t)folded & 15) != 0) return RR_E_BADARG;     // the weight stream is copied in 16-byte units
     if (src.partial && !src.scratch) return RR_E_BADARG;
-    const int grid = (n_cap + kTcTiles * kTcRois - 1) / (kTcTiles * kTcRois);
-    head_tc_kernel<<<grid, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg, kTcCtasPerSm * kSMs);
+    const int n_tiles = (n_cap + kTcRois - 1) / kTcRois;
+    head_tc_kernel<<<n_tiles < kSMs ? n_tiles : kSMs, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
     RR_LAUNCHED(rc);
     return rc;
 }

@@ -68,24 +68,17 @@ def main():
     assert rc == 0, rc
     t = np.frombuffer(buf, dtype=np.uint64).reshape(2048, 32).astype(np.int64)
     n_live = int(path.counts[-1].item())
-    n_cta = (n_live + 15) // 16
-    t = t[:min(n_cta, 2048)]
+    n_cta = min(148, (n_live + 7) // 8)
+    t = t[:n_cta]
     t0 = t[:, 0].min()
-    names = ["setup", "x0 issue", "conv1 loop", "conv1 mma wait", "epi1", "worker sync", "conv2 mma wait", "epi2",
-             "conv3a mma wait", "epi3a + conv3b", "epi3b + regress"]
-    marks = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]
-    print("CTAs traced %d; kernel span %.1f us" % (len(t), (t[:, 12].max() - t0) / 1e3))
-    dur = t[:, 12] - t[:, 0]
-    print("CTA duration us: mean %.1f  p10 %.1f  p50 %.1f  p90 %.1f  max %.1f" % (
-        dur.mean() / 1e3, *(np.percentile(dur, q) / 1e3 for q in (10, 50, 90)), dur.max() / 1e3))
-    first = t[:, 0] - t0 < 5000                     # CTAs of the first wave
-    for label, sel in (("all", np.ones(len(t), bool)), ("first wave", first), ("later waves", ~first)):
-        print("--", label, int(sel.sum()), "CTAs, mean us per phase")
-        for i, nm in enumerate(names):
-            seg = (t[sel, marks[i + 1]] - t[sel, marks[i]]) / 1e3
-            print("   %-16s %7.2f" % (nm, seg.mean()))
-    steps = np.diff(np.concatenate([t[:, 2:3], t[:, 16:24]], axis=1), axis=1) / 1e3
-    print("conv1 per-step us (mean over CTAs):", np.round(steps.mean(axis=0), 2))
+    n_my = t[:, 13]
+    print("CTAs %d; kernel span %.1f us; tiles per CTA %d..%d" % (n_cta, (t[:, 12].max() - t0) / 1e3, n_my.min(), n_my.max()))
+    print("setup %.2f us; first x tile staged after %.2f us; steady-state period %.2f us per tile (8 RoIs)" % (
+        (t[:, 1] - t[:, 0]).mean() / 1e3, (t[:, 2] - t[:, 1]).mean() / 1e3, ((t[:, 12] - t[:, 2]) / n_my).mean() / 1e3))
+    names = ["wait conv1", "E1", "-", "wait conv2", "E2", "E3 (incl. wait conv3)"]
+    print("epilogue thread 0, mean us per tile: " + "  ".join("%s %.2f" % (nm, (t[:, 16 + i] / n_my).mean() / 1e3) for i, nm in enumerate(names)))
+    print("issuer, mean us per tile blocked: on ring 2 %.2f  on t1/t2 %.2f  in blocking conv1 steps %.2f" % tuple(
+        (t[:, i] / n_my).mean() / 1e3 for i in (22, 23, 24)))
     # how many tile pieces the RoIs of this workload are cut into (approximation of roi_prep_kernel's count)
     bx = path.bxyxy[:n_live].float().cpu().numpy()
     ntx = np.floor((bx[:, 3] + 1) / 32) - np.floor(bx[:, 1] / 32) + 1

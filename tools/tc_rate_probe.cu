@@ -38,17 +38,20 @@ constexpr int kIters = 1020;
 
 __global__ void __launch_bounds__(128) rate_probe(int mode, int fill, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(8) unsigned long long mbar, mbar2;
     __shared__ uint32_t tmem_base;
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < (32768 + 32768) / 4; i += 128) reinterpret_cast<float*>(base)[i] = fill ? __uint_as_float(0x3f000000u + ((i * 2654435761u) >> 12 & 0x7fe000u)) : 0.f;
+    for (int i = tid; i < (49152 + 32768) / 4; i += 128) reinterpret_cast<float*>(base)[i] = fill ? __uint_as_float(0x3f000000u + ((i * 2654435761u) >> 12 & 0x7fe000u)) : 0.f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar2)) : "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -57,11 +60,11 @@ __global__ void __launch_bounds__(128) rate_probe(int mode, int fill, long long*
     if (warp == 1) {
         const uint32_t n = (mode == 2) ? 128u : ((mode == 3 || mode == 5) ? 256u : 64u);
         const uint32_t idesc = idesc_n(n);
-        const uint64_t da = make_desc(smem_u32(base)), db = make_desc(smem_u32(base + 32768));
+        const uint64_t da = make_desc(smem_u32(base)), db = make_desc(smem_u32(base + 49152));
         const uint32_t a_tm = tmem + 256u;       // A operand columns (zeros are fine: contents do not change the timing)
         t0 = clock64();
-        if (mode == 6 || mode == 7) {
-            const uint64_t a_hi = da, a_lo = make_desc(smem_u32(base + 16384)), b_hi = db, b_lo = make_desc(smem_u32(base + 32768 + 8192));
+        if (mode >= 6) {
+            const uint64_t a_hi = da, a_lo = make_desc(smem_u32(base + 24576)), b_hi = db, b_lo = make_desc(smem_u32(base + 49152 + 8192));
             if (mode == 6) {
                 if (lane == 0) {
                     for (int i = 0; i < kIters; i += 12) {
@@ -75,13 +78,23 @@ __global__ void __launch_bounds__(128) rate_probe(int mode, int fill, long long*
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
                 }
             } else {
+                // mode 8: + one tcgen05.commit per 12 MMAs; 9: three commits; 10: A start shifted by 5 rows (640 B);
+                // 11: alternate between two accumulators; 12: first MMA of each 12 overwrites (accumulate = 0)
+                const uint64_t sh = (mode == 10) ? (uint64_t)(640 >> 4) : 0;
                 for (int i = 0; i < kIters; i += 12) {
                     if (elect_one()) {
+                        const uint32_t d = tmem + ((mode == 11 && (i / 12 & 1)) ? 64u : 0u);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            mma_ss(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
-                            mma_ss(tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                            mma_ss(tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                            mma_ss(d, a_hi + sh + 2 * k, b_hi + 2 * k, idesc, (mode == 12 && k == 0) ? 0u : 1u);
+                            mma_ss(d, a_hi + sh + 2 * k, b_lo + 2 * k, idesc, 1u);
+                            mma_ss(d, a_lo + sh + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        }
+                        if (mode == 8 || mode == 9)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar2)) : "memory");
+                        if (mode == 9) {
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar2)) : "memory");
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar2)) : "memory");
                         }
                     }
                     __syncwarp();
@@ -128,14 +141,15 @@ __global__ void __launch_bounds__(128) rate_probe(int mode, int fill, long long*
 int main() {
     long long* d; long long h[2];
     cudaMalloc(&d, 16);
-    const int smem = 32768 + 32768 + 1024;
+    const int smem = 49152 + 32768 + 1024;
     cudaFuncSetAttribute(rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const char* names[] = {"lane==0 issue, SS, N=64", "elect.sync,    SS, N=64", "elect.sync,    SS, N=128", "elect.sync,    SS, N=256",
                            "elect.sync,    TS, N=64 (A in TMEM)", "elect.sync,    TS, N=256 (A in TMEM)"};
-    const char* names8[] = {names[0], names[1], names[2], names[3], names[4], names[5], "3xTF32 pattern, lane==0, SS, N=64", "3xTF32 pattern, elect.sync, SS, N=64"};
-    for (int grid = 1; grid <= 148; grid += 147)
-        for (int fill = 0; fill < 2; ++fill)
-            for (int mode = 0; mode < 8; ++mode) {
+    const char* names8[] = {names[0], names[1], names[2], names[3], names[4], names[5], "3xTF32 pattern, lane==0, SS, N=64", "3xTF32 pattern, elect.sync, SS, N=64",
+                            "3xTF32 + 1 commit / 12", "3xTF32 + 3 commits / 12", "3xTF32, A shifted 5 rows", "3xTF32, two accumulators", "3xTF32, overwrite every 12"};
+    for (int grid = 148; grid <= 148; grid += 147)
+        for (int fill = 1; fill < 2; ++fill)
+            for (int mode = 6; mode < 13; ++mode) {
                 for (int rep = 0; rep < 2; ++rep) rate_probe<<<grid, 128, smem>>>(mode, fill, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
