@@ -45,7 +45,7 @@ constexpr int kLoadWarps = 9;
 constexpr int kLoaders = 32 * kLoadWarps;        // 288 threads x 2 items = the 576 live (row, 16-byte chunk) items of an x tile
 constexpr int kTcItems = 2;
 constexpr int kTcSlotsInReg = 6;                 // partial slots of an item held in registers per K chunk
-constexpr int kWarpIssuer = kEpiWarps + kLoadWarps, kWarpWeights = kWarpIssuer + 1;
+constexpr int kWarpIssuer1 = kEpiWarps + kLoadWarps, kWarpIssuer2 = kWarpIssuer1 + 1, kWarpWeights = kWarpIssuer2 + 1;
 constexpr int kTcBlock = 32 * (kWarpWeights + 1);
 constexpr int kTcATile = 128 * 128;              // bytes: 128 rows x 32 tf32
 constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
@@ -211,11 +211,13 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     __shared__ __align__(8) unsigned long long s_free_b1[kAStages];  // ... consumed (tcgen05.commit)
     __shared__ __align__(8) unsigned long long s_full_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_free_b2[kRing2];
-    __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of conv1 / conv2 / conv3 first half / second half are done
+    __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of ([0] unused) conv2 / conv3 first half / second half are done
     __shared__ __align__(8) unsigned long long s_tready;             // t1, then t2 written by the epilogue (two phases per tile)
     __shared__ __align__(8) unsigned long long s_d3free;             // conv3's accumulator has been read out (one phase per tile)
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) unsigned long long s_xdone[2];           // fp32 copy of x (and s_sb) of a tile written, by tile parity
+    __shared__ __align__(8) unsigned long long s_xdone[4];           // fp32 copy of x (and s_sb) of a tile written, ring of four tiles
+    __shared__ __align__(8) unsigned long long s_c1done[2];          // MMAs of conv1 of a tile are done, by tile parity (the conv1 issuer runs ahead)
+    __shared__ __align__(8) unsigned long long s_d12free[2];         // conv1 / conv2 accumulator of a tile parity read out for good
     __shared__ int s_sb[4][kTcRois];                                 // first slot of the tile's RoIs, ring of four tiles
     __shared__ float s_b1[64], s_b2[64], s_b3[256];
     __shared__ float4 s_wr[256];                                     // regressor weights, one float4 per channel
@@ -251,12 +253,14 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         };
         for (int i = 0; i < kAStages; ++i) {
             init(&s_full_a[i], kLoadWarps); init(&s_free_a[i], 1); init(&s_full_b1[i], 1); init(&s_free_b1[i], 1);
-            init(&s_xdone[i], kLoadWarps);
+            init(&s_d12free[i], 4);
+            init(&s_c1done[i], 1);
         }
         for (int i = 0; i < kRing2; ++i) { init(&s_full_b2[i], 1); init(&s_free_b2[i], 1); }
         for (int i = 0; i < 4; ++i) init(&s_phase[i], 1);
         init(&s_tready, 4);
         init(&s_d3free, 4);
+        for (int i = 0; i < 4; ++i) init(&s_xdone[i], kLoadWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // zero fill -> visible to the MMA
@@ -297,10 +301,13 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         return;
     }
 
-    // ------------------------------ warp 9: the MMA issuer ------------------------------
-    // The warp stays converged (every lane tests the barriers, they all see the same answer) and one elected
-    // lane issues, so the compiler keeps descriptors in uniform registers and emits the MMAs back to back.
-    if (warp == kWarpIssuer) {
+    // ------------------------------ warps 17, 18: the MMA issuers ------------------------------
+    // Two instruction streams into the one tensor pipe, one warp each: conv1 of every tile (as soon as the loaders
+    // publish a stage), and conv2 + conv3 of every tile.  A warp stays converged (every lane waits on the
+    // barriers) and one elected lane issues, so the compiler keeps the descriptors in uniform registers and emits
+    // the MMAs back to back; tcgen05.mma is nearly synchronous for the issuing warp (tools/tc_rate_probe.cu: every
+    // instruction between two MMAs shows up in the rate), hence the unrolled steps with immediate operands.
+    if (warp == kWarpIssuer1 || warp == kWarpIssuer2) {
         const uint32_t sT = smem_addr(base), sA = smem_addr(stages), sB1 = smem_addr(ring1), sB2 = smem_addr(ring2);
         auto issue12 = [&](uint32_t sa_hi, uint32_t sa_lo, uint32_t sb, uint32_t d, bool first) {
             const uint64_t a_hi = umma_desc(sa_hi), a_lo = umma_desc(sa_lo);
@@ -312,62 +319,58 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 umma_tf32(d, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
             }
         };
-        uint32_t c1 = 0;                                        // conv1 steps issued: stage = c1 & 1, its use = c1 >> 1
-        uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % 3, its use c2 / 3
-        int s1 = 0;                                             // conv1 steps of the next tile issued in this period
-        uint32_t d12_next = tmem + kColD12;
-        // one conv1 step of the next tile; `block`: wait for its operands, else only take it if they are there
-        auto conv1_step = [&](bool block) {
-            const uint32_t st = c1 & 1u, par = (c1 >> 1) & 1u;
-            if (block) { bar_wait(&s_full_a[st], par); bar_wait(&s_full_b1[st], par); }
-            else if (!(bar_test(&s_full_a[st], par) && bar_test(&s_full_b1[st], par))) return;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                if (st == 0) issue12(sA, sA + kTcATile, sB1, d12_next, s1 == 0);
-                else issue12(sA + kTcAStage, sA + kTcAStage + kTcATile, sB1 + kTcBSlot, d12_next, s1 == 0);
-                umma_commit(&s_free_a[st]);
-                umma_commit(&s_free_b1[st]);
-                if (s1 == kSteps1 - 1) umma_commit(&s_phase[0]);
+        if (warp == kWarpIssuer1) {
+            for (int j = 0; j < n_my; ++j) {                    // conv1 of tile j -> D12[j & 1]
+                if (j >= 2) bar_wait(&s_d12free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));   // tile j - 2 has left that accumulator
+                const uint32_t d = tmem + kColD12 + 64u * (uint32_t)(j & 1);
+#pragma unroll
+                for (int s1 = 0; s1 < kSteps1; ++s1) {          // stage / ring-1 slot s1 & 1, its use 4 j + (s1 >> 1)
+                    const uint32_t par = (uint32_t)((s1 >> 1) & 1);     // (4 j is even)
+                    bar_wait(&s_full_a[s1 & 1], par);
+                    bar_wait(&s_full_b1[s1 & 1], par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t sa = sA + (uint32_t)((s1 & 1) * kTcAStage);
+                        issue12(sa, sa + kTcATile, sB1 + (uint32_t)((s1 & 1) * kTcBSlot), d, s1 == 0);
+                        umma_commit(&s_free_a[s1 & 1]);
+                        umma_commit(&s_free_b1[s1 & 1]);
+                        if (s1 == kSteps1 - 1) umma_commit(&s_c1done[j & 1]);
+                    }
+                }
             }
-            __syncwarp();
-            ++s1;
-            ++c1;
-        };
-        long long w_b2 = 0, w_t = 0, w_c1 = 0;                   // trace build: ns blocked on ring 2 / on t1, t2 / in blocking conv1 steps
-        while (s1 < kSteps1) conv1_step(true);                  // conv1 of the first tile
+            return;
+        }
+        uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % 3, its use c2 / 3
+        long long w_b2 = 0, w_t = 0, w_c1 = 0;                   // trace build: ns blocked on ring 2 / on t1, t2
         for (int it = 0; it < n_my; ++it) {
-            // period `it`: conv2 / conv3 of tile it in program order (steps unrolled: shifts, columns and flags are
-            // immediates), a conv1 step of tile it + 1 slotted in after each of them whenever its operands are ready
-            const bool has_next = it + 1 < n_my;
-            s1 = has_next ? 0 : kSteps1;
             const uint32_t d12_cur = tmem + kColD12 + 64u * (uint32_t)(it & 1);
-            d12_next = tmem + kColD12 + 64u * (uint32_t)((it + 1) & 1);
             uint32_t slot2 = c2 % kRing2, par2 = (c2 / kRing2) & 1u;
 #pragma unroll
-            for (int s2 = 0; s2 < kSteps2; ++s2) {
+            for (int s2 = 0; s2 < kSteps2; s2 += 2) {           // two steps (kc = 0, 1 of a tap / quarter) per round
                 if (s2 == 0) TC_TIMED(w_t, bar_wait(&s_tready, 0u));           // t1 in place
                 if (s2 == 18) {
-                    TC_TIMED(w_c1, while (s1 < kSteps1) conv1_step(true));      // every conv1 stage of the next tile, then t2
                     TC_TIMED(w_t, bar_wait(&s_tready, 1u));                    // t2 in place
                     if (it > 0) bar_wait(&s_d3free, (uint32_t)((it - 1) & 1));  // the previous tile has left conv3's accumulator
                 }
-                TC_TIMED(w_b2, bar_wait(&s_full_b2[slot2], par2));
+                const uint32_t slot_a = slot2, par_a = par2;
+                if (++slot2 == kRing2) { slot2 = 0; par2 ^= 1u; }
+                const uint32_t slot_b = slot2, par_b = par2;
+                if (++slot2 == kRing2) { slot2 = 0; par2 ^= 1u; }
+                TC_TIMED(w_b2, bar_wait(&s_full_b2[slot_a], par_a); bar_wait(&s_full_b2[slot_b], par_b));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int kc = s2 & 1;
                 int shift = 0;
                 if (s2 < 18) { const int tap = s2 >> 1; shift = 4 * (tap / 3 - 1) + (tap % 3 - 1); }
-                const uint32_t sa_hi = sT + (uint32_t)(kc * kPlaneBytes + (kMargin + shift) * 128);
+                const uint32_t sa_hi = sT + (uint32_t)((kMargin + shift) * 128);
                 const uint32_t d = s2 < 18 ? d12_cur : tmem + kColD3 + 64u * (uint32_t)((s2 - 18) >> 1);
                 if (elect_one()) {
-                    issue12(sa_hi, sa_hi + 2 * kPlaneBytes, sB2 + slot2 * (uint32_t)kTcBSlot, d, s2 < 18 ? s2 == 0 : kc == 0);
-                    umma_commit(&s_free_b2[slot2]);
-                    if (s2 == 17) umma_commit(&s_phase[1]);
-                    if (s2 == 21) umma_commit(&s_phase[2]);
-                    if (s2 == 25) umma_commit(&s_phase[3]);
+                    issue12(sa_hi, sa_hi + 2 * kPlaneBytes, sB2 + slot_a * (uint32_t)kTcBSlot, d, s2 < 18 ? s2 == 0 : true);
+                    umma_commit(&s_free_b2[slot_a]);
+                    issue12(sa_hi + kPlaneBytes, sa_hi + 3 * kPlaneBytes, sB2 + slot_b * (uint32_t)kTcBSlot, d, false);
+                    umma_commit(&s_free_b2[slot_b]);
+                    if (s2 == 16) umma_commit(&s_phase[1]);
+                    if (s2 == 20) umma_commit(&s_phase[2]);
+                    if (s2 == 24) umma_commit(&s_phase[3]);
                 }
-                __syncwarp();
-                if (++slot2 == kRing2) { slot2 = 0; par2 ^= 1u; }
-                if (s1 < kSteps1) conv1_step(false);
             }
             c2 += kSteps2;
         }
@@ -382,7 +385,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     // ahead of the tensor core as the two A stages allow.  The 316 MB of partial slots come from DRAM in 128-byte
     // pieces (about half of the HBM bandwidth is reachable that way): ~10 us per tile, which is why this runs in
     // its own warps next to the MMAs and the epilogues instead of in front of them.
-    if (warp >= kEpiWarps) {
+    if (warp >= kEpiWarps && warp < kWarpIssuer1) {
         const int ltid = tid - kEpiThreads;
         int it_row[kTcItems], it_p[kTcItems], it_ch[kTcItems], xoff[kTcItems];
 #pragma unroll
@@ -482,7 +485,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
             __threadfence_block();                              // the fp32 copy and s_sb, before the epilogue warps are told
             __syncwarp();
-            if (lane == 0) bar_arrive(&s_xdone[k & 1]);
+            if (lane == 0) bar_arrive(&s_xdone[k & 3]);
         }
         return;
     }
@@ -531,7 +534,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             const uint32_t d12 = tmem + kColD12 + 64u * par;
             if (k > 0) bar_wait_warp(&s_phase[3], par ^ 1u);    // conv3(k-1) has finished reading the t planes
             TC_LAP(w_e3);
-            bar_wait_warp(&s_phase[0], par);                    // conv1(k) done
+            bar_wait_warp(&s_c1done[k & 1], (uint32_t)((k >> 1) & 1));    // conv1(k) done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             TC_LAP(w_p0);
             epilogue_t(d12, s_b1, true);
@@ -540,6 +543,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             TC_LAP(w_p1);
             epilogue_t(d12, s_b2, false);
+            if (lane == 0) bar_arrive(&s_d12free[k & 1]);        // (after epilogue_t's tcgen05 fence and __syncwarp)
             TC_LAP(w_e2);
         }
 #ifdef RR_HEAD_TC_TRACE
@@ -553,7 +557,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             const int nroi = min(kTcRois, live - roi0);
             const uint32_t par = (uint32_t)(k & 1);
             const bool ekeep = pixel_row && (em >> 4) < nroi;
-            bar_wait_warp(&s_xdone[k & 1], (uint32_t)((k >> 1) & 1));     // the loaders' copy of x and s_sb are complete
+            bar_wait_warp(&s_xdone[k & 3], (uint32_t)((k >> 2) & 1));     // the loaders' copy of x and s_sb are complete
             const float* res = src.roi_feat;                    // residual source of this thread's row
             bool res_rows = false;                              // true: [9][256] copy, false: [256][9] feature
             if (ekeep) {
