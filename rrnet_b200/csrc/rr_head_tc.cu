@@ -62,6 +62,7 @@ static_assert(kSteps1 + kSteps2 == kTcSteps, "the two streams cover the folded i
 constexpr int kTcSmem = kTBytes + kAStages * kTcAStage + (kAStages + kRing2) * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColD12 = 0, kColD3 = 128;    // conv1 / conv2 accumulator (+64 for odd tiles), conv3 accumulator (256 columns)
+constexpr uint32_t kColT2 = 384;                 // t2 as conv3's A operand: 64 columns tf32 hi, 64 columns lo
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 //                          D = f32      A = tf32     B = tf32      N = 64               M = 128      (both K-major)
 
@@ -77,6 +78,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand in tensor memory: A[m][k] = lane m, column a_tmem + k (32-bit tf32 words)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+                   "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+                   "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+                   "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]) : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
@@ -319,6 +334,15 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 umma_tf32(d, a_lo + 2 * ks, b_hi + 2 * ks, 1u);
             }
         };
+        auto issue12_ts = [&](uint32_t a_hi, uint32_t sb, uint32_t d, bool first) {       // a_lo = a_hi + 64 columns
+            const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + kTcBTile);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                umma_tf32_ts(d, a_hi + 8u * ks, b_hi + 2 * ks, (first && ks == 0) ? 0u : 1u);
+                umma_tf32_ts(d, a_hi + 8u * ks, b_lo + 2 * ks, 1u);
+                umma_tf32_ts(d, a_hi + 64u + 8u * ks, b_hi + 2 * ks, 1u);
+            }
+        };
         if (warp == kWarpIssuer1) {
             for (int j = 0; j < n_my; ++j) {                    // conv1 of tile j -> D12[j & 1]
                 if (j >= 2) bar_wait(&s_d12free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));   // tile j - 2 has left that accumulator
@@ -363,10 +387,17 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 const uint32_t sa_hi = sT + (uint32_t)((kMargin + shift) * 128);
                 const uint32_t d = s2 < 18 ? d12_cur : tmem + kColD3 + 64u * (uint32_t)((s2 - 18) >> 1);
                 if (elect_one()) {
-                    issue12(sa_hi, sa_hi + 2 * kPlaneBytes, sB2 + slot_a * (uint32_t)kTcBSlot, d, s2 < 18 ? s2 == 0 : true);
-                    umma_commit(&s_free_b2[slot_a]);
-                    issue12(sa_hi + kPlaneBytes, sa_hi + 3 * kPlaneBytes, sB2 + slot_b * (uint32_t)kTcBSlot, d, false);
-                    umma_commit(&s_free_b2[slot_b]);
+                    if (s2 < 18) {                              // conv2: A = t1 tiles in shared memory, shifted by the tap
+                        issue12(sa_hi, sa_hi + 2 * kPlaneBytes, sB2 + slot_a * (uint32_t)kTcBSlot, d, s2 == 0);
+                        umma_commit(&s_free_b2[slot_a]);
+                        issue12(sa_hi + kPlaneBytes, sa_hi + 3 * kPlaneBytes, sB2 + slot_b * (uint32_t)kTcBSlot, d, false);
+                        umma_commit(&s_free_b2[slot_b]);
+                    } else {                                    // conv3: A = t2 in tensor memory
+                        issue12_ts(tmem + kColT2, sB2 + slot_a * (uint32_t)kTcBSlot, d, true);
+                        umma_commit(&s_free_b2[slot_a]);
+                        issue12_ts(tmem + kColT2 + 32u, sB2 + slot_b * (uint32_t)kTcBSlot, d, false);
+                        umma_commit(&s_free_b2[slot_b]);
+                    }
                     if (s2 == 16) umma_commit(&s_phase[1]);
                     if (s2 == 20) umma_commit(&s_phase[2]);
                     if (s2 == 24) umma_commit(&s_phase[3]);
@@ -498,29 +529,45 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     if (warp < 4) {
         // E1 / E2: t = relu(D + b) of conv1 / conv2 -> (hi, lo) tf32 planes in the MMA tile layout; the two column
         // halves of the accumulator are the two K chunks of the next GEMM
-        auto epilogue_t = [&](uint32_t d12, const float* bias, bool mask_pad) {
-            const bool keep = !mask_pad || pixel_row;           // conv2 reads the pad rows as zeros
+        // E1: t1 = relu(conv1 + b1) -> (hi, lo) tf32 tiles in shared memory (conv2 reads them through shifted
+        //     descriptors; pad rows are written as zeros).  The two column halves are the K chunks of conv2.
+        // E2: t2 = relu(conv2 + b2) -> (hi, lo) tf32 in tensor memory, conv3's A operand: the shared-memory tiles
+        //     are free for t1 of the next tile while conv3 runs.
+        auto epilogue_t = [&](uint32_t d12, const float* bias, bool to_smem) {
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 float v[32];
                 tmem_ld32(d12 + ((uint32_t)(32 * eq) << 16) + (uint32_t)(32 * h), v);
-                uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + em) * 128;
-                uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
+                if (to_smem) {
+                    uint8_t* p_hi = base + h * kPlaneBytes + (kMargin + em) * 128;
+                    uint8_t* p_lo = p_hi + 2 * kPlaneBytes;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 o;
-                    o.x = keep ? fmaxf(v[4 * c] + bias[32 * h + 4 * c], 0.f) : 0.f;
-                    o.y = keep ? fmaxf(v[4 * c + 1] + bias[32 * h + 4 * c + 1], 0.f) : 0.f;
-                    o.z = keep ? fmaxf(v[4 * c + 2] + bias[32 * h + 4 * c + 2], 0.f) : 0.f;
-                    o.w = keep ? fmaxf(v[4 * c + 3] + bias[32 * h + 4 * c + 3], 0.f) : 0.f;
-                    float4 hi, lo;
-                    split4(o, hi, lo);
-                    const int off = (c ^ (em & 7)) << 4;
-                    *reinterpret_cast<float4*>(p_hi + off) = hi;
-                    *reinterpret_cast<float4*>(p_lo + off) = lo;
+                    for (int c = 0; c < 8; ++c) {
+                        float4 o;
+                        o.x = pixel_row ? fmaxf(v[4 * c] + bias[32 * h + 4 * c], 0.f) : 0.f;
+                        o.y = pixel_row ? fmaxf(v[4 * c + 1] + bias[32 * h + 4 * c + 1], 0.f) : 0.f;
+                        o.z = pixel_row ? fmaxf(v[4 * c + 2] + bias[32 * h + 4 * c + 2], 0.f) : 0.f;
+                        o.w = pixel_row ? fmaxf(v[4 * c + 3] + bias[32 * h + 4 * c + 3], 0.f) : 0.f;
+                        float4 hi, lo;
+                        split4(o, hi, lo);
+                        const int off = (c ^ (em & 7)) << 4;
+                        *reinterpret_cast<float4*>(p_hi + off) = hi;
+                        *reinterpret_cast<float4*>(p_lo + off) = lo;
+                    }
+                } else {
+                    float lo[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float o = fmaxf(v[e] + bias[32 * h + e], 0.f);
+                        v[e] = to_tf32(o);
+                        lo[e] = to_tf32(o - v[e]);
+                    }
+                    tmem_st32(tmem + ((uint32_t)(32 * eq) << 16) + kColT2 + (uint32_t)(32 * h), v);
+                    tmem_st32(tmem + ((uint32_t)(32 * eq) << 16) + kColT2 + 64u + (uint32_t)(32 * h), lo);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (to_smem) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            else asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(&s_tready);
@@ -532,8 +579,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         for (int k = 0; k < n_my; ++k) {
             const uint32_t par = (uint32_t)(k & 1);
             const uint32_t d12 = tmem + kColD12 + 64u * par;
-            if (k > 0) bar_wait_warp(&s_phase[3], par ^ 1u);    // conv3(k-1) has finished reading the t planes
-            TC_LAP(w_e3);
+            TC_LAP(w_e3);      // (conv2(k-1) has left the t1 tiles: waited for before E2(k-1))
             bar_wait_warp(&s_c1done[k & 1], (uint32_t)((k >> 1) & 1));    // conv1(k) done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             TC_LAP(w_p0);
