@@ -22,16 +22,28 @@
 //
 // The kernel is persistent (one CTA per SM walks over the tiles) and software-pipelined across tiles, because
 // inside one tile the tensor pipe and the ordinary warps only take turns (conv1 -> epilogue -> conv2 ->
-// epilogue -> conv3 -> epilogue).  While the tensor core runs conv2 / conv3 of tile i the workers already sum,
-// split and stage x of tile i+1, and its conv1 MMAs are slotted between the conv2 / conv3 steps of tile i:
-//   warps 0-8   workers: E1(i) [t1 = relu(conv1 + b1) -> smem tiles], W(i+1) [x of the next tile -> conv1 A
-//               stages + fp32 copy for the residual], E2(i) [t2], E3(i) [y = conv3 + b3 + x, relu, regressor]
-//   warp  9     one elected lane issues every tcgen05.mma; two instruction streams (conv1 of tile i+1 / conv2
-//               and conv3 of tile i), whichever has its operands ready goes next
-//   warp  10    lane 0 streams the pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
-//               rr_head_fold) with cp.async.bulk (TMA) + complete_tx into one ring per stream
-// mbarriers connect the roles; there is no block-wide barrier after the prologue.  TMEM: conv1 / conv2
-// accumulator double-buffered by tile parity (columns 0-63 / 64-127), conv3 in columns 128-383.
+// epilogue -> conv3 -> epilogue), and because the 316 MB of RoIAlign partial slots come in 128-byte pieces
+// from DRAM (~10 us per tile at about half of the HBM bandwidth).  Twenty warps, five concurrent roles:
+//   warps 0-3    E1(k): t1 = relu(conv1 + b1) -> tf32 (hi, lo) tiles in shared memory (conv2's shifted A operand);
+//                E2(k): t2 = relu(conv2 + b2) -> tf32 (hi, lo) in TENSOR memory: conv3 takes its A operand there,
+//                so the shared-memory tiles are free for t1 of tile k+1 while conv3(k) runs
+//   warps 4-7    E3(k): y = conv3 + b3 + x, relu, regressor, mean over the 9 pixels (the long epilogue, off the
+//                tensor core's critical path); x comes from an fp32 copy the loaders leave in global memory
+//   warps 8-16   x loaders: sum the partial slots of tile k+1.. (slot order = roi_combine_kernel's), scale, split,
+//                fill the two conv1 A stages, as far ahead as the stages allow
+//   warp  17     issues conv1 of every tile as soon as a stage is published (accumulator double-buffered by
+//                tile parity, so conv1(k+1) runs under conv2(k) / conv3(k))
+//   warp  18     issues conv2 and conv3 of every tile, two weight steps per round, steps unrolled (immediates)
+//   warp  19     lane 0 streams the pre-split, pre-swizzled weight tile pairs (16 KB each, made once by
+//                rr_head_fold) with cp.async.bulk (TMA) + complete_tx: one slot for the conv1 stream (paced by
+//                the loaders), a ring of four for conv2 / conv3
+// In an issuer warp every lane waits on the barriers and one elected lane issues: tcgen05.mma is nearly
+// synchronous for the issuing thread (tools/tc_rate_probe.cu; every instruction between two MMAs shows up in
+// the rate), so descriptors stay in uniform registers and the MMAs go out back to back.  mbarriers connect the
+// roles; there is no block-wide barrier after the prologue.  TMEM (512 columns): conv1 / conv2 accumulator
+// 0-63 / 64-127 by tile parity, conv3 accumulator 128-383, t2 (hi | lo) 384-511.  Measured alternatives that
+// lost: L2 bulk prefetch of the next tile's slots (-6 %), two CTAs per SM with half the resources, two tiles
+// per CTA in lockstep, slot-major x loading, a single epilogue group (E3 then delays t1 of the next tile).
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
@@ -52,14 +64,15 @@ constexpr int kTcBTile = 64 * 128;               // bytes:  64 rows x 32 tf32
 constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB
 constexpr int kAStages = 2;                      // conv1 A stages; ring 1 (conv1 weights) has one slot per stage
 constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one step of the weight image
-constexpr int kRing2 = 3;                        // slots of ring 2 (conv2 / conv3 weights)
+constexpr int kRing1 = 1;                        // slots of ring 1 (conv1 weights): the conv1 stream is paced by the x loaders, not by its weights
+constexpr int kRing2 = 4;                        // slots of ring 2 (conv2 / conv3 weights)
 constexpr int kSteps1 = 8, kSteps2 = 26;         // weight steps of stream 1 (conv1) and stream 2 (conv2, conv3)
 constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
 constexpr int kPlaneBytes = (128 + 2 * kMargin) * 128;
 constexpr int kTBytes = 4 * kPlaneBytes;         // t planes (hi | lo) x (kc 0 | 1): 72 KB
 static_assert(kTcBSlot == kTcStepFloats * 4, "a ring slot is one step of the folded image");
 static_assert(kSteps1 + kSteps2 == kTcSteps, "the two streams cover the folded image");
-constexpr int kTcSmem = kTBytes + kAStages * kTcAStage + (kAStages + kRing2) * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
+constexpr int kTcSmem = kTBytes + kAStages * kTcAStage + (kRing1 + kRing2) * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColD12 = 0, kColD3 = 128;    // conv1 / conv2 accumulator (+64 for odd tiles), conv3 accumulator (256 columns)
 constexpr uint32_t kColT2 = 384;                 // t2 as conv3's A operand: 64 columns tf32 hi, 64 columns lo
@@ -222,8 +235,8 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     extern __shared__ uint8_t s_dyn[];
     __shared__ __align__(8) unsigned long long s_full_a[kAStages];   // conv1 A stage filled (one arrival per worker warp)
     __shared__ __align__(8) unsigned long long s_free_a[kAStages];   // ... consumed (tcgen05.commit)
-    __shared__ __align__(8) unsigned long long s_full_b1[kAStages];  // ring 1 slot landed (complete_tx)
-    __shared__ __align__(8) unsigned long long s_free_b1[kAStages];  // ... consumed (tcgen05.commit)
+    __shared__ __align__(8) unsigned long long s_full_b1[kRing1];    // ring 1 slot landed (complete_tx)
+    __shared__ __align__(8) unsigned long long s_free_b1[kRing1];    // ... consumed (tcgen05.commit)
     __shared__ __align__(8) unsigned long long s_full_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_free_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of ([0] unused) conv2 / conv3 first half / second half are done
@@ -247,7 +260,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     // t planes: plane (hi|lo, kc) at base + (2*lo + kc) * kPlaneBytes: 8 zero rows, the 128 tile rows, 8 zero rows
     uint8_t* stages = base + kTBytes;                           // conv1 A stages (A_hi | A_lo)
     uint8_t* ring1 = stages + kAStages * kTcAStage;             // conv1 weights, slot = stage
-    uint8_t* ring2 = ring1 + kAStages * kTcBSlot;               // conv2 / conv3 weights
+    uint8_t* ring2 = ring1 + kRing1 * kTcBSlot;                 // conv2 / conv3 weights
 
     // ------------------------------ prologue (all warps) ------------------------------
     for (int i = tid; i < (kTBytes + kAStages * kTcAStage) / 16; i += kTcBlock)   // margins and pad rows stay zero for good
@@ -267,11 +280,12 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
         };
         for (int i = 0; i < kAStages; ++i) {
-            init(&s_full_a[i], kLoadWarps); init(&s_free_a[i], 1); init(&s_full_b1[i], 1); init(&s_free_b1[i], 1);
+            init(&s_full_a[i], kLoadWarps); init(&s_free_a[i], 1);
             init(&s_d12free[i], 4);
             init(&s_c1done[i], 1);
         }
         for (int i = 0; i < kRing2; ++i) { init(&s_full_b2[i], 1); init(&s_free_b2[i], 1); }
+        for (int i = 0; i < kRing1; ++i) { init(&s_full_b1[i], 1); init(&s_free_b1[i], 1); }
         for (int i = 0; i < 4; ++i) init(&s_phase[i], 1);
         init(&s_tready, 4);
         init(&s_d3free, 4);
@@ -286,7 +300,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     const uint32_t tmem = s_tmem;
     const float* ftc = f + kOffTc;
 
-    // ------------------------------ warp 10: the weight streams ------------------------------
+    // ------------------------------ warp 19: the weight streams ------------------------------
     if (warp == kWarpWeights) {
         if (lane == 0) {
             auto load_b = [&](unsigned long long* full, uint8_t* slot, int image_step) {
@@ -304,12 +318,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     if (++s2 == kSteps2) s2 = 0;
                     if (++slot2 == kRing2) { slot2 = 0; ++use2; }
                 }
-                if (c1 < total1) {
-                    const int slot = c1 & 1, use = c1 >> 1;
-                    if (use == 0 || bar_test(&s_free_b1[slot], (uint32_t)((use - 1) & 1))) {
-                        load_b(&s_full_b1[slot], ring1 + slot * kTcBSlot, c1 & 7);
-                        ++c1;
-                    }
+                if (c1 < total1 && (c1 == 0 || bar_test(&s_free_b1[0], (uint32_t)((c1 - 1) & 1)))) {
+                    load_b(&s_full_b1[0], ring1, c1 & 7);
+                    ++c1;
                 }
             }
         }
@@ -349,15 +360,14 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 const uint32_t d = tmem + kColD12 + 64u * (uint32_t)(j & 1);
 #pragma unroll
                 for (int s1 = 0; s1 < kSteps1; ++s1) {          // stage / ring-1 slot s1 & 1, its use 4 j + (s1 >> 1)
-                    const uint32_t par = (uint32_t)((s1 >> 1) & 1);     // (4 j is even)
-                    bar_wait(&s_full_a[s1 & 1], par);
-                    bar_wait(&s_full_b1[s1 & 1], par);
+                    bar_wait(&s_full_a[s1 & 1], (uint32_t)((s1 >> 1) & 1));     // (4 j is even)
+                    bar_wait(&s_full_b1[0], (uint32_t)(s1 & 1));                // its use is 8 j + s1
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
                         const uint32_t sa = sA + (uint32_t)((s1 & 1) * kTcAStage);
-                        issue12(sa, sa + kTcATile, sB1 + (uint32_t)((s1 & 1) * kTcBSlot), d, s1 == 0);
+                        issue12(sa, sa + kTcATile, sB1, d, s1 == 0);
                         umma_commit(&s_free_a[s1 & 1]);
-                        umma_commit(&s_free_b1[s1 & 1]);
+                        umma_commit(&s_free_b1[0]);
                         if (s1 == kSteps1 - 1) umma_commit(&s_c1done[j & 1]);
                     }
                 }
@@ -467,11 +477,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     } else {
 #pragma unroll
                         for (int j = 0; j < kTcSlotsInReg; ++j)
-#ifdef RR_TC_EXP_NOX
-                            if (j < xpc[q] && kc < 0)
-#else
                             if (j < xpc[q])
-#endif
                                 xp[q][j] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)j * 2304 + 32 * kc));
                     }
                 }

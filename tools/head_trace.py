@@ -13,7 +13,7 @@ from rrnet_b200 import build as B  # noqa: E402
 TRACE_LIB = os.path.join(ROOT, "tools", "librrnet_trace.so")
 
 
-VARIANTS = {"": [], "nox": ["-DRR_TC_EXP_NOX"]}
+VARIANTS = {"": []}
 
 
 def lib_path(variant):
