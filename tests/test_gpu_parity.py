@@ -306,6 +306,31 @@ def test_head_golden_and_oracle(ops, oracle_mod, algo):
     ref = oracle_mod.head(x.numpy(), {k: v.numpy() for k, v in hp.items()})
     assert rel_err(y, ref, floor=1.0) < TOL
 
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 127, 1184, 1185, 2501])
+def test_head_tile_counts_and_device_count(ops, oracle_mod, n):
+    """The tensor-core head is persistent: 148 CTAs walk over tiles of 8 RoIs.  RoI counts around the tile size,
+    around one tile per CTA (148 * 8 = 1184) and several tiles per CTA; both kernels against the oracle, and the
+    device-side row count (rows past it must stay untouched)."""
+    hp = synth.head_params(5)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    gen = torch.Generator().manual_seed(100 + n)
+    x = torch.relu(torch.randn(n, 256, 3, 3, generator=gen)) * 3 - 0.25     # a few negative inputs too
+    ref = oracle_mod.head(x.numpy(), {k: v.numpy() for k, v in hp.items()})
+    for algo in (0, 1):
+        y = npy(ops.head_forward(dev(x), folded, algo=algo))
+        assert rel_err(y, ref, floor=1.0) < TOL
+    live = max(n - 3, 0)
+    n_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    L = ops._lib.lib()
+    reg = torch.full((n, 4), 12345.0, device="cuda")
+    xd = dev(x)
+    ops.check(L.rr_head_forward(xd.data_ptr(), n_dev.data_ptr(), n, folded.data_ptr(), 0, reg.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream), "rr_head_forward")
+    reg = npy(reg)
+    if live:
+        assert rel_err(reg[:live], ref[:live], floor=1.0) < TOL
+    assert (reg[live:] == 12345.0).all()
+
 
 # ===================================================================== whole eval path (a1..a8)
 def test_eval_path_golden(ops):
