@@ -293,6 +293,25 @@ def run_product(args):
 
     graph = None if args.no_graph else path.capture(d["hm"], d["wh"], d["off"], d["feat"])
 
+    # Batches in flight.  At B = 8 a fifth of a step is spent in kernels that cannot fill the GPU (one CTA per image
+    # or per class segment: top-K selection, greedy NMS scan, RoIAlign bookkeeping).  Steps are independent, so
+    # consecutive steps alternate between `--streams` streams (own buffers, own CUDA graph) and the persistent
+    # kernels leave `--sm-reserve` SMs free: the latency chains of one batch run next to the bandwidth-bound
+    # kernels of the other.  Same launches, same results per step; `single_batch` in the line is one batch at a time.
+    n_streams = 1 if graph is None else max(1, args.streams)
+    pipes = []
+    if n_streams > 1:
+        ops.set_sm_reserve(args.sm_reserve)         # grid sizes are baked in at capture
+        for _ in range(n_streams):
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(st):
+                pp = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo, head_algo=args.head_algo)
+                gg = pp.capture(d["hm"], d["wh"], d["off"], d["feat"])
+            gb = (torch.empty_like(gathered), torch.empty_like(gathered_cnt)) if world > 1 else None
+            pipes.append((st, pp, gg, gb))
+        ops.set_sm_reserve(0)
+        torch.cuda.synchronize()
+
     def step(events=None):
         if graph is not None and events is None:
             graph.replay()                 # the same launches, submitted as one CUDA graph
@@ -301,6 +320,25 @@ def run_product(args):
         if world > 1:            # all-gather of detections for mAP (padded rows + counts)
             dist.all_gather_into_tensor(gathered, path.s2)
             dist.all_gather_into_tensor(gathered_cnt, path.counts)
+
+    def run_steps(n):
+        """n steps on the current stream, or round-robin over the pipes (fork / join around them)."""
+        if not pipes:
+            for _ in range(n):
+                step()
+            return
+        main_stream = torch.cuda.current_stream()
+        for st, _, _, _ in pipes:
+            st.wait_stream(main_stream)
+        for i in range(n):
+            st, pp, gg, gb = pipes[i % len(pipes)]
+            with torch.cuda.stream(st):
+                gg.replay()
+                if world > 1:
+                    dist.all_gather_into_tensor(gb[0], pp.s2)
+                    dist.all_gather_into_tensor(gb[1], pp.counts)
+        for st, _, _, _ in pipes:
+            main_stream.wait_stream(st)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -313,6 +351,7 @@ def run_product(args):
     launches_per_step = ops._lib.launch_count() - launches0     # kernels of ours per step (same inside the graph)
     for _ in range(max(args.warmup, 3)):
         step()
+    run_steps(max(args.warmup, 3) * max(1, len(pipes)))
     sync_all()
 
     # ---- timed region: K steps, device-resident inputs, no host sync inside ----
@@ -321,11 +360,26 @@ def run_product(args):
     sync_all()
     sampler.start()
     t_beg.record()
-    for i in range(args.steps):
-        step()
+    run_steps(args.steps)
     t_end.record()
     sync_all()
     clocks = sampler.stop()
+    single = None
+    if pipes:                      # one batch at a time (one stream, all SMs), for comparison
+        s_beg, s_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_beg.record()
+        for i in range(args.steps):
+            step()
+        s_end.record()
+        sync_all()
+        ts = torch.tensor([s_beg.elapsed_time(s_end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        single = {"ms_per_step": float(ts.item()) / args.steps,
+                  "value": world * B * args.steps / (float(ts.item()) / 1e3), "unit": UNIT}
+        for _, pp, _, _ in pipes:  # every pipe computed what the single path computed
+            if not (torch.equal(pp.s2, path.s2) and torch.equal(pp.counts, path.counts)):
+                raise SystemExit("bench.py: a pipelined batch differs from the single-batch result")
     launches = launches_per_step * args.steps
     elapsed_ms = t_beg.elapsed_time(t_end)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -456,12 +510,13 @@ def run_product(args):
             "config": {"workload": WORKLOAD_NAME, **WORKLOAD, "global_batch": world * B,
                        "parallelism": "image-sharded x%d, all-gather of detections" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (features 1.07 GB per step)",
-                       "submission": "eager launches" if args.no_graph else "CUDA graph replay of the step (memset + 12 kernels)",
+                       "submission": "eager launches" if args.no_graph else "CUDA graph replay of the step (memset + 14 kernels)",
+                       "batches_in_flight": max(1, len(pipes)), "sm_reserve": args.sm_reserve if pipes else 0,
                        "rois_per_step": r["n"]},
             "clocks": clocks, "gpu_launches": int(launches) * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
-            "roofline": roofline, "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info,
+            "single_batch": single, "roofline": roofline, "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info,
             "reference_cuda": ref_cuda, "aux": aux}
     print(json.dumps(line))
     if world > 1:
@@ -481,6 +536,8 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
     ap.add_argument("--head-algo", type=int, default=0, help="0 tcgen05 tensor-core head (default), 1 fp32 FFMA head")
     ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
+    ap.add_argument("--streams", type=int, default=2, help="batches in flight (steps alternate between that many streams)")
+    ap.add_argument("--sm-reserve", type=int, default=8, help="SMs the persistent kernels leave free when --streams > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

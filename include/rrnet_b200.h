@@ -50,6 +50,10 @@ int         rr_version(void);
 const char* rr_error_string(int code);
 /* number of kernel launches issued by this library since load (all entry points) */
 uint64_t    rr_launch_count(void);
+/* Number of SMs (0..147, default 0) that the persistent kernels (tile RoIAlign, tensor-core head) leave free, so that
+ * the short latency-bound kernels of ANOTHER batch on another stream can run next to them (bench.py --streams 2).
+ * Process-wide; takes effect at the next launch / graph capture. */
+int         rr_set_sm_reserve(int n_sms);
 
 /* ------------------------------------------------------------------------------------------
  * Decode: replaces RRNet.transform_bbox + RRNet._topk + _gather_feat /

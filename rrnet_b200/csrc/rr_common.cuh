@@ -27,6 +27,8 @@ extern std::atomic<uint64_t> g_launches;   // defined in rr_api.cu
     } while (0)
 
 constexpr int kSMs = 148;   // B200
+extern std::atomic<int> g_sm_reserve;      // SMs the persistent kernels leave free (rr_set_sm_reserve), defined in rr_api.cu
+inline int sms_for_persistent() { const int r = g_sm_reserve.load(std::memory_order_relaxed); return kSMs - (r < 0 ? 0 : (r > kSMs - 1 ? kSMs - 1 : r)); }
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 

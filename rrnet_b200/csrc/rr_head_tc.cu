@@ -694,7 +694,8 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
     if (((uintptr_t)folded & 15) != 0) return RR_E_BADARG;     // the weight stream is copied in 16-byte units
     if (src.partial && !src.scratch) return RR_E_BADARG;
     const int n_tiles = (n_cap + kTcRois - 1) / kTcRois;
-    head_tc_kernel<<<n_tiles < kSMs ? n_tiles : kSMs, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
+    const int sms = sms_for_persistent();
+    head_tc_kernel<<<n_tiles < sms ? n_tiles : sms, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
     RR_LAUNCHED(rc);
     return rc;
 }

@@ -769,7 +769,7 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
             RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
             attr_set = true;
         }
-        roi_tile_kernel<<<2 * kSMs, kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
+        roi_tile_kernel<<<2 * sms_for_persistent(), kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
                                                                   w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
                                                                   w.td, w.partial);
         RR_LAUNCHED(rc);
@@ -779,7 +779,7 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
             w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
         RR_LAUNCHED(rc);
     }
-    roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * kSMs, kRoiThreads, 0, st>>>(
+    roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * sms_for_persistent(), kRoiThreads, 0, st>>>(
         feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
     RR_LAUNCHED(rc);
     return rc;

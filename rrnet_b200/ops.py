@@ -302,6 +302,12 @@ class EvalPath:
                 "clses": self.clses[:n], "reg": self.reg[:n], "s1": self.s1[:n], "s2": self.s2[:n]}
 
 
+def set_sm_reserve(n_sms):
+    """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
+    Process-wide; grid sizes are fixed at launch / graph capture time."""
+    check(_lib.lib().rr_set_sm_reserve(int(n_sms)), "rr_set_sm_reserve")
+
+
 # --------------------------------------------------------------------------------- training side
 def render_targets(annos, n_obj, img_h, img_w, scale_factor=4, cls_num=10):
     """to_heatmap + collate padding for a batch: annos [B,max_n,8], n_obj [B] int32 ->

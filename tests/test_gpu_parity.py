@@ -702,3 +702,36 @@ def test_zero_rois_are_a_no_op(ops):
     assert tuple(out.shape) == (5, 32, 3, 3)
     s1, s2 = ops.generate_bbox(torch.zeros(0, 5).cuda(), torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0).cuda())
     assert s1.shape[0] == 0 and s2.shape[0] == 0
+
+
+def test_sm_reserve_and_two_batches_in_flight(ops):
+    """rr_set_sm_reserve only changes the grids of the persistent kernels: same bits.  Two EvalPaths on two streams
+    (the bench's batches-in-flight mode) give what one gives."""
+    B, C, H, W, K = 2, 10, 152, 272, 300
+    x = synth.eval_inputs(B, H, W, K, 77)
+    xd = {k: dev(v) for k, v in x.items()}
+    folded = ops.head_fold({k: v.cuda() for k, v in synth.head_params(77).items()})
+    base = ops.EvalPath(B, C, H, W, K, folded)
+    base.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+    r0 = base.results()
+    L = ops._lib.lib()
+    assert L.rr_set_sm_reserve(-1) != 0 and L.rr_set_sm_reserve(148) != 0
+    try:
+        ops.set_sm_reserve(100)
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        paths = []
+        torch.cuda.synchronize()
+        for st in streams:
+            with torch.cuda.stream(st):
+                p = ops.EvalPath(B, C, H, W, K, folded)
+                for _ in range(3):
+                    p.forward(xd["hm"], xd["wh"], xd["off"], xd["feat"])
+            paths.append(p)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_sm_reserve(0)
+    for p in paths:
+        r = p.results()
+        assert r["n"] == r0["n"]
+        np.testing.assert_array_equal(npy(r["s2"]), npy(r0["s2"]))
+        np.testing.assert_array_equal(npy(r["reg"]), npy(r0["reg"]))
