@@ -41,9 +41,14 @@
 // synchronous for the issuing thread (tools/tc_rate_probe.cu; every instruction between two MMAs shows up in
 // the rate), so descriptors stay in uniform registers and the MMAs go out back to back.  mbarriers connect the
 // roles; there is no block-wide barrier after the prologue.  TMEM (512 columns): conv1 / conv2 accumulator
-// 0-63 / 64-127 by tile parity, conv3 accumulator 128-383, t2 (hi | lo) 384-511.  Measured alternatives that
-// lost: L2 bulk prefetch of the next tile's slots (-6 %), two CTAs per SM with half the resources, two tiles
-// per CTA in lockstep, slot-major x loading, a single epilogue group (E3 then delays t1 of the next tile).
+// 0-63 / 64-127 by tile parity, conv3 accumulator 128-383, t2 (hi | lo) 384-511.
+// What sets the pace now (tools/head_trace.py): the x loaders.  A tile needs 8 K chunks of ~28 KB of slot pieces and
+// one chunk is in flight per SM (48 of the 96 registers a thread may have hold it; shared and tensor memory are
+// full), so a chunk costs one loaded-DRAM latency, ~2.1 us, and a tile 17 us, against 10.3 us of MMAs.  Measured
+// alternatives that lost: L2 bulk prefetch of the next tile's slots (-6 %), two chunks ahead with fewer warps left
+// for the epilogues, slot-major x loading, two CTAs per SM with half the resources, two tiles per CTA in lockstep,
+// a single epilogue group (E3 then delays t1 of the next tile), conv2(k+1) issued before conv3(k) (no change:
+// the tensor core then simply waits for conv1 of the next tile instead of for t2).
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
@@ -239,7 +244,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     __shared__ __align__(8) unsigned long long s_free_b1[kRing1];    // ... consumed (tcgen05.commit)
     __shared__ __align__(8) unsigned long long s_full_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_free_b2[kRing2];
-    __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of ([0] unused) conv2 / conv3 first half / second half are done
+    __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of conv2 [1] / conv3 first half [2] / second half [3] are done ([0] unused)
     __shared__ __align__(8) unsigned long long s_tready;             // t1, then t2 written by the epilogue (two phases per tile)
     __shared__ __align__(8) unsigned long long s_d3free;             // conv3's accumulator has been read out (one phase per tile)
     __shared__ uint32_t s_tmem;
