@@ -42,13 +42,15 @@
 // the rate), so descriptors stay in uniform registers and the MMAs go out back to back.  mbarriers connect the
 // roles; there is no block-wide barrier after the prologue.  TMEM (512 columns): conv1 / conv2 accumulator
 // 0-63 / 64-127 by tile parity, conv3 accumulator 128-383, t2 (hi | lo) 384-511.
-// What sets the pace now (tools/head_trace.py): the x loaders.  A tile needs 8 K chunks of ~28 KB of slot pieces and
-// one chunk is in flight per SM (48 of the 96 registers a thread may have hold it; shared and tensor memory are
-// full), so a chunk costs one loaded-DRAM latency, ~2.1 us, and a tile 17 us, against 10.3 us of MMAs.  Measured
-// alternatives that lost: L2 bulk prefetch of the next tile's slots (-6 %), two chunks ahead with fewer warps left
-// for the epilogues, slot-major x loading, two CTAs per SM with half the resources, two tiles per CTA in lockstep,
-// a single epilogue group (E3 then delays t1 of the next tile), conv2(k+1) issued before conv3(k) (no change:
-// the tensor core then simply waits for conv1 of the next tile instead of for t2).
+// What sets the pace now (tools/head_trace.py, 17.3 us per tile against 10.3 us of MMAs): two chains of similar
+// length.  (1) The conv2/conv3 issuer: ~11.5 us of MMAs (48-54 cycles each with the commits), 3.7 us waiting for
+// t1 / t2 (the epilogues between conv1 -> conv2 -> conv3 of one tile), 0.9 us for weights.  (2) The x loaders:
+// 15.5 us per tile, 1.7 us per K chunk with one chunk in flight per SM (registers, shared and tensor memory are
+// full); without any x load the period is still 15.4 us.  Measured alternatives that lost or changed nothing: L2
+// prefetch of the slots (bulk, a tile ahead: -6 %; per line, 1-7 chunks ahead: +-0), two chunks ahead with fewer
+// warps left for the epilogues, slot-major x loading, two CTAs per SM with half the resources, two tiles per CTA
+// in lockstep, a single epilogue group (E3 then delays t1 of the next tile), conv2(k+1) issued before conv3(k)
+// (the tensor core then waits for conv1 of the next tile instead of for t2).
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
@@ -360,13 +362,14 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
         };
         if (warp == kWarpIssuer1) {
+            long long w_a = 0, w_b1 = 0;                         // trace build: ns blocked on the x stages / on the conv1 weight slot
             for (int j = 0; j < n_my; ++j) {                    // conv1 of tile j -> D12[j & 1]
                 if (j >= 2) bar_wait(&s_d12free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));   // tile j - 2 has left that accumulator
                 const uint32_t d = tmem + kColD12 + 64u * (uint32_t)(j & 1);
 #pragma unroll
                 for (int s1 = 0; s1 < kSteps1; ++s1) {          // stage / ring-1 slot s1 & 1, its use 4 j + (s1 >> 1)
-                    bar_wait(&s_full_a[s1 & 1], (uint32_t)((s1 >> 1) & 1));     // (4 j is even)
-                    bar_wait(&s_full_b1[0], (uint32_t)(s1 & 1));                // its use is 8 j + s1
+                    TC_TIMED(w_a, bar_wait(&s_full_a[s1 & 1], (uint32_t)((s1 >> 1) & 1)));     // (4 j is even)
+                    TC_TIMED(w_b1, bar_wait(&s_full_b1[0], (uint32_t)(s1 & 1)));                // its use is 8 j + s1
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
                         const uint32_t sa = sA + (uint32_t)((s1 & 1) * kTcAStage);
@@ -377,6 +380,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     }
                 }
             }
+#ifdef RR_HEAD_TC_TRACE
+            if (lane == 0) { TC_TRACE_VAL(25, w_a); TC_TRACE_VAL(26, w_b1); }
+#endif
             return;
         }
         uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % 3, its use c2 / 3
@@ -442,6 +448,10 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
         }
         uint32_t cw = 0;                                        // conv1 chunks staged so far (all tiles)
+        long long w_fa = 0;                                     // trace build: ns blocked on a free stage
+#ifdef RR_HEAD_TC_TRACE
+        const long long t_load0 = tc_now();
+#endif
         for (int k = 0; k < n_my; ++k) {
             const int roi0 = ((int)blockIdx.x + k * (int)gridDim.x) * kTcRois;
             const int nroi = min(kTcRois, live - roi0);
@@ -509,7 +519,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 }
                 if (kc + 1 < 8) load_x_chunk(kc + 1);           // in flight while this chunk is split and stored
                 const uint32_t st = cw & 1u, use = cw >> 1;
-                if (use > 0) bar_wait_warp(&s_free_a[st], (use - 1) & 1u);
+                if (use > 0) TC_TIMED(w_fa, bar_wait_warp(&s_free_a[st], (use - 1) & 1u));
                 uint8_t* a_hi = stages + st * kTcAStage;
                 uint8_t* a_lo = a_hi + kTcATile;
 #pragma unroll
@@ -529,6 +539,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             __syncwarp();
             if (lane == 0) bar_arrive(&s_xdone[k & 3]);
         }
+#ifdef RR_HEAD_TC_TRACE
+        if (ltid == 0) { TC_TRACE_VAL(27, w_fa); TC_TRACE_VAL(28, tc_now() - t_load0); }
+#endif
         return;
     }
 

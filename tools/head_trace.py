@@ -79,6 +79,8 @@ def main():
     print("epilogue thread 0, mean us per tile: " + "  ".join("%s %.2f" % (nm, (t[:, 16 + i] / n_my).mean() / 1e3) for i, nm in enumerate(names)))
     print("issuer, mean us per tile blocked: on ring 2 %.2f  on t1/t2 %.2f  in blocking conv1 steps %.2f" % tuple(
         (t[:, i] / n_my).mean() / 1e3 for i in (22, 23, 24)))
+    print("conv1 issuer, mean us per tile blocked: on x stages %.2f  on its weight slot %.2f | x loaders: %.2f us per tile, of which blocked on a free stage %.2f" % (
+        (t[:, 25] / n_my).mean() / 1e3, (t[:, 26] / n_my).mean() / 1e3, (t[:, 28] / n_my).mean() / 1e3, (t[:, 27] / n_my).mean() / 1e3))
     # how many tile pieces the RoIs of this workload are cut into (approximation of roi_prep_kernel's count)
     bx = path.bxyxy[:n_live].float().cpu().numpy()
     ntx = np.floor((bx[:, 3] + 1) / 32) - np.floor(bx[:, 1] / 32) + 1
