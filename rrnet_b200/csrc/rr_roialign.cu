@@ -566,6 +566,14 @@ __device__ __forceinline__ void stage_channels(const float* __restrict__ p, size
         for (int y = 0; y < kTH; ++y) d[cc * kChStride + y * kTW] = relu ? fmaxf(v[cc][y], 0.f) : v[cc][y];
 }
 
+#ifdef RR_TILE_TRACE         // tools/tile_trace.py: per-CTA phase times of roi_tile_kernel (never defined in the shipped build)
+__device__ unsigned long long g_tile_trace[512 * 16];
+__device__ __forceinline__ long long tile_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TILE_LAP(acc) do { const long long n_ = tile_now(); (acc) += n_ - lap_; lap_ = n_; } while (0)
+#else
+#define TILE_LAP(acc) do { } while (0)
+#endif
+
 // Persistent CTAs, two per SM (while one stages its next tile the other one computes).  Per ticket:
 // stage tile + piece tables -> barrier -> every warp evaluates its (piece, bin column) units -> barrier.
 // The next ticket is fetched by one thread during the compute phase.
@@ -585,8 +593,9 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
         const int ngroups = C / kTC;
         const int work = atomicAdd(ctl + kCtlTicket, 1);
         int n_pieces = -1;
-        if (work < ctl[kCtlItems] * ngroups) {
-            const int4 it = items[work / ngroups];
+        const int n_items = ctl[kCtlItems];
+        if (work < n_items * ngroups) {
+            const int4 it = items[work / ngroups];       // (group-major ticket order, x-adjacent tiles back to back: 3 % slower)
             const int t = it.x;
             const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
             const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
@@ -599,6 +608,10 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
     constexpr int kFetchTid = kTileThreads - 32;   // lane 0 of the last warp (it gets the fewest units)
     if (tid == kFetchTid) fetch(s_work[0]);
     __syncthreads();
+#ifdef RR_TILE_TRACE
+    long long lap_ = tile_now(), t_stage = 0, t_bar1 = 0, t_units = 0, t_bar2 = 0, n_tickets = 0, n_units_mine = 0;
+    const long long t_begin = lap_;
+#endif
     for (int buf = 0;; buf ^= 1) {
         const int n_pieces = s_work[buf][2];
         if (n_pieces < 0) break;
@@ -619,7 +632,9 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
             if (rows_valid == kTH) stage_channels<true>(p, plane, d, W, rows_valid, relu);
             else stage_channels<false>(p, plane, d, W, rows_valid, relu);
         }
+        TILE_LAP(t_stage);
         __syncthreads();
+        TILE_LAP(t_bar1);
         if (tid == kFetchTid) fetch(s_work[buf ^ 1]);   // next ticket, overlapped with the compute below
 
         // ---- units: (piece, bin column pw), lane = channel ----
@@ -657,9 +672,23 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
             po[0] = a0;
             po[(size_t)RR_POOL * C] = a1;
             po[(size_t)2 * RR_POOL * C] = a2;
+#ifdef RR_TILE_TRACE
+            ++n_units_mine;
+#endif
         }
+        TILE_LAP(t_units);
         __syncthreads();                           // shared tables free again; s_work[buf ^ 1] is visible
+        TILE_LAP(t_bar2);
+#ifdef RR_TILE_TRACE
+        ++n_tickets;
+#endif
     }
+#ifdef RR_TILE_TRACE
+    if (lane == 0 && (warp == 0 || warp == kTileWarps - 1) && blockIdx.x < 512) {
+        unsigned long long* o = g_tile_trace + blockIdx.x * 16 + (warp ? 8 : 0);
+        o[0] = t_stage; o[1] = t_bar1; o[2] = t_units; o[3] = t_bar2; o[4] = n_tickets; o[5] = n_units_mine; o[6] = tile_now() - t_begin;
+    }
+#endif
 }
 
 // TILE path, step 5: out[n,c,bin] = (sum over the RoI's pieces, fixed order) / count.
@@ -804,3 +833,9 @@ RR_API int rr_roi_align(const float* feat, const float* rois, const int32_t* n_r
     if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, 1, out, ws, (cudaStream_t)stream);
 }
+
+#ifdef RR_TILE_TRACE
+RR_API int rr_debug_tile_trace(unsigned long long* host, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host, rr::g_tile_trace, sizeof(unsigned long long) * (size_t)n_words);
+}
+#endif
