@@ -232,6 +232,23 @@ def aux_kernels(dev, peak):
     out["focal_render_fused_fwd_bwd_c3"] = {"ms": ms, "algorithmic_bytes": fb, "gbs": fb / ms / 1e6,
                                             "frac_of_hbm_peak": fb / ms / 1e6 / peak,
                                             "replaces": "render_targets + focal_fwd_bwd (84 MB of traffic)"}
+    # RegL1Loss of a wh map at config 3 (B=32, 2x128x128, <=150 objects per image): ours vs the reference's formula
+    # (permute copy of the map + gather + l1_loss + autograd) on the same device
+    whm = torch.randn(B, 2, h, w, generator=g).to(dev)
+    tgt = ops.render_targets(annos, n_obj, 512, 512)
+    t_wh, t_ind, t_mask = tgt[1], tgt[2], tgt[4]
+    ms = timed(lambda: ops.regl1_fwd_bwd(whm, t_mask, t_ind, t_wh))
+
+    def regl1_reference():
+        o = whm.detach().requires_grad_(True)
+        pred = o.permute(0, 2, 3, 1).contiguous().view(B, -1, 2).gather(1, t_ind.long().expand(B, t_ind.shape[1], 2))
+        m = t_mask.expand_as(pred).float()
+        (torch.nn.functional.l1_loss(pred * m, t_wh * m, reduction="sum") / (m.sum() + 1e-4)).backward()
+        return o.grad
+    ms_ref = timed(regl1_reference, reps=5)
+    out["regl1_fwd_bwd_c3"] = {"ms": ms, "reference_formula_torch_cuda_ms": ms_ref,
+                               "algorithmic_bytes": int(t_wh.numel() * 4 * 2 + whm.numel() * 4),
+                               "note": "gradient map write (4.2 MB memset) dominates; the reference moves the map 4x more"}
     d = synth.nms_stress_boxes(20000, synth.SEED_C5).to(dev)
     seg = torch.tensor([0, 20000], dtype=torch.int32, device=dev)
     boxes, scores = d[:, :4].contiguous(), d[:, 4].contiguous()

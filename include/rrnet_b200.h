@@ -247,6 +247,19 @@ int rr_focal_render_backward(const float* logits, const float* annos, const int3
                              int img_h, int img_w, int scale_factor, int cls_num,
                              const float* stats, float upstream, float* grad, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RegL1Loss of a regression map (wh or offset): modules/loss/regl1loss.py:9-17 and its backward, without the
+ * NHWC permute copy of the whole map.
+ *   output [B,c,H,W]  mask [B,max_n] (0/1 as float)  ind [B,max_n] (flat y*W+x, as FLOAT like the collate pads it)
+ *   target [B,max_n,c]
+ *   loss [1]  = sum |pred*mask - target*mask| / (c*sum(mask) + 1e-4),  pred[b,k,ch] = output[b,ch,ind[b,k]]
+ *   grad [B,c,H,W] or NULL: d loss / d output * grad_scale (zero-filled, then the <= B*max_n*c entries scattered)
+ * One memset + one launch; the sums are fixed-order doubles (bit-reproducible loss).
+ * ---------------------------------------------------------------------------------------- */
+int rr_regl1_fwd_bwd(const float* output, const float* mask, const float* ind, const float* target,
+                     int B, int c, int H, int W, int max_n, float grad_scale,
+                     float* loss, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ UNITS = {
     "rr_bbox.cu": ["--fmad=false"],
     "rr_render.cu": ["--fmad=false"],
     "rr_focal.cu": [],
+    "rr_regl1.cu": ["--fmad=false"],
 }
 
 BASE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,7 +1,23 @@
-"""modules/loss/regl1loss.py:5-17 -- RegL1Loss (SURVEY 8f "next" row; plain torch, but gathers the K
-points straight from the NCHW map instead of permuting the whole map first)."""
+"""modules/loss/regl1loss.py:5-17 -- RegL1Loss (SURVEY 8f "next" row).  Forward and backward are one CUDA launch
+(`rr_regl1_fwd_bwd`): the <= B*max_n*c predictions are read straight from the NCHW map, no permuted copy of the map,
+no gather / expand / multiply temporaries, and the gradient is written as a zero-filled map with the few entries
+scattered in."""
+import torch
 import torch.nn as nn
-import torch.nn.functional as F
+
+from .... import ops
+
+
+class _RegL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, mask, ind, target):
+        loss, grad = ops.regl1_fwd_bwd(output.detach(), mask, ind, target.detach(), 1.0, want_grad=output.requires_grad)
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.grad * g if ctx.grad is not None else None), None, None, None
 
 
 class RegL1Loss(nn.Module):
@@ -9,10 +25,4 @@ class RegL1Loss(nn.Module):
         super(RegL1Loss, self).__init__()
 
     def forward(self, output, mask, ind, target):
-        b, c, h, w = output.shape
-        idx = ind.long().view(b, 1, -1).expand(b, c, -1)           # ind arrives as float [B,max_n,1]
-        pred = output.reshape(b, c, h * w).gather(2, idx).permute(0, 2, 1)    # [B,max_n,c]
-        mask = mask.float().view(b, -1, 1).expand_as(pred)
-        loss = F.l1_loss(pred * mask, target * mask, reduction="sum")
-        loss = loss / (mask.sum() + 1e-4)
-        return loss
+        return _RegL1Fn.apply(output, mask, ind, target)

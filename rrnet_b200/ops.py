@@ -302,6 +302,25 @@ class EvalPath:
                 "clses": self.clses[:n], "reg": self.reg[:n], "s1": self.s1[:n], "s2": self.s2[:n]}
 
 
+def regl1_fwd_bwd(output, mask, ind, target, grad_scale=1.0, want_grad=True):
+    """RegL1Loss (modules/loss/regl1loss.py:9-17) of a regression map and its gradient in one launch.
+    output [B,c,H,W], mask [B,max_n(,1)], ind [B,max_n(,1)] (float or int), target [B,max_n,c]
+    -> (loss [1], grad [B,c,H,W] * grad_scale or None)."""
+    output = _f32(output, "output", 4)
+    B, c, H, W = output.shape
+    target = _f32(target, "target", 3)
+    max_n = target.shape[1]
+    mask = _f32(mask.reshape(B, max_n).float(), "mask", 2)
+    ind = _f32(ind.reshape(B, max_n).float(), "ind", 2)
+    if target.shape != (B, max_n, c):
+        raise RRNetB200Error("target must be [B,max_n,c]")
+    loss = torch.empty(1, dtype=torch.float32, device=output.device)
+    grad = torch.empty_like(output) if want_grad else None
+    check(_lib.lib().rr_regl1_fwd_bwd(_ptr(output), _ptr(mask), _ptr(ind), _ptr(target), B, c, H, W, max_n,
+                                      float(grad_scale), _ptr(loss), _ptr(grad), _stream()), "rr_regl1_fwd_bwd")
+    return loss, grad
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Process-wide; grid sizes are fixed at launch / graph capture time."""

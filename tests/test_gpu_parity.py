@@ -735,3 +735,29 @@ def test_sm_reserve_and_two_batches_in_flight(ops):
         assert r["n"] == r0["n"]
         np.testing.assert_array_equal(npy(r["s2"]), npy(r0["s2"]))
         np.testing.assert_array_equal(npy(r["reg"]), npy(r0["reg"]))
+
+
+@pytest.mark.parametrize("shape", [(4, 2, 32, 48, 37), (2, 2, 128, 128, 150), (1, 3, 8, 8, 0)])
+def test_regl1_loss_and_gradient(ops, shape):
+    """rr_regl1_fwd_bwd against the reference's formula (modules/loss/regl1loss.py:9-17) in torch on the CPU: the
+    permute + gather + l1_loss(sum) / (mask.sum() + 1e-4) and its autograd gradient; duplicate centre cells,
+    masked-out rows and an empty annotation list included."""
+    B, c, H, W, max_n = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    out = torch.randn(B, c, H, W, generator=g)
+    ind = torch.randint(0, H * W, (B, max_n, 1), generator=g).float()
+    if max_n > 4:
+        ind[:, 1] = ind[:, 0]                                    # two objects in one cell
+    mask = (torch.rand(B, max_n, 1, generator=g) > 0.3)
+    target = torch.rand(B, max_n, c, generator=g) * 30
+    ref_out = out.clone().requires_grad_(True)
+    pred = ref_out.permute(0, 2, 3, 1).contiguous().view(B, -1, c)
+    pred = pred.gather(1, ind.long().expand(B, max_n, c))
+    m = mask.expand_as(pred).float()
+    ref = torch.nn.functional.l1_loss(pred * m, target * m, reduction="sum") / (m.sum() + 1e-4)
+    ref.backward()
+    loss, grad = ops.regl1_fwd_bwd(dev(out), dev(mask.float()), dev(ind), dev(target), grad_scale=1.0)
+    assert abs(float(loss) - float(ref)) <= TOL * max(abs(float(ref)), 1e-6)
+    assert rel_err(npy(grad), ref_out.grad.numpy(), floor=1e-6) < TOL
+    loss2, none = ops.regl1_fwd_bwd(dev(out), dev(mask.float()), dev(ind), dev(target), want_grad=False)
+    assert none is None and float(loss2) == float(loss)          # fixed-order sums: bit-reproducible
