@@ -249,6 +249,18 @@ def aux_kernels(dev, peak):
     out["regl1_fwd_bwd_c3"] = {"ms": ms, "reference_formula_torch_cuda_ms": ms_ref,
                                "algorithmic_bytes": int(t_wh.numel() * 4 * 2 + whm.numel() * 4),
                                "note": "gradient map write (4.2 MB memset) dominates; the reference moves the map 4x more"}
+    # stage-2 regression loss (the per-image loop of criterion) at a config-2-like size: 8 images x 1400 RoIs x 150 GT rows
+    nb, nr, mg = 8, 1400, 150
+    gxy = torch.rand(nb, mg, 2, generator=g) * 1500
+    gtb = torch.cat([gxy, gxy + torch.rand(nb, mg, 2, generator=g) * 100 + 8, torch.zeros(nb, mg, 4)], 2).to(dev)
+    pick = torch.randint(0, mg, (nb, nr), generator=g)
+    bx = torch.gather(gtb[..., :4].cpu(), 1, pick[..., None].expand(nb, nr, 4)) + (torch.rand(nb, nr, 4, generator=g) - 0.5) * 10
+    bxy = torch.cat([torch.arange(nb).float().repeat_interleave(nr)[:, None], bx.reshape(-1, 4) / 4], 1).to(dev)
+    sreg = (torch.randn(nb * nr, 4, generator=g) * 0.5).to(dev)
+    sseg = (torch.arange(nb + 1) * nr).int().to(dev)
+    ms = timed(lambda: ops.stage2_loss(bxy, sseg, sreg, gtb, 4.0))
+    out["stage2_loss_8x1400"] = {"ms": ms, "pairs": nb * nr * mg,
+                                 "replaces": "8 x (box_iou, max, mask-select, generate_bbox_target, smooth_l1) with 2 host syncs per image"}
     d = synth.nms_stress_boxes(20000, synth.SEED_C5).to(dev)
     seg = torch.tensor([0, 20000], dtype=torch.int32, device=dev)
     boxes, scores = d[:, :4].contiguous(), d[:, 4].contiguous()

@@ -260,6 +260,20 @@ int rr_regl1_fwd_bwd(const float* output, const float* mask, const float* ind, c
                      int B, int c, int H, int W, int max_n, float grad_scale,
                      float* loss, float* grad, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stage-2 regression loss of RRNetOperator.criterion (operators/rrnet_operator.py:64-84) and its backward, one CTA
+ * per image: box_iou(bxyxy*scale, gt) -> max over the ground truth -> IoU > 0.5 (no positive in an image: that image
+ * contributes 0) -> generate_bbox_target (:86-102) -> smooth_l1_loss(mean) / B.
+ *   bxyxy [N,5] image-major, seg_offsets [B+1] row ranges of the images, s2_reg [N,4],
+ *   gt_xyxy [B,max_n,gt_stride] (columns 0..3 = x1,y1,x2,y2 in input pixels, AFTER the in-place xywh -> xyxy of :67;
+ *   zero-padded rows take part like in the reference)
+ *   loss_parts [B] (their sum is the loss); grad_reg [N,4] / grad_box [N,4] (d loss / d bxyxy[:,1:5], through the
+ *   targets, which the reference does not detach) or NULL, both times grad_scale.
+ * ---------------------------------------------------------------------------------------- */
+int rr_stage2_loss(const float* bxyxy, const int32_t* seg_offsets, const float* s2_reg, const float* gt_xyxy,
+                   int B, int max_n, int gt_stride, float scale, float grad_scale,
+                   float* loss_parts, float* grad_reg, float* grad_box, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

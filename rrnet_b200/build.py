@@ -32,6 +32,7 @@ UNITS = {
     "rr_render.cu": ["--fmad=false"],
     "rr_focal.cu": [],
     "rr_regl1.cu": ["--fmad=false"],
+    "rr_stage2loss.cu": [],
 }
 
 BASE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -27,6 +27,24 @@ def _box_iou(a, b):
     return inter / (area_a[:, None] + area_b[None, :] - inter)
 
 
+class _Stage2LossFn(torch.autograd.Function):
+    """rr_stage2_loss with the reference's gradients: to s2_reg, and to the predicted boxes through the regression
+    targets (the reference does not detach them, Appendix A.5)."""
+
+    @staticmethod
+    def forward(ctx, s2_reg, bxyxy, gt_annos, bs, scale):
+        img = bxyxy[:, 0].detach().contiguous()
+        seg = torch.searchsorted(img, torch.arange(bs + 1, dtype=img.dtype, device=img.device)).int()
+        parts, g_reg, g_box = ops.stage2_loss(bxyxy.detach(), seg, s2_reg.detach(), gt_annos.detach().float(), scale)
+        ctx.g_reg, ctx.g_box = g_reg, g_box
+        return parts.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        g_bxyxy = torch.cat([torch.zeros_like(ctx.g_box[:, :1]), ctx.g_box * g], dim=1)
+        return ctx.g_reg * g, g_bxyxy, None, None, None
+
+
 class RRNetOperator(object):
     def __init__(self, cfg, model=None, optimizer=None, lr_sch=None, training_loader=None,
                  validation_loader=None, logger=None):
@@ -56,24 +74,9 @@ class RRNetOperator(object):
             wh_loss += self.l1_loss(s1_whs[s], gt_reg_masks, gt_inds, gt_whs) / self.cfg.Model.num_stacks
             off_loss += self.l1_loss(s1_offsets[s], gt_reg_masks, gt_inds, gt_offsets) / self.cfg.Model.num_stacks
 
-        s2_reg_loss = 0
         gt_annos[:, :, 2:4] += gt_annos[:, :, 0:2]                       # in place, as the reference (:67)
-        for b_idx in range(bs):
-            batch_flag = bxyxy[:, 0] == b_idx
-            bbox = bxyxy[batch_flag][:, 1:]
-            gt_anno = gt_annos[b_idx]
-            iou = _box_iou(bbox * self.cfg.Train.scale_factor, gt_anno[:, :4])
-            max_iou, max_idx = torch.max(iou, dim=1)
-            pos_idx = max_iou > 0.5
-            if pos_idx.sum() == 0:
-                pos_idx = torch.zeros_like(max_iou, dtype=torch.bool)
-                pos_idx[0] = True
-                pos_factor = 0
-            else:
-                pos_factor = 1
-            gt_reg = self.generate_bbox_target(bbox[pos_idx, :] * self.cfg.Train.scale_factor,
-                                               gt_anno[max_idx[pos_idx], :4])
-            s2_reg_loss += F.smooth_l1_loss(s2_reg[batch_flag][pos_idx], gt_reg) * pos_factor / bs
+        # :68-84 for every image in one launch (IoU vs the padded ground truth, max, > 0.5, targets, smooth-L1 / bs)
+        s2_reg_loss = _Stage2LossFn.apply(s2_reg, bxyxy, gt_annos, bs, float(self.cfg.Train.scale_factor))
         return hm_loss, wh_loss, off_loss, s2_reg_loss
 
     @staticmethod

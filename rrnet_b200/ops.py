@@ -321,6 +321,28 @@ def regl1_fwd_bwd(output, mask, ind, target, grad_scale=1.0, want_grad=True):
     return loss, grad
 
 
+def stage2_loss(bxyxy, seg_offsets, s2_reg, gt_xyxy, scale=4.0, grad_scale=1.0, want_grad=True):
+    """Stage-2 regression loss of RRNetOperator.criterion (rrnet_operator.py:64-84) for all images in one launch.
+    bxyxy [N,5] image-major, seg_offsets [B+1] int32, s2_reg [N,4], gt_xyxy [B,max_n,>=4] (xyxy, input pixels)
+    -> (loss_parts [B], grad_reg [N,4] or None, grad_box [N,4] or None)."""
+    bxyxy = _f32(bxyxy, "bxyxy", 2)
+    s2_reg = _f32(s2_reg, "s2_reg", 2)
+    gt_xyxy = _f32(gt_xyxy, "gt_xyxy", 3)
+    seg_offsets = _i32(seg_offsets, "seg_offsets")
+    B, max_n, stride = gt_xyxy.shape
+    n = bxyxy.shape[0]
+    if seg_offsets.numel() != B + 1 or s2_reg.shape != (n, 4) or bxyxy.shape[1] != 5:
+        raise RRNetB200Error("stage2_loss: shapes")
+    dev = bxyxy.device
+    parts = torch.zeros(B, dtype=torch.float32, device=dev)
+    g_reg = torch.zeros(n, 4, dtype=torch.float32, device=dev) if want_grad else None
+    g_box = torch.zeros(n, 4, dtype=torch.float32, device=dev) if want_grad else None
+    check(_lib.lib().rr_stage2_loss(_ptr(bxyxy), _ptr(seg_offsets), _ptr(s2_reg), _ptr(gt_xyxy), B, max_n, stride,
+                                    float(scale), float(grad_scale), _ptr(parts), _ptr(g_reg), _ptr(g_box), _stream()),
+          "rr_stage2_loss")
+    return parts, g_reg, g_box
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Process-wide; grid sizes are fixed at launch / graph capture time."""

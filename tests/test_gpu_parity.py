@@ -761,3 +761,69 @@ def test_regl1_loss_and_gradient(ops, shape):
     assert rel_err(npy(grad), ref_out.grad.numpy(), floor=1e-6) < TOL
     loss2, none = ops.regl1_fwd_bwd(dev(out), dev(mask.float()), dev(ind), dev(target), want_grad=False)
     assert none is None and float(loss2) == float(loss)          # fixed-order sums: bit-reproducible
+
+
+def test_stage2_loss_and_gradients(ops):
+    """rr_stage2_loss against the reference's per-image loop (operators/rrnet_operator.py:64-102) in torch on the CPU,
+    with autograd for d/d s2_reg and d/d bxyxy (the targets are not detached).  Image 2 has no positive (factor 0),
+    image 3 no RoI-GT overlap at all; padded ground-truth rows are zero boxes."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(9)
+    B, max_n, scale = 4, 12, 4.0
+    gt = torch.zeros(B, max_n, 8)
+    rows, regs = [], []
+    for b in range(B):
+        n_gt = [7, 12, 5, 3][b]
+        xy = torch.rand(n_gt, 2, generator=g) * 300 + 20
+        wh = torch.rand(n_gt, 2, generator=g) * 60 + 12
+        gt[b, :n_gt, :2] = xy
+        gt[b, :n_gt, 2:4] = xy + wh                                       # already xyxy (after :67)
+        n = [40, 33, 25, 18][b]
+        pick = torch.randint(0, n_gt, (n,), generator=g)
+        jit = (torch.rand(n, 4, generator=g) - 0.5) * (8 if b < 2 else 400)      # images 2, 3: far off -> no positives
+        box = (torch.cat([xy[pick], xy[pick] + wh[pick]], 1) + jit) / scale
+        if b == 3:
+            box = box + 2000.0
+        box[:, 2:] = torch.maximum(box[:, 2:], box[:, :2])
+        rows.append(torch.cat([torch.full((n, 1), float(b)), box], 1))
+        regs.append(torch.randn(n, 4, generator=g) * 0.7)
+    bxyxy = torch.cat(rows)
+    s2_reg = torch.cat(regs)
+    # reference loop
+    rb = bxyxy.clone().requires_grad_(True)
+    rr = s2_reg.clone().requires_grad_(True)
+    loss = 0
+    n_pos_seen = []
+    for b in range(B):
+        flag = rb[:, 0] == b
+        bbox = rb[flag][:, 1:]
+        a, bb = bbox * scale, gt[b, :, :4]
+        area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+        area_b = (bb[:, 2] - bb[:, 0]) * (bb[:, 3] - bb[:, 1])
+        whi = (torch.min(a[:, None, 2:], bb[None, :, 2:]) - torch.max(a[:, None, :2], bb[None, :, :2])).clamp(min=0)
+        inter = whi[..., 0] * whi[..., 1]
+        iou = inter / (area_a[:, None] + area_b[None, :] - inter)
+        max_iou, max_idx = torch.max(iou, dim=1)
+        pos = max_iou > 0.5
+        n_pos_seen.append(int(pos.sum()))
+        if pos.sum() == 0:
+            pos = torch.zeros_like(pos)
+            pos[0] = True
+            factor = 0
+        else:
+            factor = 1
+        ex, gr = bbox[pos] * scale, bb[max_idx[pos]]
+        ew, eh = ex[:, 2] - ex[:, 0] + 1.0, ex[:, 3] - ex[:, 1] + 1.0
+        ecx, ecy = ex[:, 0] + 0.5 * ew, ex[:, 1] + 0.5 * eh
+        gw, gh = gr[:, 2] - gr[:, 0] + 1.0, gr[:, 3] - gr[:, 1] + 1.0
+        gcx, gcy = gr[:, 0] + 0.5 * gw, gr[:, 1] + 0.5 * gh
+        tgt = torch.stack(((gcx - ecx) / ew, (gcy - ecy) / eh, torch.log(gw / ew), torch.log(gh / eh)), 1)
+        loss = loss + F.smooth_l1_loss(rr[flag][pos], tgt) * factor / B
+    loss.backward()
+    assert n_pos_seen[0] > 0 and n_pos_seen[1] > 0 and n_pos_seen[2] == 0 and n_pos_seen[3] == 0
+    seg = torch.tensor([0, 40, 73, 98, 116], dtype=torch.int32)
+    parts, g_reg, g_box = ops.stage2_loss(dev(bxyxy), dev(seg), dev(s2_reg), dev(gt), scale)
+    assert abs(float(parts.sum()) - float(loss)) <= TOL * abs(float(loss))
+    assert float(parts[2]) == 0.0 and float(parts[3]) == 0.0
+    assert rel_err(npy(g_reg), rr.grad.numpy(), floor=1e-4) < TOL
+    assert rel_err(npy(g_box), rb.grad.numpy()[:, 1:], floor=1e-4) < TOL
