@@ -315,10 +315,9 @@ def run_product(args):
     d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     folded = ops.head_fold({k: v.to(dev) for k, v in hp.items()})
     path = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo, head_algo=args.head_algo)
-    gathered = gathered_cnt = None
+    gathered = None
     if world > 1:
-        gathered = torch.empty(world * B * K, 6, dtype=torch.float32, device=dev)
-        gathered_cnt = torch.empty(world * (B + 1), dtype=torch.int32, device=dev)
+        gathered = torch.empty(world * path.result_blob.numel(), dtype=torch.float32, device=dev)
 
     graph = None if args.no_graph else path.capture(d["hm"], d["wh"], d["off"], d["feat"])
 
@@ -336,7 +335,7 @@ def run_product(args):
             with torch.cuda.stream(st):
                 pp = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo, head_algo=args.head_algo)
                 gg = pp.capture(d["hm"], d["wh"], d["off"], d["feat"])
-            gb = (torch.empty_like(gathered), torch.empty_like(gathered_cnt)) if world > 1 else None
+            gb = torch.empty_like(gathered) if world > 1 else None
             pipes.append((st, pp, gg, gb))
         ops.set_sm_reserve(0)
         torch.cuda.synchronize()
@@ -346,9 +345,8 @@ def run_product(args):
             graph.replay()                 # the same launches, submitted as one CUDA graph
         else:
             path.forward(d["hm"], d["wh"], d["off"], d["feat"], stage_events=events)
-        if world > 1:            # all-gather of detections for mAP (padded rows + counts)
-            dist.all_gather_into_tensor(gathered, path.s2)
-            dist.all_gather_into_tensor(gathered_cnt, path.counts)
+        if world > 1:            # all-gather of detections for mAP (padded rows + per-image counts, one buffer)
+            dist.all_gather_into_tensor(gathered, path.result_blob)
 
     def run_steps(n):
         """n steps on the current stream, or round-robin over the pipes (fork / join around them)."""
@@ -364,8 +362,7 @@ def run_product(args):
             with torch.cuda.stream(st):
                 gg.replay()
                 if world > 1:
-                    dist.all_gather_into_tensor(gb[0], pp.s2)
-                    dist.all_gather_into_tensor(gb[1], pp.counts)
+                    dist.all_gather_into_tensor(gb, pp.result_blob)
         for st, _, _, _ in pipes:
             main_stream.wait_stream(st)
 
@@ -460,8 +457,7 @@ def run_product(args):
             main_stream.wait_event(h2d_done[b])
             path.forward(bufs[b]["hm"], bufs[b]["wh"], bufs[b]["off"], bufs[b]["feat"])
             if world > 1:
-                dist.all_gather_into_tensor(gathered, path.s2)
-                dist.all_gather_into_tensor(gathered_cnt, path.counts)
+                dist.all_gather_into_tensor(gathered, path.result_blob)
             free[b].record(main_stream)
             res_host.copy_(path.s2, non_blocking=True)
             cnt_host.copy_(path.counts, non_blocking=True)

@@ -3,7 +3,8 @@
 The reference shards validation images with a DistributedSampler and "gathers" detections through
 result files on a shared disk (operators/rrnet_operator.py:277-278, scripts/RRNet/eval.py:13-18).
 Here every rank runs the post-backbone path on a contiguous range of images and the padded detections
-[imgs,K,6] + per-image counts are exchanged with ONE all-gather each (NCCL over NVLink on GPUs; the
+[imgs,K,6] + per-image counts are exchanged with ONE all-gather each - or one in total through
+`all_gather_result_blobs` - (NCCL over NVLink on GPUs; the
 same code runs on gloo/CPU tensors in the tests).  No kernel of the path is followed by a collective,
 so there is nothing to fuse a collective into."""
 import torch
@@ -38,6 +39,21 @@ def all_gather_detections(padded, counts, group=None):
     dist.all_gather_into_tensor(all_p, padded.contiguous(), group=group)
     dist.all_gather_into_tensor(all_c, counts.contiguous(), group=group)
     return all_p, all_c
+
+
+def all_gather_result_blobs(blob, n_rows, n_images, group=None):
+    """ops.EvalPath.result_blob of every rank with ONE all-gather (it holds the final rows [n_rows,6] followed by the
+    int32 per-image counts [n_images + 1], last = total rows, as raw bits in the same fp32 buffer)
+    -> (rows [world,n_rows,6], counts [world,n_images+1] int32), rank-major."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        out = blob.reshape(1, -1)
+    else:
+        out = blob.new_empty(world, blob.numel())
+        dist.all_gather_into_tensor(out.view(-1), blob.contiguous(), group=group)
+    rows = out[:, : n_rows * 6].reshape(world, n_rows, 6)
+    counts = out[:, n_rows * 6: n_rows * 6 + n_images + 1].contiguous().view(torch.int32)
+    return rows, counts
 
 
 def unpack_detections(all_padded, all_counts, n_images):

@@ -257,10 +257,12 @@ class EvalPath:
         self.bxyxy = torch.empty(n, 5, **f32)
         self.scores = torch.empty(n, **f32)
         self.clses = torch.empty(n, **f32)
-        self.counts = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         self.reg = torch.empty(n, 4, **f32)
         self.s1 = torch.empty(n, 6, **f32)
-        self.s2 = torch.empty(n, 6, **f32)
+        # the final rows and the per-image counts share one buffer: a multi-GPU run exchanges them with ONE all-gather
+        self.result_blob = torch.zeros(n * 6 + B + 1, **f32)
+        self.s2 = self.result_blob[: n * 6].view(n, 6)
+        self.counts = self.result_blob[n * 6:].view(torch.int32)
         self.roi_feat = torch.empty(n, feat_ch, 3, 3, **f32) if keep_roi_feat else None
         self.ws = _ws(L.rr_eval_workspace_bytes(B, C, H, W, K, feat_ch), dev)
 

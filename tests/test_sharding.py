@@ -60,6 +60,17 @@ def _worker(rank, world, port, n_images, K, out):
                 ok &= int(all_c[slot]) == c
                 ok &= bool((all_p[slot, :c, 0] == i).all()) and bool((all_p[slot, :c, 1] == torch.arange(c)).all())
                 ok &= bool((all_p[slot, c:] == 0).all())
+        # the one-buffer form (ops.EvalPath.result_blob): rows then the int32 counts as raw bits
+        n_rows = per * K
+        blob = torch.zeros(n_rows * 6 + per + 1)
+        blob[: n_rows * 6] = padded.reshape(-1)
+        cview = blob[n_rows * 6:].view(torch.int32)
+        cview[:per] = cnt
+        cview[per] = int(cnt.sum())
+        rows_all, counts_all = sharding.all_gather_result_blobs(blob, n_rows, per)
+        ok &= tuple(rows_all.shape) == (world, n_rows, 6) and tuple(counts_all.shape) == (world, per + 1)
+        ok &= bool(torch.equal(rows_all.reshape(world * per, K, 6), all_p))
+        ok &= bool(torch.equal(counts_all[:, :per].reshape(-1), all_c))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
