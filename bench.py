@@ -163,7 +163,7 @@ def cuda_reference(x_dev, hp_dev, K, reps=5):
         torch.backends.cudnn.allow_tf32 = tf32
 
 
-def aux_kernels(dev, peak):
+def aux_kernels(dev, peak, feat=None, rois=None):
     """The other rows of the scope table, timed alone (CUDA events, L2 flushed between repetitions):
     training side at config 3 (B=32, 10x128x128) and the config-5 NMS stress (20k boxes, one class)."""
     from rrnet_b200 import ops, synth
@@ -261,6 +261,42 @@ def aux_kernels(dev, peak):
     ms = timed(lambda: ops.stage2_loss(bxy, sseg, sreg, gtb, 4.0))
     out["stage2_loss_8x1400"] = {"ms": ms, "pairs": nb * nr * mg,
                                  "replaces": "8 x (box_iou, max, mask-select, generate_bbox_target, smooth_l1) with 2 host syncs per image"}
+    # RoIAlign backward at the bench workload (config 2 features, the step's own RoIs): gather kernel vs autograd
+    # through torchvision.ops.roi_align(relu(feat)) on the same GPU (atomic scatter + ReLU backward)
+    if feat is not None and rois is not None and rois.shape[0] > 0:
+        gout = torch.randn(rois.shape[0], feat.shape[1], 3, 3, generator=g).to(dev)
+        rws = torch.empty(ops._lib.lib().rr_roi_align_workspace_bytes(rois.shape[0], *feat.shape), dtype=torch.uint8, device=dev)
+        ms = timed(lambda: ops.roi_align_backward(feat, rois, gout, ws=rws), reps=3)
+        entry = {"ms": ms, "rois": int(rois.shape[0]), "algorithmic_bytes": int(2 * feat.numel() * 4 + gout.numel() * 4),
+                 "gbs": (2 * feat.numel() * 4 + gout.numel() * 4) / ms / 1e6}
+        try:
+            import torchvision
+
+            def tv_backward():
+                f = feat.detach().requires_grad_(True)
+                o = torchvision.ops.roi_align(torch.relu(f), rois, (3, 3))
+                return torch.autograd.grad(o, f, gout)[0]
+            tv_backward()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                tv_backward()
+            b.record(); b.synchronize()
+            entry["torchvision_cuda_fwd_bwd_ms"] = a.elapsed_time(b) / 3
+            f = feat.detach().requires_grad_(True)
+            tv_out = torchvision.ops.roi_align(torch.relu(f), rois, (3, 3))
+            torch.cuda.synchronize()
+            a.record()
+            torch.autograd.grad(tv_out, f, gout)
+            b.record(); b.synchronize()
+            entry["torchvision_cuda_bwd_ms"] = a.elapsed_time(b)
+            del f, tv_out
+        except Exception as e:
+            entry["torchvision_cuda"] = "unavailable: " + repr(e)[:120]
+        out["roi_align_backward_c2"] = entry
+        del gout, rws
+        torch.cuda.empty_cache()
     d = synth.nms_stress_boxes(20000, synth.SEED_C5).to(dev)
     seg = torch.tensor([0, 20000], dtype=torch.int32, device=dev)
     boxes, scores = d[:, :4].contiguous(), d[:, 4].contiguous()
@@ -522,7 +558,7 @@ def run_product(args):
                                 "device-resident batch, wall clock incl. its host syncs"}
         except Exception as e:                                       # torchvision CUDA ops missing on the box
             ref_cuda = {"unavailable": repr(e)[:200]}
-        aux = aux_kernels(dev, peak)
+        aux = aux_kernels(dev, peak, feat=d["feat"], rois=r["bxyxy"])
 
     # ---- CPU baseline beside it (rank 0, bounded sample) ----
     cpu_info = None

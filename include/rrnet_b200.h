@@ -248,6 +248,16 @@ int rr_focal_render_backward(const float* logits, const float* annos, const int3
                              const float* stats, float upstream, float* grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Backward of rr_roi_align (training; SURVEY 8b `_backward`): grad_feat [B,C,H,W] = d loss / d feat of
+ * roi_align(relu(feat), rois, (3,3)) given grad_out [n_cap,C,3,3].  Same arguments, algo and workspace size as the
+ * forward (the RoI bookkeeping is recomputed).  Tile path: a gather, every element written once with a plain store (no
+ * atomics on the data; summation order = piece list order); direct-path RoIs (windows over 64 pixels) are added with atomicAdd.  grad_feat is fully written.
+ * ---------------------------------------------------------------------------------------- */
+int rr_roi_align_backward(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
+                          int B, int C, int H, int W, int relu, int algo, const float* grad_out, float* grad_feat,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RegL1Loss of a regression map (wh or offset): modules/loss/regl1loss.py:9-17 and its backward, without the
  * NHWC permute copy of the whole map.
  *   output [B,c,H,W]  mask [B,max_n] (0/1 as float)  ind [B,max_n] (flat y*W+x, as FLOAT like the collate pads it)

@@ -30,6 +30,7 @@ SIGNATURES = {
     "rr_soft_nms_batched": (c_int, [P, P, c_int, c_int, c_float, c_float, c_float, c_int, P, P, P, c_size_t, P]),
     "rr_roi_align_workspace_bytes": (c_size_t, [c_int] * 5),
     "rr_roi_align": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
+    "rr_roi_align_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "rr_head_folded_floats": (c_size_t, []),
     "rr_head_fold": (c_int, [P] * 9 + [P]),
     "rr_head_forward": (c_int, [P, P, c_int, P, c_int, P, P]),

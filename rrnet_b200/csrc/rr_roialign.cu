@@ -814,6 +814,205 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
     return rc;
 }
 
+// --------------------------------------------------------------------------------------------
+// BACKWARD (training): d loss / d feat of roi_align(relu(feat)) from d loss / d out [n,C,3,3].
+// The transpose of the tile path, as a GATHER: a CTA owns one (tile, 32-channel group), warp y owns row y of the
+// tile and keeps that row's 32 pixels of its lane's channel in registers; it walks over the tile's pieces in list
+// order and adds  sum_pw wx[pw][x] * (sum_ph wy[ph][y] * G[c,ph,pw] / count)  for the pieces that cover its row.
+// Every output element is written exactly once with a plain store, no atomics on the data (torchvision's backward
+// scatters 4 atomicAdds per sample); the pieces of a tile are summed in the fill kernel's list order, which is not
+// fixed from run to run, so the last bits may differ between runs, like the reference's.  The ReLU mask is applied in the coalesced write-out.  RoIs of the direct path
+// (windows over 64 pixels) are added afterwards by a per-RoI kernel with atomicAdd.
+// --------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 32 * kTH;                 // 24 warps = 24 tile rows
+constexpr int kBwdWxFloats = kChunk * RR_POOL * kTW;  // weights placed at tile columns
+constexpr int kBwdGFloats = kChunk * kTC * RR_POOL * RR_POOL;
+constexpr int kBwdSmemFloats = kChunk * 2 * 4 + kChunk * kTH * 4 + kBwdWxFloats + kBwdGFloats + kChunk + kTH * kTC * 33;
+constexpr int kBwdSmem = kBwdSmemFloats * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ grad_out, const int4* __restrict__ list,
+                    const float* __restrict__ list_wx, const float4* __restrict__ list_wy, const float* __restrict__ cnt_arr,
+                    const int* __restrict__ tile_off, const int* __restrict__ tile_fill,
+                    int C, int H, int W, int relu, TileDims td, float* __restrict__ grad_feat) {
+    extern __shared__ float s_bwd[];
+    int4* s_desc = reinterpret_cast<int4*>(s_bwd);
+    float4* s_wy = reinterpret_cast<float4*>(s_desc + 2 * kChunk);
+    float* s_wx = reinterpret_cast<float*>(s_wy + kChunk * kTH);      // [piece][pw][tile column]
+    float* s_g = s_wx + kBwdWxFloats;                                // [piece][channel][9]
+    float* s_inv = s_g + kBwdGFloats;
+    float* s_t = s_inv + kChunk;                                     // [row][channel][33]
+    const int tid = threadIdx.x, lane = tid & 31, y = tid >> 5;
+    const int ngroups = C / kTC;
+    const int t = blockIdx.x / ngroups, g = blockIdx.x - t * ngroups;
+    const int n_p = tile_fill[t];
+    if (n_p == 0) return;                                            // the map was zero-filled
+    const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
+    const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
+    const int px0 = tx * kTW, py0 = ty * kTH;
+    float acc[kTW];
+#pragma unroll
+    for (int x = 0; x < kTW; ++x) acc[x] = 0.f;
+
+    for (int base = 0; base < n_p; base += kChunk) {
+        const int cnt = min(kChunk, n_p - base), list0 = tile_off[t] + base;
+        __syncthreads();                                             // previous chunk's tables are no longer read
+        if (tid < 2 * cnt) s_desc[tid] = __ldg(list + 2 * (size_t)list0 + tid);
+        for (int i = tid; i < cnt * kTH; i += kBwdThreads) s_wy[i] = __ldg(list_wy + (size_t)list0 * kTH + i);
+        for (int i = tid; i < cnt * RR_POOL * kTW; i += kBwdThreads) s_wx[i] = 0.f;
+        __syncthreads();
+        for (int i = tid; i < cnt * RR_POOL * kTW; i += kBwdThreads) {   // list_wx[pos][pw][i] belongs to tile column c0 + i
+            const int p = i / (RR_POOL * kTW), r = i - p * (RR_POOL * kTW), pw = r / kTW, k = r - pw * kTW;
+            const int4 d0 = s_desc[2 * p], d1 = s_desc[2 * p + 1];
+            const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
+            const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
+            if (k < ncols) s_wx[(p * RR_POOL + pw) * kTW + c0 + k] = __ldg(list_wx + ((size_t)(list0 + p) * RR_POOL + pw) * kTW + k);
+        }
+        for (int i = tid; i < cnt * kTC * 9; i += kBwdThreads) {         // 288 contiguous floats per (RoI, channel group)
+            const int p = i / (kTC * 9), e = i - p * (kTC * 9);
+            const int roi = s_desc[2 * p].x;
+            s_g[i] = __ldg(grad_out + ((size_t)roi * C + (size_t)g * kTC) * 9 + e);
+        }
+        if (tid < cnt) s_inv[tid] = 1.0f / __ldg(cnt_arr + s_desc[2 * tid].x);
+        __syncthreads();
+
+        for (int p = 0; p < cnt; ++p) {
+            const int4 d0 = s_desc[2 * p], d1 = s_desc[2 * p + 1];
+            const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
+            if ((unsigned)(y - r0) >= (unsigned)nrows) continue;     // warp-uniform: this piece does not cover row y
+            const float4 wy = s_wy[p * kTH + (y - r0)];
+            const float inv = s_inv[p];
+            const float* gp = s_g + (p * kTC + lane) * 9;
+            float s3[RR_POOL];
+#pragma unroll
+            for (int pw = 0; pw < RR_POOL; ++pw)
+                s3[pw] = fmaf(wy.x, gp[pw], fmaf(wy.y, gp[3 + pw], wy.z * gp[6 + pw])) * inv;
+            int cmin = kTW, cmax = -1;
+            const int colsv[RR_POOL] = {d0.w, d1.x, d1.y};
+#pragma unroll
+            for (int pw = 0; pw < RR_POOL; ++pw) {
+                const int c0 = colsv[pw] & 0xff, nc = (colsv[pw] >> 8) & 0xff;
+                if (nc > 0) { cmin = min(cmin, c0); cmax = max(cmax, c0 + nc - 1); }
+            }
+            const float4* w0 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 0) * kTW);
+            const float4* w1 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 1) * kTW);
+            const float4* w2 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 2) * kTW);
+#pragma unroll
+            for (int q = 0; q < kTW / 4; ++q) {
+                if (4 * q + 3 >= cmin && 4 * q <= cmax) {            // warp-uniform
+                    const float4 a = w0[q], b = w1[q], c = w2[q];
+                    acc[4 * q + 0] = fmaf(a.x, s3[0], fmaf(b.x, s3[1], fmaf(c.x, s3[2], acc[4 * q + 0])));
+                    acc[4 * q + 1] = fmaf(a.y, s3[0], fmaf(b.y, s3[1], fmaf(c.y, s3[2], acc[4 * q + 1])));
+                    acc[4 * q + 2] = fmaf(a.z, s3[0], fmaf(b.z, s3[1], fmaf(c.z, s3[2], acc[4 * q + 2])));
+                    acc[4 * q + 3] = fmaf(a.w, s3[0], fmaf(b.w, s3[1], fmaf(c.w, s3[2], acc[4 * q + 3])));
+                }
+            }
+        }
+    }
+    // ---- write-out: transpose the warp's [channel][x] block through shared memory, 128-byte rows, ReLU mask ----
+    float* st = s_t + (size_t)y * kTC * 33;
+#pragma unroll
+    for (int x = 0; x < kTW; ++x) st[lane * 33 + x] = acc[x];
+    __syncwarp();
+    const int gy = py0 + y, gx = px0 + lane;
+    if (gy < H && gx < W) {
+        for (int c = 0; c < kTC; ++c) {
+            const size_t idx = (((size_t)img * C + (size_t)g * kTC + c) * H + gy) * W + gx;
+            float v = st[c * 33 + lane];
+            if (relu && !(__ldg(feat + idx) > 0.f)) v = 0.f;
+            grad_feat[idx] = v;
+        }
+    }
+}
+
+// direct-path RoIs: one CTA per RoI, one atomicAdd per (channel, window pixel)
+__global__ void __launch_bounds__(kRoiThreads)
+roi_direct_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ rois, const float* __restrict__ grad_out,
+                      const int* __restrict__ direct_list, const int* __restrict__ ctl,
+                      int B, int C, int H, int W, int relu, float* __restrict__ grad_feat) {
+    __shared__ float s_ax[RR_POOL][kMaxWin];
+    __shared__ float s_ay[RR_POOL][kMaxWin];
+    __shared__ AxisGeom s_g[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int n_direct = ctl[kCtlDirect];
+    for (int i = blockIdx.x; i < n_direct; i += gridDim.x) {
+        const int n = direct_list[i];
+        const float* r = rois + (size_t)n * 5;
+        const int bi = (int)r[0];
+        __syncthreads();
+        if (bi < 0 || bi >= B) continue;
+        if (tid == 0) s_g[0] = axis_geom(r[1], r[3], W);
+        if (tid == 32) s_g[1] = axis_geom(r[2], r[4], H);
+        __syncthreads();
+        const AxisGeom gx = s_g[0], gy = s_g[1];
+        if (gx.n == 0 || gy.n == 0) continue;
+        const float inv = 1.0f / (float)max(gx.grid * gy.grid, 1);
+        const bool fits = gx.n <= kMaxWin && gy.n <= kMaxWin;
+        if (fits) {
+            for (int t = tid; t < RR_POOL * gx.n; t += blockDim.x) { const int p = t / gx.n, k = t - p * gx.n; s_ax[p][k] = axis_weight(gx, p, k, W); }
+            for (int t = tid; t < RR_POOL * gy.n; t += blockDim.x) { const int p = t / gy.n, k = t - p * gy.n; s_ay[p][k] = axis_weight(gy, p, k, H); }
+        }
+        __syncthreads();
+        for (int c = warp; c < C; c += nwarp) {
+            const float* gp = grad_out + ((size_t)n * C + c) * 9;
+            float G[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) G[k] = __ldg(gp + k) * inv;
+            const size_t plane = (((size_t)bi * C + c) * H + gy.lo) * W + gx.lo;
+            for (int yy = 0; yy < gy.n; ++yy) {
+                const float a0 = fits ? s_ay[0][yy] : axis_weight(gy, 0, yy, H);
+                const float a1 = fits ? s_ay[1][yy] : axis_weight(gy, 1, yy, H);
+                const float a2 = fits ? s_ay[2][yy] : axis_weight(gy, 2, yy, H);
+                const float t0 = a0 * G[0] + a1 * G[3] + a2 * G[6];
+                const float t1 = a0 * G[1] + a1 * G[4] + a2 * G[7];
+                const float t2 = a0 * G[2] + a1 * G[5] + a2 * G[8];
+                for (int x = lane; x < gx.n; x += 32) {
+                    const float b0 = fits ? s_ax[0][x] : axis_weight(gx, 0, x, W);
+                    const float b1 = fits ? s_ax[1][x] : axis_weight(gx, 1, x, W);
+                    const float b2 = fits ? s_ax[2][x] : axis_weight(gx, 2, x, W);
+                    const float v = b0 * t0 + b1 * t1 + b2 * t2;
+                    const size_t idx = plane + (size_t)yy * W + x;
+                    if (v != 0.f && (!relu || __ldg(feat + idx) > 0.f)) atomicAdd(grad_feat + idx, v);
+                }
+            }
+        }
+    }
+}
+
+int roi_align_backward_launch(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
+                              int B, int C, int H, int W, int relu, int algo, const float* grad_out, float* grad_feat,
+                              void* ws, cudaStream_t st) {
+    int rc = 0;
+    RoiWs w = carve_roi(ws, n_cap, B, C, H, W);
+    RR_CUDA(cudaMemsetAsync(w.zeroed, 0, w.zeroed_bytes, st), rc);
+    RR_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st), rc);
+    if (rc) return rc;
+    const int force_direct = algo == 1;
+    roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
+                                                    w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
+    RR_LAUNCHED(rc);
+    roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
+                                                w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
+    RR_LAUNCHED(rc);
+    if (!force_direct && C % kTC == 0) {
+        roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
+                                                        w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
+        RR_LAUNCHED(rc);
+        static bool attr_set = false;
+        if (!attr_set) {
+            RR_CUDA(cudaFuncSetAttribute(roi_tile_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), rc);
+            attr_set = true;
+        }
+        roi_tile_bwd_kernel<<<w.n_tiles * (C / kTC), kBwdThreads, kBwdSmem, st>>>(feat, grad_out, w.list, w.list_wx, w.list_wy,
+                                                                              w.cnt, w.tile_off, w.tile_fill, C, H, W, relu,
+                                                                              w.td, grad_feat);
+        RR_LAUNCHED(rc);
+    }
+    roi_direct_bwd_kernel<<<8 * kSMs, kRoiThreads, 0, st>>>(feat, rois, grad_out, w.direct_list, w.ctl, B, C, H, W, relu, grad_feat);
+    RR_LAUNCHED(rc);
+    return rc;
+}
+
 }  // namespace rr
 
 using namespace rr;
@@ -832,6 +1031,17 @@ RR_API int rr_roi_align(const float* feat, const float* rois, const int32_t* n_r
     if (C > 1024) return RR_E_RANGE;                 // roi_combine stages one RoI (C*9 floats) in shared memory
     if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, 1, out, ws, (cudaStream_t)stream);
+}
+
+RR_API int rr_roi_align_backward(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
+                                 int B, int C, int H, int W, int relu, int algo, const float* grad_out, float* grad_feat,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (!grad_feat || B <= 0 || C <= 0 || H <= 0 || W <= 0 || n_cap < 0 || algo < 0 || algo > 1) return RR_E_BADARG;
+    if (n_cap == 0) return (int)cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, (cudaStream_t)stream);
+    if (!feat || !rois || !grad_out || !ws) return RR_E_BADARG;
+    if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    return roi_align_backward_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, grad_out, grad_feat, ws,
+                                     (cudaStream_t)stream);
 }
 
 #ifdef RR_TILE_TRACE

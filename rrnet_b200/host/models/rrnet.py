@@ -156,9 +156,8 @@ class RRNet(nn.Module):
 
 
 class _RoIAlignReLU(torch.autograd.Function):
-    """roi_align(relu(feat), rois, (3,3)) with the fused kernel; the backward (training only) scatters
-    through torchvision's roi_align backward on relu(feat) -- RoIAlign backward is outside this round's
-    kernels (SURVEY 8b lists it as part of rr_roi_align's `_backward`, still to come)."""
+    """roi_align(relu(feat), rois, (3,3)) with the fused kernel; the backward (training only) is the tile-centric
+    gather kernel `rr_roi_align_backward`: ReLU mask included, no atomics on the tile path."""
 
     @staticmethod
     def forward(ctx, feat, rois):
@@ -167,13 +166,8 @@ class _RoIAlignReLU(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        import torchvision
         feat, rois = ctx.saved_tensors
-        with torch.enable_grad():
-            f = feat.detach().requires_grad_(True)
-            out = torchvision.ops.roi_align(torch.relu(f), rois, (3, 3))
-            (g,) = torch.autograd.grad(out, f, grad_out)
-        return g, None
+        return ops.roi_align_backward(feat.detach(), rois.detach(), grad_out.contiguous(), relu=True), None
 
 
 class _DecodeFn(torch.autograd.Function):

@@ -207,6 +207,27 @@ def head_params_from_module(head_detector):
     }
 
 
+def roi_align_backward(feat, rois, grad_out, relu=True, algo=0, n_dev=None, ws=None):
+    """d loss / d feat of roi_align(relu(feat), rois, (3,3)): feat [B,C,H,W], rois [n,5], grad_out [n,C,3,3]
+    -> grad_feat [B,C,H,W] (a gather on the tile path; atomics only for direct-path RoIs)."""
+    feat = _f32(feat, "feat", 4)
+    rois = _f32(rois, "rois", 2)
+    grad_out = _f32(grad_out, "grad_out", 4)
+    B, C, H, W = feat.shape
+    n = rois.shape[0]
+    if grad_out.shape != (n, C, 3, 3) or (n and rois.shape[1] != 5):
+        raise RRNetB200Error("roi_align_backward: grad_out must be [n,C,3,3], rois [n,5]")
+    grad = torch.empty_like(feat)
+    L = _lib.lib()
+    if ws is None:
+        ws = _ws(L.rr_roi_align_workspace_bytes(max(n, 1), B, C, H, W), feat.device)
+    if n_dev is not None:
+        n_dev = _i32(n_dev, "n_dev")
+    check(L.rr_roi_align_backward(_ptr(feat), _ptr(rois), _ptr(n_dev), n, B, C, H, W, int(bool(relu)), int(algo),
+                                  _ptr(grad_out), _ptr(grad), _ptr(ws), ws.numel(), _stream()), "rr_roi_align_backward")
+    return grad
+
+
 def head_forward(roi_feat, folded, n_dev=None, algo=0):
     """Re-regression head on [n,256,3,3] RoI features -> [n,4].  algo 0 = tcgen05 tensor cores (3xTF32),
     1 = fp32 FFMA."""

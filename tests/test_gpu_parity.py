@@ -827,3 +827,40 @@ def test_stage2_loss_and_gradients(ops):
     assert float(parts[2]) == 0.0 and float(parts[3]) == 0.0
     assert rel_err(npy(g_reg), rr.grad.numpy(), floor=1e-4) < TOL
     assert rel_err(npy(g_box), rb.grad.numpy()[:, 1:], floor=1e-4) < TOL
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("C", [64, 40])
+def test_roi_align_backward_vs_torchvision(ops, algo, C):
+    """rr_roi_align_backward against autograd through torchvision.ops.roi_align(relu(feat)) on the CPU: small and
+    large RoIs (a window over 64 pixels goes through the direct path), RoIs over the map border, empty and
+    degenerate boxes, overlapping RoIs in one tile, two images; C = 40 forces the direct path (C % 32 != 0).
+    Tolerance 3e-5 relative: a gradient element is a sum over all samples of all RoIs that touch the pixel; the
+    reference accumulates it sample by sample (in an arbitrary atomic order on the GPU), this kernel through the
+    separable per-axis weights, so the fp32 sums are associated differently (measured: 1.0e-5)."""
+    import torchvision
+    tol = 3e-5
+    g = torch.Generator().manual_seed(31 + C)
+    B, H, W = 2, 70, 100
+    feat = torch.randn(B, C, H, W, generator=g)
+    n = 60
+    cx, cy = torch.rand(n, generator=g) * W, torch.rand(n, generator=g) * H
+    bw, bh = torch.rand(n, generator=g) * 30 + 1, torch.rand(n, generator=g) * 30 + 1
+    rois = torch.stack([torch.randint(0, B, (n,), generator=g).float(), cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    rois[0, 1:] = torch.tensor([3.0, 2.0, 95.0, 66.0])          # window > 64: direct path
+    rois[1, 1:] = torch.tensor([-20.0, -10.0, 12.0, 9.0])        # over the top-left border
+    rois[2, 1:] = torch.tensor([90.0, 60.0, 140.0, 99.0])        # over the bottom-right border
+    rois[3, 1:] = torch.tensor([50.0, 30.0, 50.0, 30.0])         # degenerate (size clamps to 1)
+    rois[4, 1:] = torch.tensor([300.0, 300.0, 320.0, 330.0])     # entirely outside
+    rois = rois[torch.argsort(rois[:, 0], stable=True)]
+    gout = torch.randn(n, C, 3, 3, generator=g)
+    f = feat.clone().requires_grad_(True)
+    out = torchvision.ops.roi_align(torch.relu(f), rois, (3, 3))
+    (ref,) = torch.autograd.grad(out, f, gout)
+    got = npy(ops.roi_align_backward(dev(feat), dev(rois), dev(gout), relu=True, algo=algo))
+    assert rel_err(got, ref.numpy(), floor=1e-3) < tol
+    # without the ReLU
+    f2 = feat.clone().requires_grad_(True)
+    (ref2,) = torch.autograd.grad(torchvision.ops.roi_align(f2, rois, (3, 3)), f2, gout)
+    got2 = npy(ops.roi_align_backward(dev(feat), dev(rois), dev(gout), relu=False, algo=algo))
+    assert rel_err(got2, ref2.numpy(), floor=1e-3) < tol
