@@ -250,8 +250,8 @@ int rr_focal_render_backward(const float* logits, const float* annos, const int3
 /* ------------------------------------------------------------------------------------------
  * Backward of rr_roi_align (training; SURVEY 8b `_backward`): grad_feat [B,C,H,W] = d loss / d feat of
  * roi_align(relu(feat), rois, (3,3)) given grad_out [n_cap,C,3,3].  Same arguments, algo and workspace size as the
- * forward (the RoI bookkeeping is recomputed).  Tile path: a gather, every element written once with a plain store (no
- * atomics on the data; summation order = piece list order); direct-path RoIs (windows over 64 pixels) are added with atomicAdd.  grad_feat is fully written.
+ * forward (the RoI bookkeeping is recomputed).  Tile path: a gather, every element written once with a plain store, pieces
+ * summed in ascending RoI order (bit-reproducible); direct-path RoIs (windows over 64 pixels) are added with atomicAdd.  grad_feat is fully written.
  * ---------------------------------------------------------------------------------------- */
 int rr_roi_align_backward(const float* feat, const float* rois, const int32_t* n_rois_dev, int n_cap,
                           int B, int C, int H, int W, int relu, int algo, const float* grad_out, float* grad_feat,

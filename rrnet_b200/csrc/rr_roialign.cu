@@ -820,14 +820,14 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
 // tile and keeps that row's 32 pixels of its lane's channel in registers; it walks over the tile's pieces in list
 // order and adds  sum_pw wx[pw][x] * (sum_ph wy[ph][y] * G[c,ph,pw] / count)  for the pieces that cover its row.
 // Every output element is written exactly once with a plain store, no atomics on the data (torchvision's backward
-// scatters 4 atomicAdds per sample); the pieces of a tile are summed in the fill kernel's list order, which is not
-// fixed from run to run, so the last bits may differ between runs, like the reference's.  The ReLU mask is applied in the coalesced write-out.  RoIs of the direct path
+// scatters 4 atomicAdds per sample); the pieces of a tile are summed in ascending RoI order: bit-reproducible.  The ReLU mask is applied in the coalesced write-out.  RoIs of the direct path
 // (windows over 64 pixels) are added afterwards by a per-RoI kernel with atomicAdd.
 // --------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 32 * kTH;                 // 24 warps = 24 tile rows
 constexpr int kBwdWxFloats = kChunk * RR_POOL * kTW;  // weights placed at tile columns
 constexpr int kBwdGFloats = kChunk * kTC * RR_POOL * RR_POOL;
-constexpr int kBwdSmemFloats = kChunk * 2 * 4 + kChunk * kTH * 4 + kBwdWxFloats + kBwdGFloats + kChunk + kTH * kTC * 33;
+constexpr int kBwdMaxSort = 2048;                      // pieces of one tile that are brought into RoI order (more: list order)
+constexpr int kBwdSmemFloats = kChunk * 2 * 4 + kChunk * kTH * 4 + kBwdWxFloats + kBwdGFloats + kChunk + kTH * kTC * 33 + 2 * kBwdMaxSort;
 constexpr int kBwdSmem = kBwdSmemFloats * (int)sizeof(float);
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -842,6 +842,8 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
     float* s_g = s_wx + kBwdWxFloats;                                // [piece][channel][9]
     float* s_inv = s_g + kBwdGFloats;
     float* s_t = s_inv + kChunk;                                     // [row][channel][33]
+    int* s_ids = reinterpret_cast<int*>(s_t + kTH * kTC * 33);       // RoI index of every piece of the tile
+    int* s_perm = s_ids + kBwdMaxSort;                               // pieces in ascending RoI order
     const int tid = threadIdx.x, lane = tid & 31, y = tid >> 5;
     const int ngroups = C / kTC;
     const int t = blockIdx.x / ngroups, g = blockIdx.x - t * ngroups;
@@ -854,11 +856,27 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
 #pragma unroll
     for (int x = 0; x < kTW; ++x) acc[x] = 0.f;
 
+    // The fill kernel hands out list positions with an atomic, so the list order of a tile's pieces changes from run to
+    // run; summing them in ascending RoI order (a RoI has at most one piece per tile) makes the result bit-reproducible.
+    const int off = tile_off[t];
+    const bool sorted = n_p <= kBwdMaxSort;
+    if (sorted) {
+        for (int i = tid; i < n_p; i += kBwdThreads) s_ids[i] = __ldg(&list[2 * (size_t)(off + i)].x);
+        __syncthreads();
+        for (int i = tid; i < n_p; i += kBwdThreads) {
+            const int me = s_ids[i];
+            int rank = 0;
+            for (int j = 0; j < n_p; ++j) rank += s_ids[j] < me;
+            s_perm[rank] = i;
+        }
+    }
+
     for (int base = 0; base < n_p; base += kChunk) {
-        const int cnt = min(kChunk, n_p - base), list0 = tile_off[t] + base;
-        __syncthreads();                                             // previous chunk's tables are no longer read
-        if (tid < 2 * cnt) s_desc[tid] = __ldg(list + 2 * (size_t)list0 + tid);
-        for (int i = tid; i < cnt * kTH; i += kBwdThreads) s_wy[i] = __ldg(list_wy + (size_t)list0 * kTH + i);
+        const int cnt = min(kChunk, n_p - base);
+        __syncthreads();                                             // previous chunk's tables are no longer read (and s_perm is complete)
+        auto pos_of = [&](int p) { return off + (sorted ? s_perm[base + p] : base + p); };
+        if (tid < 2 * cnt) s_desc[tid] = __ldg(list + 2 * (size_t)pos_of(tid >> 1) + (tid & 1));
+        for (int i = tid; i < cnt * kTH; i += kBwdThreads) s_wy[i] = __ldg(list_wy + (size_t)pos_of(i / kTH) * kTH + i % kTH);
         for (int i = tid; i < cnt * RR_POOL * kTW; i += kBwdThreads) s_wx[i] = 0.f;
         __syncthreads();
         for (int i = tid; i < cnt * RR_POOL * kTW; i += kBwdThreads) {   // list_wx[pos][pw][i] belongs to tile column c0 + i
@@ -866,7 +884,7 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
             const int4 d0 = s_desc[2 * p], d1 = s_desc[2 * p + 1];
             const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
             const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
-            if (k < ncols) s_wx[(p * RR_POOL + pw) * kTW + c0 + k] = __ldg(list_wx + ((size_t)(list0 + p) * RR_POOL + pw) * kTW + k);
+            if (k < ncols) s_wx[(p * RR_POOL + pw) * kTW + c0 + k] = __ldg(list_wx + ((size_t)pos_of(p) * RR_POOL + pw) * kTW + k);
         }
         for (int i = tid; i < cnt * kTC * 9; i += kBwdThreads) {         // 288 contiguous floats per (RoI, channel group)
             const int p = i / (kTC * 9), e = i - p * (kTC * 9);

@@ -864,3 +864,7 @@ def test_roi_align_backward_vs_torchvision(ops, algo, C):
     (ref2,) = torch.autograd.grad(torchvision.ops.roi_align(f2, rois, (3, 3)), f2, gout)
     got2 = npy(ops.roi_align_backward(dev(feat), dev(rois), dev(gout), relu=False, algo=algo))
     assert rel_err(got2, ref2.numpy(), floor=1e-3) < tol
+    if algo == 0 and C % 32 == 0:              # tile path: pieces summed in RoI order, one atomicAdd per element for RoI 0
+        for _ in range(3):
+            again = npy(ops.roi_align_backward(dev(feat), dev(rois), dev(gout), relu=True, algo=0))
+            np.testing.assert_array_equal(again, got)
