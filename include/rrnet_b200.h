@@ -284,6 +284,20 @@ int rr_stage2_loss(const float* bxyxy, const int32_t* seg_offsets, const float* 
                    int B, int max_n, int gt_stride, float scale, float grad_scale,
                    float* loss_parts, float* grad_reg, float* grad_box, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * True-positive matching of the evaluation, utils/metrics/metrics.py:51-136 (`get_tp`) for B images in one launch.
+ *   pred [B,M,6] = x,y,w,h,score,cls (n_pred [B] valid rows each), target [B,N,6] = x,y,w,h,*,cls with cls 0 = ignore
+ *   region (n_tgt [B]), thresholds [T] IoU thresholds; M, N <= 768, T <= 16, cls_num <= 32 (the reference: 500, 500, 10, 11)
+ *   order [B,M]        index into pred of the p-th best detection (-1 past n_pred)
+ *   tp [B,M,T]         1 where that detection is a true positive at the threshold
+ *   out_cls [B,M]      its class, or -1 when the reference would not emit it (inside an ignore region, or no ground
+ *                      truth of its class in the image)
+ *   target_count, in_img [B,cls_num-1]   ground-truth boxes per class / 1 if the class occurs (after the ignore filter)
+ * ---------------------------------------------------------------------------------------- */
+int rr_ap_match(const float* pred, const int32_t* n_pred, const float* target, const int32_t* n_tgt,
+                const float* thresholds, int B, int M, int N, int T, int cls_num,
+                int32_t* order, float* tp, int32_t* out_cls, float* target_count, float* in_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

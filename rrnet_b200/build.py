@@ -33,6 +33,7 @@ UNITS = {
     "rr_focal.cu": [],
     "rr_regl1.cu": ["--fmad=false"],
     "rr_stage2loss.cu": [],
+    "rr_apmatch.cu": ["--fmad=false"],
 }
 
 BASE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -13,7 +13,8 @@ SYMBOLS = (("modules.loss.focalloss", "FocalLossHM", "rrnet_b200.host.modules.lo
            ("modules.loss.functional", "focal_loss_for_hm", "rrnet_b200.host.modules.loss.functional"),
            ("modules.loss.regl1loss", "RegL1Loss", "rrnet_b200.host.modules.loss.regl1loss"),
            ("datasets.transforms.functional", "to_heatmap", "rrnet_b200.host.datasets.transforms.functional"),
-           ("datasets.transforms.transforms", "ToHeatmap", "rrnet_b200.host.datasets.transforms.transforms"))
+           ("datasets.transforms.transforms", "ToHeatmap", "rrnet_b200.host.datasets.transforms.transforms"),
+           ("utils.metrics.metrics", "get_tp", "rrnet_b200.host.utils.metrics.metrics"))
 
 
 def install():

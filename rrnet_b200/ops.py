@@ -366,6 +366,31 @@ def stage2_loss(bxyxy, seg_offsets, s2_reg, gt_xyxy, scale=4.0, grad_scale=1.0, 
     return parts, g_reg, g_box
 
 
+def ap_match(pred, n_pred, target, n_tgt, thresholds, cls_num=11):
+    """Evaluation true-positive matching (utils/metrics/metrics.py:get_tp) for a batch of images.
+    pred [B,M,6] x,y,w,h,score,cls; target [B,N,6] x,y,w,h,*,cls (0 = ignore region); n_pred / n_tgt [B] int32
+    -> order [B,M] int32, tp [B,M,T], cls [B,M] int32 (-1: not emitted), target_count [B,cls_num-1], in_img [B,cls_num-1]."""
+    pred = _f32(pred, "pred", 3)
+    target = _f32(target, "target", 3)
+    thresholds = _f32(thresholds, "thresholds", 1)
+    n_pred = _i32(n_pred, "n_pred")
+    n_tgt = _i32(n_tgt, "n_tgt")
+    B, M, six = pred.shape
+    N, T = target.shape[1], thresholds.numel()
+    if six != 6 or target.shape[0] != B or (N and target.shape[2] != 6) or n_pred.numel() != B or n_tgt.numel() != B:
+        raise RRNetB200Error("ap_match: pred [B,M,6], target [B,N,6], n_pred / n_tgt [B]")
+    dev = pred.device
+    order = torch.empty(B, M, dtype=torch.int32, device=dev)
+    tp = torch.empty(B, M, T, dtype=torch.float32, device=dev)
+    cls = torch.empty(B, M, dtype=torch.int32, device=dev)
+    cnt = torch.empty(B, cls_num - 1, dtype=torch.float32, device=dev)
+    img = torch.empty(B, cls_num - 1, dtype=torch.float32, device=dev)
+    check(_lib.lib().rr_ap_match(_ptr(pred), _ptr(n_pred), _ptr(target), _ptr(n_tgt), _ptr(thresholds), B, M, N, T,
+                                 int(cls_num), _ptr(order), _ptr(tp), _ptr(cls), _ptr(cnt), _ptr(img), _stream()),
+          "rr_ap_match")
+    return order, tp, cls, cnt, img
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Process-wide; grid sizes are fixed at launch / graph capture time."""

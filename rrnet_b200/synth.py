@@ -210,3 +210,34 @@ def nms_stress_boxes(n, seed, cluster=20):
     x1y1 = ctr - wh / 2
     x2y2 = ctr + wh / 2
     return torch.cat([x1y1, x2y2, scores[:, None]], dim=1).contiguous()
+
+
+AP_MATCH_CASES = ((30, 20, 2, 1), (60, 40, 0, 2), (5, 3, 1, 3), (80, 100, 4, 4), (200, 150, 6, 5), (1, 0, 0, 6))
+
+
+def ap_match_case(n_gt, n_fp, n_ign, seed):
+    """One image for the evaluation's true-positive matching (utils/metrics/metrics.py:get_tp): ground truth
+    [n,6] = x,y,w,h,1,cls (cls 0 = ignore region) and detections [m,6] = x,y,w,h,score,cls: two jittered copies of every
+    box (10 % with a wrong class), n_fp random false positives, distinct scores."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    xy = torch.rand(n_gt, 2, generator=g) * 400
+    wh = torch.rand(n_gt, 2, generator=g) * 60 + 8
+    cls = torch.randint(1, 11, (n_gt,), generator=g).float()
+    tgt = torch.cat([xy, wh, torch.ones(n_gt, 1), cls[:, None]], 1)
+    if n_ign:
+        ixy = torch.rand(n_ign, 2, generator=g) * 300
+        iwh = torch.rand(n_ign, 2, generator=g) * 120 + 60
+        tgt = torch.cat([tgt, torch.cat([ixy, iwh, torch.zeros(n_ign, 1), torch.zeros(n_ign, 1)], 1)])
+        tgt = tgt[torch.randperm(tgt.shape[0], generator=g)]
+    rep = torch.randint(0, n_gt, (2 * n_gt,), generator=g)
+    jit = (torch.rand(2 * n_gt, 4, generator=g) - 0.5) * torch.tensor([12.0, 12.0, 10.0, 10.0])
+    det = torch.cat([xy[rep], wh[rep]], 1) + jit
+    det[:, 2:] = det[:, 2:].clamp(min=2)
+    dcls = cls[rep].clone()
+    flip = torch.rand(2 * n_gt, generator=g) < 0.1
+    dcls[flip] = torch.randint(1, 11, (int(flip.sum()),), generator=g).float()
+    fp = torch.cat([torch.rand(n_fp, 2, generator=g) * 400, torch.rand(n_fp, 2, generator=g) * 60 + 8], 1)
+    boxes = torch.cat([det, fp])
+    c = torch.cat([dcls, torch.randint(1, 11, (n_fp,), generator=g).float()])
+    score = torch.randperm(boxes.shape[0], generator=g).float() / boxes.shape[0] * 0.98 + 0.01
+    return torch.cat([boxes, score[:, None], c[:, None]], 1).contiguous(), tgt.contiguous()

@@ -250,6 +250,25 @@ def gold_criterion(ref):
          grad_hm=hm.grad, grad_wh=wh.grad, grad_off=off.grad)
 
 
+def gold_ap_match(ref):
+    """utils/metrics/metrics.py:get_tp of the reference on the seeded images of synth.AP_MATCH_CASES."""
+    import utils.metrics.metrics as M
+    thr = torch.arange(0.5, 1.0, 0.05)
+    out = {"thresholds": thr}
+    for k, case in enumerate(synth.AP_MATCH_CASES):
+        pred, tgt = synth.ap_match_case(*case)
+        flags = [torch.zeros(0, thr.numel()) for _ in range(10)]
+        confs = [torch.zeros(0) for _ in range(10)]
+        f, cf, tc, ii = M.get_tp(pred.clone(), tgt.clone(), flags, confs, torch.zeros(10), torch.zeros(10), thr)
+        out["tp_%d" % k] = torch.cat(f)
+        out["conf_%d" % k] = torch.cat(cf)
+        out["sizes_%d" % k] = torch.tensor([x.shape[0] for x in f])
+        out["target_count_%d" % k] = tc
+        out["in_img_%d" % k] = ii
+        out["sha_%d" % k] = np.frombuffer(bytes.fromhex(sha1(pred, tgt)), dtype=np.uint8)
+    save("ap_match", **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -264,6 +283,7 @@ def main():
     gold_render(ref)
     gold_focal(ref)
     gold_criterion(ref)
+    gold_ap_match(ref)
 
 
 if __name__ == "__main__":

@@ -868,3 +868,44 @@ def test_roi_align_backward_vs_torchvision(ops, algo, C):
         for _ in range(3):
             again = npy(ops.roi_align_backward(dev(feat), dev(rois), dev(gout), relu=True, algo=0))
             np.testing.assert_array_equal(again, got)
+
+
+def test_ap_match_vs_reference_goldens_and_oracle(ops):
+    """rr_ap_match: all seeded images as ONE padded batch against the reference's own get_tp outputs
+    (tests/golden/ap_match.npz) and against oracle/metrics_np on the same inputs - bit-exact flags, counts, order."""
+    from oracle import metrics_np
+    g = load_golden("ap_match")
+    cases = [synth.ap_match_case(*c) for c in synth.AP_MATCH_CASES]
+    B = len(cases)
+    M = max(p.shape[0] for p, _ in cases) + 3
+    N = max(t.shape[0] for _, t in cases) + 2
+    pred = torch.zeros(B, M, 6)
+    tgt = torch.zeros(B, N, 6)
+    for b, (p, t) in enumerate(cases):
+        pred[b, : p.shape[0]] = p
+        tgt[b, : t.shape[0]] = t
+    n_pred = torch.tensor([p.shape[0] for p, _ in cases], dtype=torch.int32)
+    n_tgt = torch.tensor([t.shape[0] for _, t in cases], dtype=torch.int32)
+    thr = torch.from_numpy(g["thresholds"])
+    order, tp, cls, cnt, img = [npy(x) for x in ops.ap_match(dev(pred), dev(n_pred), dev(tgt), dev(n_tgt), dev(thr))]
+    for b, (p, t) in enumerate(cases):
+        m = p.shape[0]
+        o = metrics_np.get_tp_image(p.numpy(), t.numpy(), g["thresholds"])
+        np.testing.assert_array_equal(cnt[b], g["target_count_%d" % b])
+        np.testing.assert_array_equal(img[b], g["in_img_%d" % b])
+        assert (order[b, m:] == -1).all() and (cls[b, m:] == -1).all()
+        assert sorted(order[b, :m].tolist()) == list(range(m))
+        sc = p[:, 4].numpy()[order[b, :m]]
+        assert (sc[:-1] >= sc[1:]).all()
+        # the emitted detections, class by class in rank order = the reference's concatenated lists
+        tps, confs, sizes = [], [], []
+        for c in range(1, 11):
+            sel = cls[b, :m] == c
+            tps.append(tp[b, :m][sel]); confs.append(sc[sel]); sizes.append(int(sel.sum()))
+        np.testing.assert_array_equal(np.array(sizes), g["sizes_%d" % b])
+        np.testing.assert_array_equal(np.concatenate(tps), g["tp_%d" % b])
+        np.testing.assert_array_equal(np.concatenate(confs), g["conf_%d" % b])
+        # and the oracle's view of the same image (kept detections, their classes)
+        kept = np.zeros(m, bool)
+        kept[o["order"][o["emit"]]] = True
+        np.testing.assert_array_equal(cls[b, :m] >= 0, kept[order[b, :m]])

@@ -249,3 +249,28 @@ def test_criterion_golden(host):
     assert rel_err(npy(hm.grad), g["grad_hm"], floor=1e-3) < 1e-4
     assert rel_err(npy(wh.grad), g["grad_wh"], floor=1e-3) < 1e-4
     assert rel_err(npy(off.grad), g["grad_off"], floor=1e-3) < 1e-4
+
+
+def test_get_tp_mirror_golden(host):
+    """host.utils.metrics.metrics.get_tp (rr_ap_match behind the reference's signature and list protocol), accumulated
+    over all seeded images like evaluate_results does, against the reference's get_tp accumulated the same way."""
+    from rrnet_b200.host.utils.metrics import metrics as HM
+    g = load_golden("ap_match")
+    thr = torch.from_numpy(g["thresholds"])
+    flags = [torch.zeros(0, thr.numel()) for _ in range(10)]
+    confs = [torch.zeros(0) for _ in range(10)]
+    tc, ii = torch.zeros(10), torch.zeros(10)
+    ref_flags = [[] for _ in range(10)]
+    ref_confs = [[] for _ in range(10)]
+    for k, case in enumerate(synth.AP_MATCH_CASES):
+        pred, tgt = synth.ap_match_case(*case)
+        flags, confs, tc, ii = HM.get_tp(pred, tgt, flags, confs, tc, ii, thr)
+        off = 0
+        for c, n in enumerate(g["sizes_%d" % k].tolist()):
+            ref_flags[c].append(g["tp_%d" % k][off:off + n]); ref_confs[c].append(g["conf_%d" % k][off:off + n])
+            off += n
+    np.testing.assert_array_equal(tc.numpy(), sum(g["target_count_%d" % k] for k in range(len(synth.AP_MATCH_CASES))))
+    np.testing.assert_array_equal(ii.numpy(), sum(g["in_img_%d" % k] for k in range(len(synth.AP_MATCH_CASES))))
+    for c in range(10):
+        np.testing.assert_array_equal(flags[c].numpy(), np.concatenate(ref_flags[c]))
+        np.testing.assert_array_equal(confs[c].numpy(), np.concatenate(ref_confs[c]))

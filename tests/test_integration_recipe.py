@@ -39,6 +39,8 @@ def test_dropin_install_keeps_the_rest_of_the_reference_importable():
         import datasets.transforms.functional as TF, datasets.transforms.transforms as TT
         assert TF.to_heatmap.__module__.startswith("rrnet_b200.host") and callable(TF.denormalize)
         assert TT.ToHeatmap.__module__.startswith("rrnet_b200.host")
+        import utils.metrics.metrics as UM
+        assert UM.get_tp.__module__.startswith("rrnet_b200.host") and UM.calculate_ap_rc.__module__ == "utils.metrics.metrics"
         # an operator of the reference that is NOT on the path still imports, and gets the mirror's losses / NMS
         import operators.centernet_operator as CO
         assert CO.FocalLossHM is FL.FocalLossHM and CO.RegL1Loss is RL.RegL1Loss

@@ -208,3 +208,30 @@ def test_focal(oracle_mod):
     assert sums[2] == 0
     assert abs(loss - float(g["loss_nopos"])) / abs(float(g["loss_nopos"])) < TOL
     assert rel_err(grad, g["grad_nopos"], floor=1e-5) < 1e-4
+
+
+# ------------------------------------------------------------------ evaluation: true-positive matching
+def _sha(*tensors):
+    h = hashlib.sha1()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.numpy()).tobytes())
+    return np.frombuffer(bytes.fromhex(h.hexdigest()), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("k", range(len(synth.AP_MATCH_CASES)))
+def test_ap_match_oracle_vs_reference_get_tp(k):
+    """oracle/metrics_np.get_tp_image against the outputs of the reference's own get_tp (utils/metrics/metrics.py:51-136)."""
+    from oracle import metrics_np
+    g = load_golden("ap_match")
+    pred, tgt = synth.ap_match_case(*synth.AP_MATCH_CASES[k])
+    np.testing.assert_array_equal(_sha(pred, tgt), g["sha_%d" % k])          # same bytes the reference saw
+    o = metrics_np.get_tp_image(pred.numpy(), tgt.numpy(), g["thresholds"])
+    np.testing.assert_array_equal(o["target_count"], g["target_count_%d" % k])
+    np.testing.assert_array_equal(o["in_img"], g["in_img_%d" % k])
+    tp, conf, sizes = [], [], []
+    for c in range(1, 11):
+        sel = (o["cls"] == c) & o["emit"]
+        tp.append(o["tp"][sel]); conf.append(o["conf"][sel]); sizes.append(int(sel.sum()))
+    np.testing.assert_array_equal(np.array(sizes), g["sizes_%d" % k])
+    np.testing.assert_array_equal(np.concatenate(tp), g["tp_%d" % k])
+    np.testing.assert_array_equal(np.concatenate(conf), g["conf_%d" % k])
