@@ -37,45 +37,59 @@ stage2_loss_kernel(const float* __restrict__ bxyxy, const int* __restrict__ seg,
     if (threadIdx.x == 0) s_npos = 0;
     __syncthreads();
 
-    // ---- pass 1: positives of this image (rrnet_operator.py:72-74) ----
-    int n_pos = 0;
-    for (int r = lo + threadIdx.x; r < hi; r += kS2Threads) {
+    // ---- pass 1: best ground-truth box per RoI, positives of this image (rrnet_operator.py:72-74) ----
+    // the row maxima of the first kCache strides of a thread stay in registers for pass 2
+    constexpr int kCache = 4;                        // 4 x 512 = 2048 RoIs per image without recomputation
+    float c_best[kCache];
+    int c_arg[kCache];
+    auto row_max = [&](int r, float& best, int& arg) {
         const float* bx = bxyxy + (size_t)r * 5 + 1;
         const float x1 = __fmul_rn(bx[0], scale), y1 = __fmul_rn(bx[1], scale);
         const float x2 = __fmul_rn(bx[2], scale), y2 = __fmul_rn(bx[3], scale);
         const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-        float best = -1.f;
+        best = -1.f;
+        arg = 0;
         for (int k = 0; k < max_n; ++k) {
             const float gx1 = s_gt[4 * k], gy1 = s_gt[4 * k + 1], gx2 = s_gt[4 * k + 2], gy2 = s_gt[4 * k + 3];
             const float iw = fmaxf(__fsub_rn(fminf(x2, gx2), fmaxf(x1, gx1)), 0.f);
             const float ih = fmaxf(__fsub_rn(fminf(y2, gy2), fmaxf(y1, gy1)), 0.f);
             const float inter = __fmul_rn(iw, ih);
             const float ga = __fmul_rn(__fsub_rn(gx2, gx1), __fsub_rn(gy2, gy1));
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, ga), inter));   // 0/0 = NaN never wins below
-            if (iou > best) best = iou;
+            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, ga), inter));   // 0/0 = NaN never wins
+            if (iou > best) { best = iou; arg = k; }              // first maximum, like torch.max
         }
-        n_pos += best > 0.5f;
+    };
+    int n_pos = 0;
+    {
+        int it = 0;
+        for (int r = lo + threadIdx.x; r < hi; r += kS2Threads, ++it) {
+            float best;
+            int arg;
+            row_max(r, best, arg);
+#pragma unroll
+            for (int q = 0; q < kCache; ++q)
+                if (q == it) { c_best[q] = best; c_arg[q] = arg; }
+            n_pos += best > 0.5f;
+        }
     }
     n_pos = (int)block_sum_s2((double)n_pos, s_red);
 
     // ---- pass 2: targets, smooth-L1, gradients ----
     const float w = n_pos > 0 ? __fdiv_rn(inv_bs, (float)(4 * n_pos)) : 0.f;      // mean over n_pos x 4, then / bs
     double sum = 0.0;
-    for (int r = lo + threadIdx.x; r < hi; r += kS2Threads) {
+    int it2 = 0;
+    for (int r = lo + threadIdx.x; r < hi; r += kS2Threads, ++it2) {
         const float* bx = bxyxy + (size_t)r * 5 + 1;
         const float x1 = __fmul_rn(bx[0], scale), y1 = __fmul_rn(bx[1], scale);
         const float x2 = __fmul_rn(bx[2], scale), y2 = __fmul_rn(bx[3], scale);
-        const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
         float best = -1.f;
         int arg = 0;
-        for (int k = 0; k < max_n; ++k) {
-            const float gx1 = s_gt[4 * k], gy1 = s_gt[4 * k + 1], gx2 = s_gt[4 * k + 2], gy2 = s_gt[4 * k + 3];
-            const float iw = fmaxf(__fsub_rn(fminf(x2, gx2), fmaxf(x1, gx1)), 0.f);
-            const float ih = fmaxf(__fsub_rn(fminf(y2, gy2), fmaxf(y1, gy1)), 0.f);
-            const float inter = __fmul_rn(iw, ih);
-            const float ga = __fmul_rn(__fsub_rn(gx2, gx1), __fsub_rn(gy2, gy1));
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, ga), inter));
-            if (iou > best) { best = iou; arg = k; }              // first maximum, like torch.max
+        if (it2 < kCache) {
+#pragma unroll
+            for (int q = 0; q < kCache; ++q)
+                if (q == it2) { best = c_best[q]; arg = c_arg[q]; }
+        } else {
+            row_max(r, best, arg);
         }
         float4 g_reg = make_float4(0.f, 0.f, 0.f, 0.f), g_box = g_reg;
         if (n_pos > 0 && best > 0.5f) {
