@@ -16,17 +16,6 @@ from ..modules.loss.focalloss import FocalLossHM
 from ..modules.loss.regl1loss import RegL1Loss
 
 
-def _box_iou(a, b):
-    """torchvision.ops.box_iou (rrnet_operator.py:72) in plain torch: [n,4] x [m,4] -> [n,m]."""
-    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
-    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
-    lt = torch.max(a[:, None, :2], b[None, :, :2])
-    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
-    wh = (rb - lt).clamp(min=0)
-    inter = wh[..., 0] * wh[..., 1]
-    return inter / (area_a[:, None] + area_b[None, :] - inter)
-
-
 class _Stage2LossFn(torch.autograd.Function):
     """rr_stage2_loss with the reference's gradients: to s2_reg, and to the predicted boxes through the regression
     targets (the reference does not detach them, Appendix A.5)."""
@@ -140,80 +129,104 @@ class RRNetOperator(object):
     # ------------------------------------------------------------------ rrnet_operator.py:234-244
     @staticmethod
     def save_result(file_path, pred_bbox):
-        pred_bbox = torch.clamp(pred_bbox, min=0.)
-        with open(file_path, 'w') as f:
-            for i in range(pred_bbox.size()[0]):
-                bbox = pred_bbox[i]
-                line = '%f,%f,%f,%f,%.4f,%d,-1,-1\n' % (
-                    float(bbox[0]), float(bbox[1]), float(bbox[2]), float(bbox[3]),
-                    float(bbox[4]), int(bbox[5])
-                )
-                f.write(line)
+        """One VisDrone result file: 'x,y,w,h,score,cls,-1,-1' per row (%f x4, %.4f, %d), negative values clamped to 0
+        first like the reference (:236).  Written in one call instead of a Python loop over the rows."""
+        rows = torch.clamp(pred_bbox.detach().float().cpu(), min=0.).numpy().astype(np.float64)
+        table = np.concatenate([rows[:, :5], np.trunc(rows[:, 5:6]), np.full((rows.shape[0], 2), -1.0)], axis=1)
+        np.savetxt(file_path, table, fmt=['%f', '%f', '%f', '%f', '%.4f', '%d', '%d', '%d'], delimiter=',')
 
     # ------------------------------------------------------------------ rrnet_operator.py:104-186
     def training_process(self):
-        """The reference's loop: forward, criterion, loss = hm + 0.1*wh + off + s2 (after 2000 steps),
-        backward, step.  Logging / checkpointing go through the optional `logger` / cfg.Train fields."""
+        """forward -> criterion -> loss = hm + 0.1 wh + off + s2 (s2 only from step 2000 on, Appendix A.6) -> backward ->
+        optimiser step, with the scheduler stepped first like the reference (:117).  Running means of the five numbers
+        go to `logger` every cfg.Train.print_interval steps; image logging and checkpoints are the caller's."""
         self.model.train()
-        total_loss = 0
+        names = ('total_loss', 'hm_loss', 'wh_loss', 'off_loss', 's2_reg_loss')
+        running = dict.fromkeys(names, 0.0)
+        every = getattr(self.cfg.Train, 'print_interval', 0)
         for step in range(self.cfg.Train.iter_num):
             self.lr_sch.step()
             self.optimizer.zero_grad()
             try:
-                imgs, annos, gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks, names = self.training_loader.get_batch()
-                targets = gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks, annos
-            except RuntimeError as e:
+                batch = self.training_loader.get_batch()
+            except RuntimeError as e:                       # the reference skips a batch that does not fit (:121-124)
                 if 'out of memory' in str(e):
                     print('WARNING: ran out of memory with exception at step {}.'.format(step))
                 continue
-            outs = self.model(imgs)
-            hm_loss, wh_loss, offset_loss, s2_reg_loss = self.criterion(outs, targets)
-            s2_factor = 0 if step < 2000 else 1
-            loss = hm_loss + (0.1 * wh_loss) + offset_loss + s2_factor * s2_reg_loss
+            imgs, annos, gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks = batch[:7]
+            losses = self.criterion(self.model(imgs), (gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks, annos))
+            hm_loss, wh_loss, off_loss, s2_loss = losses
+            loss = hm_loss + 0.1 * wh_loss + off_loss + (s2_loss if step >= 2000 else 0 * s2_loss)
             loss.backward()
             self.optimizer.step()
-            total_loss += float(loss)
-            if self.main_proc_flag and self.logger is not None and step % self.cfg.Train.print_interval == \
-                    self.cfg.Train.print_interval - 1:
-                self.logger.log({'scalar': {'train/total_loss': total_loss / self.cfg.Train.print_interval,
-                                            'train/hm_loss': float(hm_loss), 'train/wh_loss': float(wh_loss),
-                                            'train/off_loss': float(offset_loss),
-                                            'train/s2_reg_loss': float(s2_reg_loss)}}, step)
-                total_loss = 0
-        return total_loss
+            for key, value in zip(names, (loss, hm_loss, wh_loss, off_loss, s2_loss)):
+                running[key] += float(value)
+            if every and step % every == every - 1:
+                if self.main_proc_flag and self.logger is not None:
+                    self.logger.log({'scalar': {'train/' + k: v / every for k, v in running.items()}}, step)
+                running = dict.fromkeys(names, 0.0)
+        return running['total_loss']
 
-    # ------------------------------------------------------------------ rrnet_operator.py:246-284
+    # ------------------------------------------------------------------ rrnet_operator.py:246-284, batched
+    def detect_multi_scale(self, imgs, scales=(1,), score_thr=0.01, final_nms=True):
+        """The body of the reference's evaluation loop for a whole batch (the reference handles image 0 only):
+        every scale through the model, stage-2 boxes of ALL images from one generate_bbox launch, boxes back to the
+        input resolution, then per image: score-descending order -> Gaussian soft-NMS per class (one launch for all
+        (image, class) segments) -> score-descending order.  One device->host copy.
+        -> list of CPU tensors [n_i,6] = x,y,w,h,score,cls."""
+        B = imgs.size(0) if torch.is_tensor(imgs) else len(imgs)
+        rows, owner = [], []
+        for scale in scales:
+            x = F.interpolate(imgs, scale_factor=scale, mode='bilinear', align_corners=True) if torch.is_tensor(imgs) else imgs
+            outs = self.model(x)
+            s2_reg, bxyxy, scores, clses = outs[3], outs[4], outs[5], outs[6]
+            _, s2 = ops.generate_bbox(bxyxy.contiguous(), s2_reg.contiguous(), scores.contiguous(),
+                                      clses.float().contiguous(), scale=float(self.cfg.Train.scale_factor))
+            img_idx = bxyxy[:, 0].long()
+            if final_nms:                                   # :266-267
+                keep = s2[:, 4] > score_thr
+                s2, img_idx = s2[keep], img_idx[keep]
+            s2 = s2.clone()
+            s2[:, :4] = s2[:, :4] / scale                   # :269
+            rows.append(s2)
+            owner.append(img_idx)
+        rows, owner = torch.cat(rows), torch.cat(owner)
+        by_score = torch.sort(rows[:, 4], descending=True, stable=True).indices          # :273-274
+        rows, owner = rows[by_score], owner[by_score]
+        if final_nms and rows.size(0):
+            key = owner * 4096 + rows[:, 5].long()          # (image, class) segments, score order kept inside
+            grouped = torch.sort(key, stable=True).indices
+            rows, owner, key = rows[grouped], owner[grouped], key[grouped]
+            _, counts = torch.unique_consecutive(key, return_counts=True)
+            seg = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=rows.device)
+            seg[1:] = torch.cumsum(counts, 0).int()
+            boxes5 = rows[:, :5].clone()
+            boxes5[:, 2:4] += boxes5[:, 0:2]                # xywh -> xyxy (:222-223)
+            kept, _, cnt = ops.soft_nms_batched(boxes5.contiguous(), seg, 0.5, 0.7, 0.1, 2)
+            kept = kept.clone()
+            kept[:, 2:4] -= kept[:, 0:2]
+            pos = torch.arange(rows.size(0), device=rows.device) - seg[:-1].long().repeat_interleave(counts)
+            alive = pos < cnt.long().repeat_interleave(counts)           # the first cnt rows of a segment survive
+            rows = torch.cat((kept, rows[:, 5:6]), dim=1)[alive]          # column 5 is constant inside a segment
+            owner = owner[alive]
+        host_rows, host_owner = rows.cpu(), owner.cpu()
+        out = []
+        for b in range(B):
+            mine = host_rows[host_owner == b]
+            out.append(mine[torch.sort(mine[:, 4], descending=True, stable=True).indices])   # :278-279
+        return out
+
     def evaluation_process(self):
-        """Multi-scale test of every validation image, soft-NMS unless cfg.Val.auto_test, result files
-        '<result_dir>/<name>.txt'.  Batch-1 like the reference (generate_bbox(outs) defaults to image 0)."""
+        """Multi-scale test of the validation set: `detect_multi_scale` per batch, one result file per image
+        ('<cfg.Val.result_dir>/<name>.txt').  Any batch size; with cfg.Val.auto_test the score filter and the final
+        soft-NMS are left to the metric code, as in the reference."""
         self.model.eval()
-        model_path = getattr(self.cfg.Val, "model_path", None)
+        model_path = getattr(self.cfg.Val, 'model_path', None)
         if model_path:
-            state_dict = torch.load(model_path, map_location='cpu')
-            getattr(self.model, "module", self.model).load_state_dict(state_dict)
-        step = 0
+            getattr(self.model, 'module', self.model).load_state_dict(torch.load(model_path, map_location='cpu'))
         with torch.no_grad():
-            for data in self.validation_loader:
-                multi_scale_bboxes = []
-                step += 1
-                imgs, annos, names = data
-                imgs = imgs.cuda()
-                for scale in self.cfg.Val.scales:
-                    img = F.interpolate(imgs, scale_factor=scale, mode='bilinear', align_corners=True)
-                    outs = self.model(img)
-                    _, pred_bbox = self.generate_bbox(outs)
-                    if not self.cfg.Val.auto_test:
-                        pred_bbox = pred_bbox[pred_bbox[:, 4] > 0.01]
-                    pred_bbox = pred_bbox.cpu()
-                    pred_bbox[:, :4] = pred_bbox[:, :4] / scale
-                    multi_scale_bboxes.append(pred_bbox)
-                pred_bbox = torch.cat(multi_scale_bboxes, dim=0)
-                _, idx = torch.sort(pred_bbox[:, 4], descending=True)
-                pred_bbox = pred_bbox[idx]
-                if not self.cfg.Val.auto_test:
-                    pred_bbox = self._ext_nms(pred_bbox)
-                _, idx = torch.sort(pred_bbox[:, 4], descending=True)
-                pred_bbox = pred_bbox[idx]
-                file_path = os.path.join(self.cfg.Val.result_dir, names[0] + '.txt')
-                self.save_result(file_path, pred_bbox)
+            for imgs, annos, names in self.validation_loader:
+                dets = self.detect_multi_scale(imgs.cuda(), self.cfg.Val.scales, final_nms=not self.cfg.Val.auto_test)
+                for name, det in zip(names, dets):
+                    self.save_result(os.path.join(self.cfg.Val.result_dir, name + '.txt'), det)
         print('=> Evaluation Done!')

@@ -274,3 +274,48 @@ def test_get_tp_mirror_golden(host):
     for c in range(10):
         np.testing.assert_array_equal(flags[c].numpy(), np.concatenate(ref_flags[c]))
         np.testing.assert_array_equal(confs[c].numpy(), np.concatenate(ref_confs[c]))
+
+
+class _FeatsForImages(nn.Module):
+    """The evaluation driver hands the model an image batch; the test net wants the backbone features."""
+
+    def __init__(self, net, feat, k):
+        super().__init__()
+        self.net, self.feat, self.k = net, feat, k
+
+    def forward(self, imgs):
+        return self.net([self.feat, self.feat], k=self.k)
+
+
+def test_batched_eval_driver_and_result_file(host, tmp_path):
+    """RRNetOperator.detect_multi_scale (all images of a batch, one generate_bbox launch, one soft-NMS launch over all
+    (image, class) segments) against the reference's per-image sequence generate_bbox -> score filter -> sort ->
+    _ext_nms -> sort built from the mirror's own (golden-checked) methods; save_result against the reference's format."""
+    g = load_golden("pipeline")
+    B, C, H, W, K = g["shape"].tolist()
+    seed = int(g["seed"])
+    x = {k: v.cuda() for k, v in synth.eval_inputs(B, H, W, K, seed).items()}
+    net = make_net(host, x["hm"], x["wh"], x["off"], seed)
+    op = host.RRNetOperator(CFG, model=_FeatsForImages(net, x["feat"], K))
+    imgs = torch.zeros(B, 3, 4 * H, 4 * W, device="cuda")
+    with torch.no_grad():
+        dets = op.detect_multi_scale(imgs, scales=(1,))
+        outs = net([x["feat"], x["feat"]], k=K)
+    assert len(dets) == B
+    for b in range(B):
+        _, s2 = op.generate_bbox(outs, b)
+        s2 = s2[s2[:, 4] > 0.01].cpu()
+        s2 = s2[torch.sort(s2[:, 4], descending=True, stable=True).indices]
+        ref = op._ext_nms(s2)
+        ref = ref[torch.sort(ref[:, 4], descending=True, stable=True).indices]
+        assert tuple(dets[b].shape) == tuple(ref.shape)
+        np.testing.assert_array_equal(npy(dets[b]), npy(ref))
+    # result file: '%f,%f,%f,%f,%.4f,%d,-1,-1' per row after clamp(min=0) (rrnet_operator.py:234-244)
+    rows = dets[0][:50].clone()
+    rows[0, 0] = -3.25
+    path = tmp_path / "img.txt"
+    op.save_result(str(path), rows)
+    want = "".join('%f,%f,%f,%f,%.4f,%d,-1,-1\n' % (max(float(r[0]), 0.), max(float(r[1]), 0.), max(float(r[2]), 0.),
+                                                     max(float(r[3]), 0.), max(float(r[4]), 0.), int(max(float(r[5]), 0.)))
+                   for r in rows)
+    assert path.read_text() == want
