@@ -72,6 +72,7 @@ constexpr int kTcAStage = 2 * kTcATile;          // A_hi | A_lo = 32 KB
 constexpr int kAStages = 2;                      // conv1 A stages; ring 1 (conv1 weights) has one slot per stage
 constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one step of the weight image
 constexpr int kRing1 = 1;                        // slots of ring 1 (conv1 weights): the conv1 stream is paced by the x loaders, not by its weights
+constexpr int kXRing = 8;                        // tiles of loader -> output-epilogue hand-off state (s_xdone, s_sb)
 constexpr int kRing2 = 4;                        // slots of ring 2 (conv2 / conv3 weights)
 constexpr int kSteps1 = 8, kSteps2 = 26;         // weight steps of stream 1 (conv1) and stream 2 (conv2, conv3)
 constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
@@ -247,13 +248,17 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     __shared__ __align__(8) unsigned long long s_full_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_free_b2[kRing2];
     __shared__ __align__(8) unsigned long long s_phase[4];           // MMAs of conv2 [1] / conv3 first half [2] / second half [3] are done ([0] unused)
-    __shared__ __align__(8) unsigned long long s_tready;             // t1, then t2 written by the epilogue (two phases per tile)
+    __shared__ __align__(8) unsigned long long s_t1ready, s_t2ready; // t1 / t2 of a tile written by the epilogue (one phase per tile each,
+                                                                     // so that the issuer can never miss a phase: see the waits)
     __shared__ __align__(8) unsigned long long s_d3free;             // conv3's accumulator has been read out (one phase per tile)
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) unsigned long long s_xdone[4];           // fp32 copy of x (and s_sb) of a tile written, ring of four tiles
+    // Ring of kXRing tiles for the loaders -> output-epilogue hand-off.  When the loaders start tile j, the dependency chain
+    // (stage free <- conv1(j-1) issued <- E2(j-3) done <- conv2(j-3) complete <- conv3(j-4) issued <- E3(j-5) done) only
+    // guarantees that the output epilogue of tile j-5 is over, so the ring must hold more than five tiles.
+    __shared__ __align__(8) unsigned long long s_xdone[kXRing];      // fp32 copy of x (and s_sb) of a tile written
     __shared__ __align__(8) unsigned long long s_c1done[2];          // MMAs of conv1 of a tile are done, by tile parity (the conv1 issuer runs ahead)
     __shared__ __align__(8) unsigned long long s_d12free[2];         // conv1 / conv2 accumulator of a tile parity read out for good
-    __shared__ int s_sb[4][kTcRois];                                 // first slot of the tile's RoIs, ring of four tiles
+    __shared__ int s_sb[kXRing][kTcRois];                            // first slot of the tile's RoIs
     __shared__ float s_b1[64], s_b2[64], s_b3[256];
     __shared__ float4 s_wr[256];                                     // regressor weights, one float4 per channel
     TC_TRACE(0);
@@ -294,9 +299,10 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         for (int i = 0; i < kRing2; ++i) { init(&s_full_b2[i], 1); init(&s_free_b2[i], 1); }
         for (int i = 0; i < kRing1; ++i) { init(&s_full_b1[i], 1); init(&s_free_b1[i], 1); }
         for (int i = 0; i < 4; ++i) init(&s_phase[i], 1);
-        init(&s_tready, 4);
+        init(&s_t1ready, 4);
+        init(&s_t2ready, 4);
         init(&s_d3free, 4);
-        for (int i = 0; i < 4; ++i) init(&s_xdone[i], kLoadWarps);
+        for (int i = 0; i < kXRing; ++i) init(&s_xdone[i], kLoadWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // zero fill -> visible to the MMA
@@ -392,9 +398,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             uint32_t slot2 = c2 % kRing2, par2 = (c2 / kRing2) & 1u;
 #pragma unroll
             for (int s2 = 0; s2 < kSteps2; s2 += 2) {           // two steps (kc = 0, 1 of a tap / quarter) per round
-                if (s2 == 0) TC_TIMED(w_t, bar_wait(&s_tready, 0u));           // t1 in place
+                if (s2 == 0) TC_TIMED(w_t, bar_wait(&s_t1ready, (uint32_t)(it & 1)));           // t1 in place
                 if (s2 == 18) {
-                    TC_TIMED(w_t, bar_wait(&s_tready, 1u));                    // t2 in place
+                    TC_TIMED(w_t, bar_wait(&s_t2ready, (uint32_t)(it & 1)));                    // t2 in place
                     if (it > 0) bar_wait(&s_d3free, (uint32_t)((it - 1) & 1));  // the previous tile has left conv3's accumulator
                 }
                 const uint32_t slot_a = slot2, par_a = par2;
@@ -479,7 +485,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     }
                 }
             }
-            if (ltid < kTcRois) s_sb[k & 3][ltid] = (ltid < nroi && src.partial) ? __ldg(src.slot + roi0 + ltid) : -1;
+            if (ltid < kTcRois) s_sb[k % kXRing][ltid] = (ltid < nroi && src.partial) ? __ldg(src.slot + roi0 + ltid) : -1;
             // one K chunk ahead in registers, up to six slots per item, every load issued before the first add
             float4 xp[kTcItems][kTcSlotsInReg];
             auto load_x_chunk = [&](int kc) {
@@ -537,7 +543,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
             __threadfence_block();                              // the fp32 copy and s_sb, before the epilogue warps are told
             __syncwarp();
-            if (lane == 0) bar_arrive(&s_xdone[k & 3]);
+            if (lane == 0) bar_arrive(&s_xdone[k % kXRing]);
         }
 #ifdef RR_HEAD_TC_TRACE
         if (ltid == 0) { TC_TRACE_VAL(27, w_fa); TC_TRACE_VAL(28, tc_now() - t_load0); }
@@ -594,7 +600,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             else asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) bar_arrive(&s_tready);
+            if (lane == 0) bar_arrive(to_smem ? &s_t1ready : &s_t2ready);
         };
         TC_TRACE(2);
 #ifdef RR_HEAD_TC_TRACE
@@ -627,12 +633,12 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             const int nroi = min(kTcRois, live - roi0);
             const uint32_t par = (uint32_t)(k & 1);
             const bool ekeep = pixel_row && (em >> 4) < nroi;
-            bar_wait_warp(&s_xdone[k & 3], (uint32_t)((k >> 2) & 1));     // the loaders' copy of x and s_sb are complete
+            bar_wait_warp(&s_xdone[k % kXRing], (uint32_t)((k / kXRing) & 1));     // the loaders' copy of x and s_sb are complete
             const float* res = src.roi_feat;                    // residual source of this thread's row
             bool res_rows = false;                              // true: [9][256] copy, false: [256][9] feature
             if (ekeep) {
                 const int rl = em >> 4, rr = em & 15, p = 3 * ((rr - 4) >> 2) + (rr & 3), n = roi0 + rl;
-                res_rows = s_sb[k & 3][rl] >= 0;
+                res_rows = s_sb[k % kXRing][rl] >= 0;
                 res = res_rows ? src.scratch + (size_t)n * 2304 + p * 256 : src.roi_feat + (size_t)n * 2304 + p;
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
