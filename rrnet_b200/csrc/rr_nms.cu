@@ -281,7 +281,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
 // Stage-1 compaction: image-major, class-ascending, score-descending rows
 // (models/rrnet.py:44-49,60-72) + counts [B+1].
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 stage1_compact_kernel(const float4* __restrict__ sbox, const float* __restrict__ sscore,
                       const int* __restrict__ slab, const int* __restrict__ seg_off,
                       const int* __restrict__ keep_pos, const int* __restrict__ keep_cnt,
@@ -291,32 +291,33 @@ stage1_compact_kernel(const float4* __restrict__ sbox, const float* __restrict__
     __shared__ int s_cls_base[RR_MAX_CLASSES + 1];
     __shared__ int s_img_base;
     const int b = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) {
-        int base = 0;
-        for (int bb = 0; bb < b; ++bb)
-            for (int c = 0; c < C; ++c) base += keep_cnt[bb * C + c];
-        s_img_base = base;
-        int run = 0;
-        for (int c = 0; c < C; ++c) { s_cls_base[c] = run; run += keep_cnt[b * C + c]; }
-        s_cls_base[C] = run;
-        out_counts[b] = run;
-        if (b == B - 1) out_counts[B] = base + run;
+    if (tid < 32) {                                 // warp 0: rows of the images before this one, class offsets inside it
+        int before = 0;
+        for (int i = tid; i < b * C; i += 32) before += keep_cnt[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        if (tid == 0) {
+            s_img_base = before;
+            int run = 0;
+            for (int c = 0; c < C; ++c) { s_cls_base[c] = run; run += keep_cnt[b * C + c]; }
+            s_cls_base[C] = run;
+            out_counts[b] = run;
+            if (b == B - 1) out_counts[B] = before + run;
+        }
     }
     __syncthreads();
-    const int base = s_img_base;
-    for (int c = 0; c < C; ++c) {
-        const int n = s_cls_base[c + 1] - s_cls_base[c];
-        const int so = seg_off[b * (C + 1) + c];
-        for (int t = tid; t < n; t += blockDim.x) {
-            int pos = keep_pos[(size_t)b * K + so + t];
-            size_t src = (size_t)b * K + pos;
-            float4 q = sbox[src];
-            size_t o = (size_t)base + s_cls_base[c] + t;
-            float* r = out_bxyxy + o * 5;
-            r[0] = (float)b; r[1] = q.x; r[2] = q.y; r[3] = q.z; r[4] = q.w;
-            out_scores[o] = sscore[src];
-            out_clses[o] = (float)slab[src];
-        }
+    const int base = s_img_base, total = s_cls_base[C];
+    for (int t = tid; t < total; t += blockDim.x) {       // all classes in one sweep: row t of the image's output
+        int c = 0;
+        while (t >= s_cls_base[c + 1]) ++c;
+        const int pos = keep_pos[(size_t)b * K + seg_off[b * (C + 1) + c] + (t - s_cls_base[c])];
+        const size_t src = (size_t)b * K + pos;
+        const float4 q = sbox[src];
+        const size_t o = (size_t)base + t;
+        float* r = out_bxyxy + o * 5;
+        r[0] = (float)b; r[1] = q.x; r[2] = q.y; r[3] = q.z; r[4] = q.w;
+        out_scores[o] = sscore[src];
+        out_clses[o] = (float)slab[src];
     }
 }
 
@@ -380,7 +381,7 @@ int stage1_nms_launch(const float* dets, int B, int K, int C, double thr, float*
     int r2 = launch_mask_scan(w.sbox, w.slab, w.seg_off, B, C, K, K, thr, 0, 0, w.mask, nullptr,
                               w.keep_pos, w.keep_cnt, st);
     if (rc == 0) rc = r2;
-    stage1_compact_kernel<<<B, 256, 0, st>>>(w.sbox, w.sscore, w.slab, w.seg_off, w.keep_pos, w.keep_cnt,
+    stage1_compact_kernel<<<B, 1024, 0, st>>>(w.sbox, w.sscore, w.slab, w.seg_off, w.keep_pos, w.keep_cnt,
                                              B, K, C, out_bxyxy, out_scores, out_clses, out_counts);
     RR_LAUNCHED(rc);
     return rc;
