@@ -487,6 +487,13 @@ roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
     if (rp.flags != kFlagTile || sb < 0) return;
     const float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
     const float4* wyn = wy4 + (size_t)n * kMaxWinT;
+    // list positions of all pieces of the RoI at once: lane p takes piece p (one atomic latency instead of one per piece)
+    const int m = rp.ntx * rp.nty;                                 // <= kMaxPieces
+    int my_pos = 0;
+    if (lane < m) {
+        const int t = rp.img * td.tiles_per_img + (rp.ty0 + lane / rp.ntx) * td.ntx + rp.tx0 + lane % rp.ntx;
+        my_pos = tile_off[t] + atomicAdd(tile_fill + t, 1);
+    }
     for (int j = 0; j < rp.nty; ++j) {
         const int py0 = (rp.ty0 + j) * kTH;
         const int r0 = max(rp.y_lo, py0), r1 = min(rp.y_lo + rp.ny - 1, py0 + kTH - 1);
@@ -502,10 +509,7 @@ roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
                 wxo[p] = c0 - rp.x_lo;
                 cols[p] = ncol[p] > 0 ? ((c0 - px0) | (ncol[p] << 8)) : 0;
             }
-            const int t = rp.img * td.tiles_per_img + (rp.ty0 + j) * td.ntx + rp.tx0 + i;
-            int pos = 0;
-            if (lane == 0) pos = tile_off[t] + atomicAdd(tile_fill + t, 1);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
+            const int pos = __shfl_sync(0xffffffffu, my_pos, j * rp.ntx + i);
             if (lane == 0) {
                 list[2 * pos] = make_int4(n, sb + j * rp.ntx + i, rows, cols[0]);
                 list[2 * pos + 1] = make_int4(cols[1], cols[2], 0, 0);
