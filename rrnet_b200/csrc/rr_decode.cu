@@ -325,9 +325,9 @@ __device__ void exact_select(const float* __restrict__ img, int H, int W, int N,
 __device__ int select_top_k(unsigned long long* s_e, int n, int K, unsigned long long* tmp) {
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_need, s_fill;
+    __shared__ int s_need, s_fill, s_done;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_prefix = 0ull; s_need = K; s_fill = 0; }
+    if (tid == 0) { s_prefix = 0ull; s_need = K; s_fill = 0; s_done = 0; }
     for (int round = 0; round < 8; ++round) {
         const int shift = 56 - 8 * round;
         if (tid < 256) s_hist[tid] = 0;
@@ -363,9 +363,13 @@ __device__ int select_top_k(unsigned long long* s_e, int n, int K, unsigned long
             if (pick >= 0) {                                   // exactly one lane (1 <= need <= matching entries)
                 s_prefix = prefix | ((unsigned long long)pick << shift);
                 s_need = need_in;
+                // the whole bin is wanted (always so once it holds a single entry): every entry >= the prefix padded
+                // with zero bits is in the cut, the remaining bytes need not be looked at
+                if (need_in == s_hist[pick]) s_done = 1;
             }
         }
         __syncthreads();
+        if (s_done) break;
     }
     const unsigned long long kth = s_prefix;                   // the K-th largest entry itself
     for (int i0 = tid - lane; i0 < n; i0 += nthr) {            // order is irrelevant: sorted next
