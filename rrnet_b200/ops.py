@@ -308,7 +308,7 @@ class EvalPath:
 
     def capture(self, hm, wh, off, feat):
         """Capture forward() on these (static) input tensors into a CUDA graph; graph.replay() then re-runs
-        the whole path (a memset + 12 kernels) with one launch.  The C entry points never allocate or
+        the whole path (a memset + 14 kernels) with one launch.  The C entry points never allocate or
         synchronise, so they are capturable as they are."""
         self.forward(hm, wh, off, feat)                    # warm-up: function attributes, lazy module load
         torch.cuda.synchronize()
