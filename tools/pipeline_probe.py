@@ -50,7 +50,8 @@ def run(n_streams, reserve, steps=100):
 
 
 if __name__ == "__main__":
-    run(1, 0)
-    for r in (0, 4, 8, 12, 16, 24):
-        run(2, r)
-    run(3, 12)
+    combos = [(1, 0)] + [(2, r) for r in (0, 4, 8, 12, 16, 24)] + [(3, 12)]
+    if len(sys.argv) > 1:                              # e.g.  python tools/pipeline_probe.py 2:6 2:10 3:8
+        combos = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]]
+    for n_streams, reserve in combos:
+        run(n_streams, reserve)
