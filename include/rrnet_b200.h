@@ -140,7 +140,9 @@ int rr_soft_nms_batched(float* boxes, const int32_t* seg_offsets, int M, int S,
  *   to process all n_cap rows.  relu != 0 applies max(v,0) to every tap (fused ReLU).
  *   algo: 0 = tile-centric (each feature tile is staged once in shared memory and serves every
  *   RoI piece that crosses it; RoIs wider/taller than 64 pixels or over the partial-slot budget
- *   take the direct path), 1 = direct gather for every RoI.  Both are deterministic.
+ *   take the direct path; the tiles arrive by TMA when W % 4 == 0 and feat is 16-byte aligned),
+ *   1 = direct gather for every RoI, 2 = tile-centric with tiles staged by ordinary loads (the
+ *   kernel used when TMA cannot be).  All are deterministic.
  *   out [n_cap,C,3,3].  C <= 1024.
  * ---------------------------------------------------------------------------------------- */
 size_t rr_roi_align_workspace_bytes(int n_cap, int B, int C, int H, int W);
@@ -186,7 +188,7 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
  * RRNetOperator.generate_bbox for every image.  All launches go to `stream`, no host sync.
  * Outputs have capacity B*K rows; counts [B+1] as in rr_stage1_nms.
  * roi_feat may be NULL (the workspace then holds it).  roi_algo: bit 0 as in rr_roi_align (1 = direct
- * gather), bit 1 selects the head kernel (0 = tcgen05, 2 = fp32 FFMA).
+ * gather), bit 1 selects the head kernel (0 = tcgen05, 2 = fp32 FFMA), bit 2 (4) = rr_roi_align's algo 2.
  * stage_events: NULL, or 6 cudaEvent_t handles (as void*) recorded on `stream` before decode and
  * after decode, stage-1 NMS, RoIAlign, head and generate_bbox (a per-stage timing hook; recording
  * an event does not synchronise).

@@ -39,6 +39,8 @@
 // The separable order of summation differs from torchvision's sample-by-sample sum at the
 // 1e-7 level (all terms are >= 0 after ReLU, so there is no cancellation); parity is held to
 // 1e-5 relative against the CPU oracle.
+#include <cuda.h>
+
 #include "rr_common.cuh"
 
 namespace rr {
@@ -695,6 +697,245 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 #endif
 }
 
+// --------------------------------------------------------------------------------------------
+// TILE path, step 4 (default when W % 4 == 0): the same tickets, but the tile arrives by TMA.
+//
+// One CTA per SM, 32 warps.  Warp 31 is the producer: it pulls tickets, issues ONE
+// cp.async.bulk.tensor (box 32 x | 32 c | 24 y of a 4-D tensor map whose dimensions are ordered
+// x, c, y, image) per ticket into one of two 96 KB tile buffers and copies the ticket's piece
+// tables next to it; `full` / `empty` mbarriers hand the buffers over, so the load of ticket i+1
+// runs under the evaluation of ticket i and no thread ever issues a tile load or store.
+// Layout in shared memory (SWIZZLE_128B): row (y, c) is 128 bytes = the 32 pixels of one tile row of
+// channel c, rows in (y, c) order, so the 8-row swizzle period runs over c: 16-byte chunk q of row
+// (y, c) sits at chunk q ^ (c & 7).  lane = channel: a quarter warp reading the SAME logical chunk
+// of 8 consecutive channels touches 8 different physical chunks = all 32 banks once: LDS.128 without
+// conflicts, 4 pixels per load.  The price is chunk granularity: a unit reads the aligned chunks
+// covering its columns (weights outside the unit are zero) and the ReLU moves into the evaluation.
+// The 31 consumer warps take (piece, bin column) units from a shared counter and move on to the
+// next ticket on their own (no CTA-wide barrier).
+// --------------------------------------------------------------------------------------------
+constexpr int kT2Threads = 1024;
+constexpr int kT2Consumers = kT2Threads / 32 - 1;
+constexpr int kT2TileBytes = kTC * kTH * kTW * (int)sizeof(float);            // 98304 = one TMA box
+constexpr int kT2TableBytes = kChunk * 2 * 16 + kChunk * kTH * 16;            // descriptors + row weights
+constexpr int kT2Smem = 2 * kT2TileBytes + 2 * kT2TableBytes + 1024;          // + slack to align the tiles to 1024 bytes
+
+__device__ __forceinline__ uint32_t t2_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t2_bar_wait_warp(unsigned long long* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t ok;
+        for (;;) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(t2_saddr(bar)), "r"(parity) : "memory");
+            if (ok) break;
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void t2_bar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(t2_saddr(bar)) : "memory");
+}
+
+// rows of one unit over NQ aligned 16-byte chunks: s(y) = sum_x w[x] relu(f[y][x]), a_ph += wy[ph][y] s(y)
+template <int NQ, bool kRelu>
+__device__ __forceinline__ void unit_rows_q(const float* __restrict__ rowp, const int (&off)[3],
+                                            const float4* __restrict__ s_wy, int nrows, const float (&w)[3][4],
+                                            float& a0, float& a1, float& a2) {
+    const float* p[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) p[j] = rowp + off[j];
+#pragma unroll 2
+    for (int y = 0; y < nrows; ++y) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            float4 v = *reinterpret_cast<const float4*>(p[j]);
+            p[j] += kTC * kTW;
+            if (kRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            s0 = fmaf(w[j][0], v.x, s0);
+            s1 = fmaf(w[j][1], v.y, s1);
+            s0 = fmaf(w[j][2], v.z, s0);
+            s1 = fmaf(w[j][3], v.w, s1);
+        }
+        const float s = s0 + s1;
+        const float4 wy = s_wy[y];                 // warp-uniform address: broadcast
+        a0 = fmaf(wy.x, s, a0);
+        a1 = fmaf(wy.y, s, a1);
+        a2 = fmaf(wy.z, s, a2);
+    }
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kT2Threads, 1)
+roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __restrict__ list,
+                    const float* __restrict__ list_wx, const float4* __restrict__ list_wy,
+                    const int4* __restrict__ items, const int* __restrict__ tile_off,
+                    const int* __restrict__ tile_fill, int* __restrict__ ctl,
+                    int C, TileDims td, float* __restrict__ partial) {
+    extern __shared__ unsigned char s_raw[];
+    __shared__ int s_work[2][4];                   // g, list start, pieces (-1: no more tickets)
+    __shared__ int s_next[2];                      // unit counter of the ticket in buffer b
+    __shared__ unsigned long long s_full[2], s_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* base = s_raw + ((1024u - (t2_saddr(s_raw) & 1023u)) & 1023u);
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_full[b])), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_empty[b])), "r"(kT2Consumers) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kT2Consumers) {
+        // ------------------------------ producer warp ------------------------------
+        const int ngroups = C / kTC;
+        auto fetch = [&](int& g, int& list0, int& n_pieces, int& px0, int& py0, int& img) {   // lane 0
+            const int work = atomicAdd(ctl + kCtlTicket, 1);
+            n_pieces = -1; g = list0 = px0 = py0 = img = 0;
+            if (work < ctl[kCtlItems] * ngroups) {
+                const int4 it = items[work / ngroups];
+                const int t = it.x;
+                img = t / td.tiles_per_img;
+                const int trem = t - img * td.tiles_per_img;
+                const int ty = trem / td.ntx;
+                n_pieces = max(min(it.z, tile_off[t] + tile_fill[t] - it.y), 0);
+                g = work % ngroups; list0 = it.y;
+                px0 = (trem - ty * td.ntx) * kTW; py0 = ty * kTH;
+            }
+        };
+        int g = 0, list0 = 0, n_pieces = -1, px0 = 0, py0 = 0, img = 0;
+        if (lane == 0) fetch(g, list0, n_pieces, px0, py0, img);
+        for (int i = 0;; ++i) {
+            const int b = i & 1;
+            n_pieces = __shfl_sync(0xffffffffu, n_pieces, 0);
+            list0 = __shfl_sync(0xffffffffu, list0, 0);
+            if (i >= 2) t2_bar_wait_warp(&s_empty[b], (uint32_t)(((i >> 1) - 1) & 1));
+            unsigned char* tile = base + b * kT2TileBytes;
+            int4* desc = reinterpret_cast<int4*>(base + 2 * kT2TileBytes + b * kT2TableBytes);
+            float4* wy = reinterpret_cast<float4*>(desc + 2 * kChunk);
+            if (lane == 0) {
+                s_work[b][0] = g; s_work[b][1] = list0; s_work[b][2] = n_pieces; s_next[b] = 0;
+                if (n_pieces >= 0) {
+                    const uint32_t bar = t2_saddr(&s_full[b]);
+                    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(kT2TileBytes) : "memory");
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                                 "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                 ::"r"(t2_saddr(tile)), "l"(&tmap), "r"(px0), "r"(g * kTC), "r"(py0), "r"(img), "r"(bar) : "memory");
+                }
+            }
+            if (n_pieces > 0) {                    // piece tables: 16-byte asynchronous copies, all in flight at once
+                const int4* src_d = list + 2 * (size_t)list0;
+                for (int j = lane; j < 2 * n_pieces; j += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t2_saddr(desc + j)), "l"(src_d + j) : "memory");
+                const float4* src_w = list_wy + (size_t)list0 * kTH;
+                for (int j = lane; j < n_pieces * kTH; j += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t2_saddr(wy + j)), "l"(src_w + j) : "memory");
+            }
+            const int done = n_pieces < 0;
+            if (!done && lane == 0) fetch(g, list0, n_pieces, px0, py0, img);     // next ticket, under the copies
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) t2_bar_arrive(&s_full[b]);
+            if (done) break;
+        }
+        return;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
+    const int k7 = lane & 7;
+    for (int i = 0;; ++i) {
+        const int b = i & 1;
+        t2_bar_wait_warp(&s_full[b], (uint32_t)((i >> 1) & 1));
+        const int n_pieces = s_work[b][2];
+        if (n_pieces < 0) break;
+        const int g = s_work[b][0], list0 = s_work[b][1];
+        const float* tile = reinterpret_cast<const float*>(base + b * kT2TileBytes);
+        const int4* s_desc = reinterpret_cast<const int4*>(base + 2 * kT2TileBytes + b * kT2TableBytes);
+        const float4* s_wy = reinterpret_cast<const float4*>(s_desc + 2 * kChunk);
+        const int n_units = n_pieces * RR_POOL;
+        const float* wxp = list_wx + (size_t)list0 * RR_POOL * kTW + lane;     // unit u: wxp[u * kTW]
+        auto grab = [&]() {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next[b], 1);
+            return __shfl_sync(0xffffffffu, u, 0);
+        };
+        int u = grab();
+        float wxv = u < n_units ? __ldg(wxp + u * kTW) : 0.f;
+        while (u < n_units) {
+            const int ucur = u;
+            const float wcur = wxv;
+            u = grab();                                    // next unit and its column weights, under this unit's rows
+            if (u < n_units) wxv = __ldg(wxp + u * kTW);
+            const int piece = ucur / RR_POOL, pw = ucur - piece * RR_POOL;
+            const int4 d0 = s_desc[2 * piece], d1 = s_desc[2 * piece + 1];
+            const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
+            const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
+            const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
+            // weights re-indexed by tile column: lane x holds the weight of column x (0 outside the unit)
+            float wal = __shfl_sync(0xffffffffu, wcur, (lane - c0) & 31);
+            if (lane < c0 || lane >= c0 + ncols) wal = 0.f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if (ncols > 0) {
+                const float* rowp = tile + (r0 * kTC + lane) * kTW;
+                const float4* wyp = s_wy + piece * kTH;
+                const int q1 = (c0 + ncols - 1) >> 2;
+                for (int q = c0 >> 2; q <= q1; q += 3) {
+                    float w[3][4];
+                    int off[3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        off[j] = (((q + j) & 7) ^ k7) << 2;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) w[j][e] = __shfl_sync(0xffffffffu, wal, (4 * (q + j) + e) & 31);
+                    }
+                    switch (min(q1 - q + 1, 3)) {
+                        case 1: unit_rows_q<1, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
+                        case 2: unit_rows_q<2, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
+                        default: unit_rows_q<3, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
+                    }
+                }
+            }
+            float* po = partial + ((size_t)d0.y * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
+            po[0] = a0;
+            po[(size_t)RR_POOL * C] = a1;
+            po[(size_t)2 * RR_POOL * C] = a2;
+        }
+        __syncwarp();
+        if (lane == 0) t2_bar_arrive(&s_empty[b]);
+    }
+}
+
+// The 4-D tensor map of the feature maps, dimensions ordered (x, c, y, image) so that a box lands in shared
+// memory as [y][c][x].  cuTensorMapEncodeTiled is a host-only driver entry point, resolved through the runtime.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_tile_tmap(const float* feat, int B, int C, int H, int W, CUtensorMap* out) {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    if (!fn || (W & 3) || (reinterpret_cast<uintptr_t>(feat) & 15)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint32_t box[4] = {kTW, kTC, kTH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(feat), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // TILE path, step 5: out[n,c,bin] = (sum over the RoI's pieces, fixed order) / count.
 __global__ void __launch_bounds__(256)
 roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
@@ -800,11 +1041,23 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
         static bool attr_set = false;
         if (!attr_set) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
+            RR_CUDA(cudaFuncSetAttribute(roi_tile_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem), rc);
+            RR_CUDA(cudaFuncSetAttribute(roi_tile_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem), rc);
             attr_set = true;
         }
-        roi_tile_kernel<<<2 * sms_for_persistent(), kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
-                                                                  w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
-                                                                  w.td, w.partial);
+        CUtensorMap tm;
+        if (algo != 2 && make_tile_tmap(feat, B, C, H, W, &tm)) {      // TMA-staged tiles (needs 16-byte rows)
+            if (relu)
+                roi_tile_tma_kernel<true><<<sms_for_persistent(), kT2Threads, kT2Smem, st>>>(
+                    tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial);
+            else
+                roi_tile_tma_kernel<false><<<sms_for_persistent(), kT2Threads, kT2Smem, st>>>(
+                    tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial);
+        } else {                                                        // tiles staged through the load/store path
+            roi_tile_kernel<<<2 * sms_for_persistent(), kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
+                                                                      w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
+                                                                      w.td, w.partial);
+        }
         RR_LAUNCHED(rc);
     }
     if (combine) {
@@ -1049,7 +1302,7 @@ RR_API int rr_roi_align(const float* feat, const float* rois, const int32_t* n_r
                         void* ws, size_t ws_bytes, void* stream) {
     if (n_cap == 0) return 0;
     if (!feat || !rois || !out || !ws) return RR_E_BADARG;
-    if (n_cap < 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0 || algo < 0 || algo > 1) return RR_E_BADARG;
+    if (n_cap < 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0 || algo < 0 || algo > 2) return RR_E_BADARG;
     if (C > 1024) return RR_E_RANGE;                 // roi_combine stages one RoI (C*9 floats) in shared memory
     if (ws_bytes < roi_align_ws_bytes(n_cap, B, C, H, W) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     return roi_align_launch(feat, rois, n_rois_dev, n_cap, B, C, H, W, relu, algo, 1, out, ws, (cudaStream_t)stream);

@@ -215,7 +215,8 @@ def test_stage1_single_class_worst_case(ops, oracle_mod):
 
 
 # ===================================================================== RoIAlign (a6)
-ALGOS = [0, 1]      # 0 = tile-centric kernel (+ direct fallback), 1 = direct gather for every RoI
+ALGOS = [0, 1, 2]   # 0 = tile-centric kernel, TMA-staged tiles when W % 4 == 0 (+ direct fallback), 1 = direct gather for every RoI,
+                    # 2 = tile-centric kernel with tiles staged by ordinary loads
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -265,6 +266,27 @@ def test_roi_align_tile_path_mixed_sizes(ops, oracle_mod):
     out1 = ops.roi_align(dev(feat), dev(rois), algo=1)
     assert rel_err(npy(out), npy(out1), floor=1e-3) < TOL
     assert torch.equal(out, ops.roi_align(dev(feat), dev(rois), algo=0))
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_roi_align_tma_tiles_edge_tiles_and_long_lists(ops, oracle_mod, relu):
+    """W % 4 == 0 -> the TMA-staged tile kernel: partial edge tiles (zero filled by the TMA), W not a multiple of
+    the tile width, tiles with more than 32 pieces (several work items per tile), every column alignment of a
+    unit inside its 16-byte chunks; against the oracle, against the load-staged tile kernel, run to run."""
+    B, C, H, W = 3, 64, 77, 152
+    feat = synth.features(B, C, H, W, 21)
+    rois = _random_rois(900, B, H, W, 22, wh_max=60.0)
+    rois[:300, 1:3] = rois[:300, 1:3] * 0.2 + 30.0                       # crowd one corner: long piece lists
+    rois[:300, 3:] = rois[:300, 1:3] + (rois[:300, 3:] - rois[:300, 3:].floor()) * 25.0 + 1.0
+    rois[7] = torch.tensor([0.0, 31.5, 23.5, 32.5, 24.5])                # straddles a tile corner
+    rois[8] = torch.tensor([2.0, 88.0, 13.0, 151.9, 76.9])               # reaches the map's last column and row
+    rois[9] = torch.tensor([1.0, 140.0, 70.0, 170.0, 90.0])              # hangs over the map edge
+    out = ops.roi_align(dev(feat), dev(rois), relu=relu, algo=0)
+    ref = oracle_mod.roi_align(feat.numpy(), rois.numpy(), relu=relu)
+    assert rel_err(npy(out), ref, floor=1e-3 if relu else 1.0) < TOL
+    out2 = ops.roi_align(dev(feat), dev(rois), relu=relu, algo=2)
+    assert rel_err(npy(out), npy(out2), floor=1e-3 if relu else 1.0) < TOL
+    assert torch.equal(out, ops.roi_align(dev(feat), dev(rois), relu=relu, algo=0))
 
 
 def test_roi_align_channels_not_multiple_of_32_and_slot_overflow(ops, oracle_mod):
