@@ -716,6 +716,7 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 // --------------------------------------------------------------------------------------------
 constexpr int kT2Threads = 1024;
 constexpr int kT2Consumers = kT2Threads / 32 - 1;
+constexpr int kT2Passes = 4;             // unit size classes, handed out largest first
 constexpr int kT2TileBytes = kTC * kTH * kTW * (int)sizeof(float);            // 98304 = one TMA box
 constexpr int kT2TableBytes = kChunk * 2 * 16 + kChunk * kTH * 16;            // descriptors + row weights
 constexpr int kT2Smem = 2 * kT2TileBytes + 2 * kT2TableBytes + 1024;          // + slack to align the tiles to 1024 bytes
@@ -728,6 +729,7 @@ __device__ __forceinline__ void t2_bar_wait_warp(unsigned long long* bar, uint32
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(t2_saddr(bar)), "r"(parity) : "memory");
             if (ok) break;
+            __nanosleep(64);                       // a spinning warp takes issue slots from the evaluating ones
         }
     }
     __syncwarp();
@@ -736,28 +738,41 @@ __device__ __forceinline__ void t2_bar_arrive(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(t2_saddr(bar)) : "memory");
 }
 
+// packed fp32 FMA (SASS FFMA2): the FMA rate of two FFMAs for one issue slot
+__device__ __forceinline__ unsigned long long t2_pack(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ unsigned long long t2_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // rows of one unit over NQ aligned 16-byte chunks: s(y) = sum_x w[x] relu(f[y][x]), a_ph += wy[ph][y] s(y)
 template <int NQ, bool kRelu>
 __device__ __forceinline__ void unit_rows_q(const float* __restrict__ rowp, const int (&off)[3],
-                                            const float4* __restrict__ s_wy, int nrows, const float (&w)[3][4],
+                                            const float4* __restrict__ s_wy, int nrows, const ulonglong2 (&w)[3],
                                             float& a0, float& a1, float& a2) {
     const float* p[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) p[j] = rowp + off[j];
 #pragma unroll 2
     for (int y = 0; y < nrows; ++y) {
-        float s0 = 0.f, s1 = 0.f;
+        unsigned long long s01 = 0ull, s23 = 0ull;
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
             float4 v = *reinterpret_cast<const float4*>(p[j]);
             p[j] += kTC * kTW;
             if (kRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            s0 = fmaf(w[j][0], v.x, s0);
-            s1 = fmaf(w[j][1], v.y, s1);
-            s0 = fmaf(w[j][2], v.z, s0);
-            s1 = fmaf(w[j][3], v.w, s1);
+            s01 = t2_fma2(w[j].x, t2_pack(v.x, v.y), s01);
+            s23 = t2_fma2(w[j].y, t2_pack(v.z, v.w), s23);
         }
-        const float s = s0 + s1;
+        float sx, sy, sz, sw;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(s01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sz), "=f"(sw) : "l"(s23));
+        const float s = (sx + sz) + (sy + sw);
         const float4 wy = s_wy[y];                 // warp-uniform address: broadcast
         a0 = fmaf(wy.x, s, a0);
         a1 = fmaf(wy.y, s, a1);
@@ -775,7 +790,9 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
     extern __shared__ unsigned char s_raw[];
     __shared__ int s_work[2][4];                   // g, list start, pieces (-1: no more tickets)
     __shared__ int s_next[2];                      // unit counter of the ticket in buffer b
+    __shared__ unsigned char s_order[2][kChunk * RR_POOL];     // the ticket's units, largest size class first
     __shared__ unsigned long long s_full[2], s_empty[2];
+    __shared__ __align__(16) float s_wal[kT2Consumers][kTW];   // per consumer warp: the current unit's column weights
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char* base = s_raw + ((1024u - (t2_saddr(s_raw) & 1023u)) & 1023u);
     if (tid == 0) {
@@ -791,27 +808,41 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
 
     if (warp == kT2Consumers) {
         // ------------------------------ producer warp ------------------------------
+        // Tickets are pulled in blocks of `blk` consecutive ones = the same work item for blk channel groups: one
+        // chain of dependent loads (ticket counter -> item -> list fill) per block instead of per ticket, and the
+        // item's piece tables, already in a buffer from the block's earlier ticket, are not copied again.
         const int ngroups = C / kTC;
-        auto fetch = [&](int& g, int& list0, int& n_pieces, int& px0, int& py0, int& img) {   // lane 0
-            const int work = atomicAdd(ctl + kCtlTicket, 1);
-            n_pieces = -1; g = list0 = px0 = py0 = img = 0;
-            if (work < ctl[kCtlItems] * ngroups) {
-                const int4 it = items[work / ngroups];
+        const int blk = (ngroups & 3) == 0 ? 4 : ((ngroups & 1) == 0 ? 2 : 1);
+        const int n_tickets = ctl[kCtlItems] * ngroups;
+        int work0 = 0, g0 = 0, list0 = 0, n_pieces = -1, px0 = 0, py0 = 0, img = 0;
+        auto fetch = [&]() {                       // lane 0
+            work0 = atomicAdd(ctl + kCtlTicket, blk);
+            n_pieces = -1; g0 = list0 = px0 = py0 = img = 0;
+            if (work0 < n_tickets) {
+                const int4 it = items[work0 / ngroups];
                 const int t = it.x;
                 img = t / td.tiles_per_img;
                 const int trem = t - img * td.tiles_per_img;
                 const int ty = trem / td.ntx;
                 n_pieces = max(min(it.z, tile_off[t] + tile_fill[t] - it.y), 0);
-                g = work % ngroups; list0 = it.y;
+                g0 = work0 % ngroups; list0 = it.y;
                 px0 = (trem - ty * td.ntx) * kTW; py0 = ty * kTH;
             }
         };
-        int g = 0, list0 = 0, n_pieces = -1, px0 = 0, py0 = 0, img = 0;
-        if (lane == 0) fetch(g, list0, n_pieces, px0, py0, img);
+        int pos = blk, tables_of[2] = {-1, -1};
         for (int i = 0;; ++i) {
             const int b = i & 1;
-            n_pieces = __shfl_sync(0xffffffffu, n_pieces, 0);
-            list0 = __shfl_sync(0xffffffffu, list0, 0);
+            if (pos == blk) {
+                if (lane == 0) fetch();
+                n_pieces = __shfl_sync(0xffffffffu, n_pieces, 0);
+                list0 = __shfl_sync(0xffffffffu, list0, 0);
+                work0 = __shfl_sync(0xffffffffu, work0, 0);
+                pos = 0;
+            }
+            const int g = g0 + pos;
+            ++pos;
+            const bool new_tables = n_pieces > 0 && tables_of[b] != work0;
+            tables_of[b] = work0;
             if (i >= 2) t2_bar_wait_warp(&s_empty[b], (uint32_t)(((i >> 1) - 1) & 1));
             unsigned char* tile = base + b * kT2TileBytes;
             int4* desc = reinterpret_cast<int4*>(base + 2 * kT2TileBytes + b * kT2TableBytes);
@@ -826,7 +857,7 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                                  ::"r"(t2_saddr(tile)), "l"(&tmap), "r"(px0), "r"(g * kTC), "r"(py0), "r"(img), "r"(bar) : "memory");
                 }
             }
-            if (n_pieces > 0) {                    // piece tables: 16-byte asynchronous copies, all in flight at once
+            if (new_tables) {                      // piece tables: 16-byte asynchronous copies, all in flight at once
                 const int4* src_d = list + 2 * (size_t)list0;
                 for (int j = lane; j < 2 * n_pieces; j += 32)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t2_saddr(desc + j)), "l"(src_d + j) : "memory");
@@ -834,12 +865,44 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                 for (int j = lane; j < n_pieces * kTH; j += 32)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(t2_saddr(wy + j)), "l"(src_w + j) : "memory");
             }
-            const int done = n_pieces < 0;
-            if (!done && lane == 0) fetch(g, list0, n_pieces, px0, py0, img);     // next ticket, under the copies
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
+            if (new_tables) {                      // order the units by size class (rows x chunks), largest first
+                const int n_units = n_pieces * RR_POOL;
+                int cls[RR_POOL], cnt[kT2Passes];
+#pragma unroll
+                for (int k = 0; k < kT2Passes; ++k) cnt[k] = 0;
+#pragma unroll
+                for (int r = 0; r < RR_POOL; ++r) {
+                    const int u = r * 32 + lane;
+                    cls[r] = kT2Passes;
+                    if (u < n_units) {
+                        const int piece = u / RR_POOL, pw = u - piece * RR_POOL;
+                        const int4 d0 = desc[2 * piece], d1 = desc[2 * piece + 1];
+                        const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
+                        const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
+                        const int size = ((d0.z >> 8) & 0xff) * (ncols > 0 ? ((c0 + ncols - 1) >> 2) - (c0 >> 2) + 1 : 0);
+                        cls[r] = size >= 48 ? 0 : (size >= 24 ? 1 : (size >= 10 ? 2 : 3));
+                    }
+#pragma unroll
+                    for (int k = 0; k < kT2Passes; ++k) cnt[k] += __popc(__ballot_sync(0xffffffffu, cls[r] == k));
+                }
+                int off[kT2Passes];
+                off[0] = 0;
+#pragma unroll
+                for (int k = 1; k < kT2Passes; ++k) off[k] = off[k - 1] + cnt[k - 1];
+#pragma unroll
+                for (int r = 0; r < RR_POOL; ++r)
+#pragma unroll
+                    for (int k = 0; k < kT2Passes; ++k) {
+                        const unsigned m = __ballot_sync(0xffffffffu, cls[r] == k);
+                        if (cls[r] == k) s_order[b][off[k] + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(r * 32 + lane);
+                        off[k] += __popc(m);
+                    }
+                __syncwarp();
+            }
             if (lane == 0) t2_bar_arrive(&s_full[b]);
-            if (done) break;
+            if (n_pieces < 0) break;
         }
         return;
     }
@@ -857,39 +920,46 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
         const float4* s_wy = reinterpret_cast<const float4*>(s_desc + 2 * kChunk);
         const int n_units = n_pieces * RR_POOL;
         const float* wxp = list_wx + (size_t)list0 * RR_POOL * kTW + lane;     // unit u: wxp[u * kTW]
-        auto grab = [&]() {
+        // Units are handed out largest first (the producer warp has ordered them by size class): the buffer can
+        // only be refilled when its last unit is done, so the stragglers should be the small ones.
+        auto next_unit = [&]() {
             int u = 0;
             if (lane == 0) u = atomicAdd(&s_next[b], 1);
-            return __shfl_sync(0xffffffffu, u, 0);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            return u < n_units ? (int)s_order[b][u] : n_units;
         };
-        int u = grab();
+        int u = next_unit();
         float wxv = u < n_units ? __ldg(wxp + u * kTW) : 0.f;
         while (u < n_units) {
             const int ucur = u;
             const float wcur = wxv;
-            u = grab();                                    // next unit and its column weights, under this unit's rows
+            u = next_unit();                               // next unit and its column weights, under this unit's rows
             if (u < n_units) wxv = __ldg(wxp + u * kTW);
             const int piece = ucur / RR_POOL, pw = ucur - piece * RR_POOL;
             const int4 d0 = s_desc[2 * piece], d1 = s_desc[2 * piece + 1];
             const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
             const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
             const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
-            // weights re-indexed by tile column: lane x holds the weight of column x (0 outside the unit)
+            // weights re-indexed by tile column (0 outside the unit) -> the warp's scratch row: a chunk's four
+            // weights come back as one broadcast 128-bit read
             float wal = __shfl_sync(0xffffffffu, wcur, (lane - c0) & 31);
             if (lane < c0 || lane >= c0 + ncols) wal = 0.f;
+            __syncwarp();
+            s_wal[warp][lane] = wal;
+            __syncwarp();
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             if (ncols > 0) {
                 const float* rowp = tile + (r0 * kTC + lane) * kTW;
                 const float4* wyp = s_wy + piece * kTH;
+                const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(s_wal[warp]);
                 const int q1 = (c0 + ncols - 1) >> 2;
                 for (int q = c0 >> 2; q <= q1; q += 3) {
-                    float w[3][4];
+                    ulonglong2 w[3];
                     int off[3];
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         off[j] = (((q + j) & 7) ^ k7) << 2;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) w[j][e] = __shfl_sync(0xffffffffu, wal, (4 * (q + j) + e) & 31);
+                        w[j] = wq[(q + j) & 7];
                     }
                     switch (min(q1 - q + 1, 3)) {
                         case 1: unit_rows_q<1, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
