@@ -596,7 +596,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-aux", action="store_true", help="skip the reference-CUDA leg and the aux kernel timings")
     ap.add_argument("--head-algo", type=int, default=0, help="0 tcgen05 tensor-core head (default), 1 fp32 FFMA head")
-    ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign (default), 1 direct gather")
+    ap.add_argument("--roi-algo", type=int, default=0, help="0 tile-centric RoIAlign with TMA-staged tiles (default), 1 direct gather, 4 tile-centric with load-staged tiles")
     ap.add_argument("--streams", type=int, default=2, help="batches in flight (steps alternate between that many streams)")
     ap.add_argument("--sm-reserve", type=int, default=8, help="SMs the persistent kernels leave free when --streams > 1")
     args = ap.parse_args()

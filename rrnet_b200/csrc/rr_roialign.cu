@@ -19,11 +19,12 @@
 //  * TILE path (default).  The RoI windows of a detector's top-K boxes overlap heavily (4.5x at
 //    config 2: 5.3 GB of window bytes over a 1.07 GB map), so gathering per RoI is bound by L2,
 //    not HBM.  Instead the map is cut into 32x24-pixel tiles; a work item is (tile, 32 channels,
-//    <= 32 RoI pieces).  A persistent CTA stages the tile once from HBM into shared memory
-//    (coalesced 128-byte rows, ReLU applied on the way in, channel stride odd so that
-//    lane = channel reads are bank-conflict free) and every warp then evaluates (piece, bin
+//    <= 32 RoI pieces).  A persistent CTA brings the tile once from HBM into shared memory - by
+//    ONE TMA tensor copy per tile into a swizzled [y][c][x] layout (roi_tile_tma_kernel, the
+//    default), or with coalesced 128-byte row loads, ReLU on the way in and an odd channel stride
+//    (roi_tile_kernel: W % 4 != 0, or algo = 2) - and every warp then evaluates (piece, bin
 //    column) units with lane = channel: no cross-lane reduction, all 32 lanes busy whatever the
-//    piece shape, weights warp-uniform.  Pieces of one RoI land in private partial slots
+//    piece shape, weights warp-uniform, bank-conflict free in both layouts.  Pieces of one RoI land in private partial slots
 //    ([slot][9][C], coalesced stores) and a combine kernel adds them in a fixed order, so the
 //    result is deterministic (no floating-point atomics).  Each feature element is read from
 //    HBM once per step (tiles without RoIs are never read).
@@ -726,10 +727,11 @@ __device__ __forceinline__ void t2_bar_wait_warp(unsigned long long* bar, uint32
     if ((threadIdx.x & 31) == 0) {
         uint32_t ok;
         for (;;) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok) : "r"(t2_saddr(bar)), "r"(parity) : "memory");
+            // suspend-time hint: the thread sleeps in hardware until the phase completes (or ~1 us passes) instead of
+            // polling - a spinning warp takes issue slots from the evaluating ones
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(t2_saddr(bar)), "r"(parity), "r"(1000u) : "memory");
             if (ok) break;
-            __nanosleep(64);                       // a spinning warp takes issue slots from the evaluating ones
         }
     }
     __syncwarp();

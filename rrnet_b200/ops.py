@@ -154,7 +154,8 @@ def soft_nms_batched(boxes5, seg_offsets, sigma=0.5, Nt=0.3, threshold=0.001, me
 # --------------------------------------------------------------------------------- RoIAlign / head / bbox
 def roi_align(feat, rois, n_dev=None, relu=True, algo=0):
     """torchvision.ops.roi_align(relu(feat), rois, (3,3)) (models/rrnet.py:51) -> [n,C,3,3].
-    algo 0 = tile-centric kernel (default), 1 = direct per-RoI gather."""
+    algo 0 = tile-centric kernel (default; tiles arrive by TMA when W % 4 == 0), 1 = direct per-RoI gather,
+    2 = tile-centric kernel with tiles staged by ordinary loads."""
     feat, rois = _f32(feat, "feat", 4), _f32(rois, "rois", 2)
     B, C, H, W = feat.shape
     n = rois.shape[0]
@@ -269,7 +270,7 @@ class EvalPath:
         dev = torch.device(device if device is not None else "cuda")
         self.shape = (B, C, H, W, K, feat_ch)
         self.pool, self.nms_thr, self.scale = int(pool), float(nms_thr), float(scale)
-        self.roi_algo = int(roi_algo) | (int(head_algo) << 1)     # bit 0: direct RoIAlign, bit 1: FFMA head
+        self.roi_algo = int(roi_algo) | (int(head_algo) << 1)     # bit 0: direct RoIAlign, bit 2 (roi_algo=4): load-staged tiles, bit 1: FFMA head
         self.folded = _f32(head_folded, "head_folded")
         n = B * K
         f32 = dict(dtype=torch.float32, device=dev)
