@@ -701,7 +701,7 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 // --------------------------------------------------------------------------------------------
 // TILE path, step 4 (default when W % 4 == 0): the same tickets, but the tile arrives by TMA.
 //
-// One CTA per SM, 32 warps.  Warp 31 is the producer: it pulls tickets, issues ONE
+// One CTA per SM, 23 warps.  The last warp is the producer: it pulls tickets, issues ONE
 // cp.async.bulk.tensor (box 32 x | 32 c | 24 y of a 4-D tensor map whose dimensions are ordered
 // x, c, y, image) per ticket into one of two 96 KB tile buffers and copies the ticket's piece
 // tables next to it; `full` / `empty` mbarriers hand the buffers over, so the load of ticket i+1
@@ -712,10 +712,17 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 // of 8 consecutive channels touches 8 different physical chunks = all 32 banks once: LDS.128 without
 // conflicts, 4 pixels per load.  The price is chunk granularity: a unit reads the aligned chunks
 // covering its columns (weights outside the unit are zero) and the ReLU moves into the evaluation.
-// The 31 consumer warps take (piece, bin column) units from a shared counter and move on to the
+// The 22 consumer warps take (piece, bin column) units from a shared counter and move on to the
 // next ticket on their own (no CTA-wide barrier).
 // --------------------------------------------------------------------------------------------
-constexpr int kT2Threads = 1024;
+#ifndef RR_T2_THREADS
+#define RR_T2_THREADS 736    // 22 consumer warps + the producer.  Measured (RoIAlign stage, ms): 416: 0.557, 480: 0.538,
+#endif                       // 544: 0.524, 608: 0.518, 672: 0.513, 736: 0.512, 800 (spills): 0.534, 1024 (64 registers): 0.533
+#ifndef RR_T2_UNROLL
+#define RR_T2_UNROLL 2       // rows per iteration of the unit loop (3 and 4 were not faster at 544 - 672 threads)
+#endif
+constexpr int kT2Threads = RR_T2_THREADS;
+constexpr int kT2Unroll = RR_T2_UNROLL;
 constexpr int kT2Consumers = kT2Threads / 32 - 1;
 constexpr int kT2Passes = 4;             // unit size classes, handed out largest first
 constexpr int kT2TileBytes = kTC * kTH * kTW * (int)sizeof(float);            // 98304 = one TMA box
@@ -760,7 +767,7 @@ __device__ __forceinline__ void unit_rows_q(const float* __restrict__ rowp, cons
     const float* p[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) p[j] = rowp + off[j];
-#pragma unroll 2
+#pragma unroll kT2Unroll
     for (int y = 0; y < nrows; ++y) {
         unsigned long long s01 = 0ull, s23 = 0ull;
 #pragma unroll
