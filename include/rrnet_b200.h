@@ -52,7 +52,7 @@ const char* rr_error_string(int code);
 uint64_t    rr_launch_count(void);
 /* Number of SMs (0..147, default 0) that the persistent kernels (tile RoIAlign, tensor-core head) leave free, so that
  * the short latency-bound kernels of ANOTHER batch on another stream can run next to them (bench.py --streams 2).
- * Process-wide; takes effect at the next launch / graph capture. */
+ * Per calling host thread (thread-local); read when that thread issues / captures the next launch. */
 int         rr_set_sm_reserve(int n_sms);
 
 /* ------------------------------------------------------------------------------------------

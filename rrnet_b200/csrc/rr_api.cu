@@ -7,7 +7,7 @@
 namespace rr {
 
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_sm_reserve{0};
+thread_local int g_sm_reserve = 0;
 
 // implemented in the per-kernel translation units
 int decode_launch(const float*, const float*, const float*, int, int, int, int, int, int, float*, int64_t*,
@@ -48,7 +48,7 @@ RR_API int rr_version(void) { return 100; }
 RR_API uint64_t rr_launch_count(void) { return g_launches.load(); }
 RR_API int rr_set_sm_reserve(int n_sms) {
     if (n_sms < 0 || n_sms >= kSMs) return RR_E_BADARG;
-    g_sm_reserve.store(n_sms);
+    g_sm_reserve = n_sms;
     return 0;
 }
 

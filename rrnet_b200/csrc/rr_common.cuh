@@ -27,8 +27,23 @@ extern std::atomic<uint64_t> g_launches;   // defined in rr_api.cu
     } while (0)
 
 constexpr int kSMs = 148;   // B200
-extern std::atomic<int> g_sm_reserve;      // SMs the persistent kernels leave free (rr_set_sm_reserve), defined in rr_api.cu
-inline int sms_for_persistent() { const int r = g_sm_reserve.load(std::memory_order_relaxed); return kSMs - (r < 0 ? 0 : (r > kSMs - 1 ? kSMs - 1 : r)); }
+// SMs the persistent kernels leave free (rr_set_sm_reserve).  Per calling host thread: the value is read when a
+// launch is issued (or captured into a graph) by that thread, so two threads driving two streams do not interfere.
+extern thread_local int g_sm_reserve;      // defined in rr_api.cu
+inline int sms_for_persistent() { const int r = g_sm_reserve; return kSMs - (r < 0 ? 0 : (r > kSMs - 1 ? kSMs - 1 : r)); }
+
+// Function attributes (e.g. the dynamic shared memory opt-in) are per device: do `first-use` work once per device
+// of the process.  Two racing threads may both do it, which is harmless (the calls are idempotent).
+struct OncePerDevice {
+    std::atomic<uint64_t> done[4]{};          // up to 256 devices
+    bool need(int* dev_out) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) { *dev_out = -1; return true; }
+        *dev_out = d;
+        return !(done[d >> 6].load(std::memory_order_acquire) & (1ull << (d & 63)));
+    }
+    void mark(int d) { if (d >= 0) done[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release); }
+};
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 

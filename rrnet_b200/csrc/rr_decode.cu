@@ -494,11 +494,11 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     dim3 gc((unsigned)per_img, (unsigned)B);
     decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
     RR_LAUNCHED(rc);
-    static bool attr_set = false;
+    static OncePerDevice attr_once; int attr_dev;
     const size_t smem = (size_t)kCap * sizeof(unsigned long long);
-    if (!attr_set) {
+    if (attr_once.need(&attr_dev)) {
         RR_CUDA(cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
-        attr_set = true;
+        if (rc == 0) attr_once.mark(attr_dev);
     }
     decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
                                                          out_dets, (long long*)out_inds);

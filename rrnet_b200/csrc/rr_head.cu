@@ -271,10 +271,10 @@ head_forward_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
 int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded,
                          float* reg, cudaStream_t st) {
     int rc = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr_once; int attr_dev;
+    if (attr_once.need(&attr_dev)) {
         RR_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem), rc);
-        attr_set = true;
+        if (rc == 0) attr_once.mark(attr_dev);
     }
     const int grid = (n_cap + kHeadWarps - 1) / kHeadWarps;
     head_forward_kernel<<<grid, kHeadThreads, kHeadSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);

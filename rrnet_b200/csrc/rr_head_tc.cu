@@ -710,10 +710,10 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
 
 int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded, float* reg, cudaStream_t st) {
     int rc = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr_once; int attr_dev;
+    if (attr_once.need(&attr_dev)) {
         RR_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem), rc);
-        attr_set = true;
+        if (rc == 0) attr_once.mark(attr_dev);
     }
     if (((uintptr_t)folded & 15) != 0) return RR_E_BADARG;     // the weight stream is copied in 16-byte units
     if (src.partial && !src.scratch) return RR_E_BADARG;

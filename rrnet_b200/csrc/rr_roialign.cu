@@ -1117,12 +1117,12 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
         roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
         RR_LAUNCHED(rc);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static OncePerDevice attr_once; int attr_dev;
+        if (attr_once.need(&attr_dev)) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
             RR_CUDA(cudaFuncSetAttribute(roi_tile_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem), rc);
             RR_CUDA(cudaFuncSetAttribute(roi_tile_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2Smem), rc);
-            attr_set = true;
+            if (rc == 0) attr_once.mark(attr_dev);
         }
         CUtensorMap tm;
         if (algo != 2 && make_tile_tmap(feat, B, C, H, W, &tm)) {      // TMA-staged tiles (needs 16-byte rows)
@@ -1352,10 +1352,10 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
         roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
         RR_LAUNCHED(rc);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static OncePerDevice attr_once; int attr_dev;
+        if (attr_once.need(&attr_dev)) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), rc);
-            attr_set = true;
+            if (rc == 0) attr_once.mark(attr_dev);
         }
         roi_tile_bwd_kernel<<<w.n_tiles * (C / kTC), kBwdThreads, kBwdSmem, st>>>(feat, grad_out, w.list, w.list_wx, w.list_wy,
                                                                               w.cnt, w.tile_off, w.tile_fill, C, H, W, relu,

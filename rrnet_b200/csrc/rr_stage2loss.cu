@@ -49,15 +49,20 @@ stage2_loss_kernel(const float* __restrict__ bxyxy, const int* __restrict__ seg,
         const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
         best = -1.f;
         arg = 0;
+        bool nan_seen = false;
         for (int k = 0; k < max_n; ++k) {
             const float gx1 = s_gt[4 * k], gy1 = s_gt[4 * k + 1], gx2 = s_gt[4 * k + 2], gy2 = s_gt[4 * k + 3];
             const float iw = fmaxf(__fsub_rn(fminf(x2, gx2), fmaxf(x1, gx1)), 0.f);
             const float ih = fmaxf(__fsub_rn(fminf(y2, gy2), fmaxf(y1, gy1)), 0.f);
             const float inter = __fmul_rn(iw, ih);
             const float ga = __fmul_rn(__fsub_rn(gx2, gx1), __fsub_rn(gy2, gy1));
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, ga), inter));   // 0/0 = NaN never wins
+            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, ga), inter));
+            nan_seen |= iou != iou;                               // 0/0: zero-area RoI against a zero-padded gt row
             if (iou > best) { best = iou; arg = k; }              // first maximum, like torch.max
         }
+        // torch.max propagates NaN: the reference's max_iou of such a row is NaN and `NaN > 0.5` makes it a negative
+        // (rrnet_operator.py:73-74).  Same decision here; `arg` of a negative row is never used.
+        if (nan_seen) best = __int_as_float(0x7fc00000);
     };
     int n_pos = 0;
     {
@@ -138,10 +143,10 @@ RR_API int rr_stage2_loss(const float* bxyxy, const int32_t* seg_offsets, const 
     const size_t smem = sizeof(float) * 4 * (size_t)max_n;
     if (smem > 200 * 1024) return RR_E_BADARG;
     int rc = 0;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    static OncePerDevice attr_once; int attr_dev;
+    if (attr_once.need(&attr_dev) && smem > 48 * 1024) {
         RR_CUDA(cudaFuncSetAttribute(stage2_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), rc);
-        attr_set = true;
+        if (rc == 0) attr_once.mark(attr_dev);
     }
     stage2_loss_kernel<<<B, kS2Threads, smem, (cudaStream_t)stream>>>(bxyxy, seg_offsets, s2_reg, gt_xyxy, max_n, gt_stride,
                                                                       scale, 1.0f / (float)B, grad_scale, loss_parts,

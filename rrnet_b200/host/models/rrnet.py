@@ -51,11 +51,11 @@ class RRNet(nn.Module):
             and self.nms_per_class and feat.size(1) == 256
         if fused:
             # decode -> per-class NMS -> RoIAlign(+ReLU) -> head in one C-ABI call, one host sync for N
-            B, C, H, W = hms[-1].shape
-            path = ops.EvalPath(B, C, H, W, k, self.head_detector.folded(), device=feat.device)
+            path = self._eval_path(hms[-1].shape, k, feat.device)
             path.forward(hms[-1], whs[-1], offsets[-1], feat)
             r = path.results()
-            return hms, whs, offsets, r["reg"], r["bxyxy"], r["scores"], r["clses"]
+            # the path's buffers are reused by the next forward of the same shape: hand out copies (a few hundred KB)
+            return hms, whs, offsets, r["reg"].clone(), r["bxyxy"].clone(), r["scores"].clone(), r["clses"].clone()
         bboxs = self.transform_bbox(hms[-1], whs[-1], offsets[-1], k)     # (bs, k, 6)
         bxyxys, scores, clses = [], [], []
         for b_idx in range(bboxs.size(0)):
@@ -71,6 +71,25 @@ class RRNet(nn.Module):
         roi_feat = _RoIAlignReLU.apply(feat, bxyxys)
         stage2_reg = self.forward_stage2(roi_feat)
         return hms, whs, offsets, stage2_reg, bxyxys, scores, clses
+
+    _EVAL_PATH_SLOTS = 8          # multi-scale test: one pre-allocated path per scale (cfg.Val.scales has 6)
+
+    def _eval_path(self, hm_shape, k, device):
+        """Pre-allocated outputs + workspace per (B,C,H,W,k,device), reused across forwards (least recently used one
+        dropped beyond _EVAL_PATH_SLOTS); only the folded head weights are refreshed (they follow the parameters'
+        versions, FasterRCNNDetector.folded)."""
+        cache = self.__dict__.setdefault('_eval_paths', {})
+        key = (tuple(hm_shape), int(k), str(device))
+        path = cache.pop(key, None)
+        folded = self.head_detector.folded()
+        if path is None:
+            B, C, H, W = hm_shape
+            path = ops.EvalPath(B, C, H, W, k, folded, device=device)
+            while len(cache) >= self._EVAL_PATH_SLOTS:
+                cache.pop(next(iter(cache)))
+        path.folded = folded
+        cache[key] = path                      # re-inserted last = most recently used
+        return path
 
     # ------------------------------------------------------------------ models/rrnet.py:56-80
     def nms(self, bbox):

@@ -3,13 +3,18 @@
 Hot-path members: criterion's heat-map loss (:55-57, fused sigmoid+clamp+focal fwd/bwd),
 generate_bbox (:188-209), _ext_nms (:211-232, Gaussian soft-NMS on the GPU), plus save_result and the
 static generate_bbox_target.  The training / evaluation loops are the callers of the path: they follow
-the reference step for step but take the model, loaders and optimiser as constructor arguments (the
-dataset, backbone and logging code are outside this repo)."""
+the reference step for step; `RRNetOperator(cfg)` builds model / optimiser / scheduler / loaders / DDP from the
+configuration like the reference's constructor (the dataset, backbone and logging code are the reference's own
+modules, imported from sys.path), or takes them as constructor arguments."""
 import os
+import random
 
 import numpy as np
 import torch
+import torch.nn as nn
 import torch.nn.functional as F
+import torch.optim as optim
+from torch.nn.parallel import DistributedDataParallel
 
 from rrnet_b200 import ops
 from ..modules.loss.focalloss import FocalLossHM
@@ -35,9 +40,43 @@ class _Stage2LossFn(torch.autograd.Function):
 
 
 class RRNetOperator(object):
+    """`RRNetOperator(cfg)` builds everything from the configuration exactly like the reference
+    (operators/rrnet_operator.py:23-40 + operators/base_operator.py:11-26): seeds, RRNet(cfg) on
+    cfg.Distributed.gpu_id, SyncBatchNorm conversion, Adam, MultiStepLR, make_dataloader(cfg, collate_fn='rrnet'),
+    DistributedDataParallel(find_unused_parameters=True).  That is what DistributedWrapper.init_operator
+    (operators/distributed_wrapper.py:28-45) calls, so train.py / eval.py run unchanged after dropin.install().
+    Every piece can also be passed in (tests, other harnesses); a piece that is passed in is used as it is."""
+
     def __init__(self, cfg, model=None, optimizer=None, lr_sch=None, training_loader=None,
                  validation_loader=None, logger=None):
         self.cfg = cfg
+        dist_cfg = getattr(cfg, "Distributed", None)
+        gpu_id = getattr(dist_cfg, "gpu_id", 0)
+        built = model is None
+        if built:
+            from ..models.rrnet import RRNet
+            model = RRNet(cfg).cuda(gpu_id)                                         # :26
+            model = nn.SyncBatchNorm.convert_sync_batchnorm(model)                  # :27
+        if optimizer is None and built:
+            optimizer = optim.Adam(model.parameters(), lr=cfg.Train.lr)             # :29
+        if lr_sch is None and optimizer is not None and built:
+            lr_sch = optim.lr_scheduler.MultiStepLR(optimizer, milestones=cfg.Train.lr_milestones, gamma=0.1)   # :31
+        if built and training_loader is None and validation_loader is None:
+            from datasets import make_dataloader                                    # the reference's package (sys.path)
+            training_loader, validation_loader = make_dataloader(cfg, collate_fn='rrnet')   # :32
+        if built:
+            # base_operator.py:19-24
+            seed = getattr(cfg, "seed", None)
+            if seed is not None:
+                random.seed(seed)
+                torch.manual_seed(seed)
+                torch.cuda.manual_seed(seed)
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                model = DistributedDataParallel(model, find_unused_parameters=True, device_ids=[gpu_id])
+            else:
+                # the reference always runs under DistributedWrapper (a process group exists); without one the
+                # model is used bare -- `self.model.module` below goes through _unwrap() for that reason
+                pass
         self.model = model
         self.optimizer = optimizer
         self.lr_sch = lr_sch
@@ -46,8 +85,15 @@ class RRNetOperator(object):
         self.logger = logger
         self.hm_focal_loss = FocalLossHM()
         self.l1_loss = RegL1Loss()
-        dist_cfg = getattr(cfg, "Distributed", None)
-        self.main_proc_flag = getattr(dist_cfg, "gpu_id", 0) == 0
+        self.main_proc_flag = gpu_id == 0
+
+    def _unwrap(self):
+        return getattr(self.model, 'module', self.model)
+
+    @staticmethod
+    def save_ckp(models, step, path):
+        """base_operator.py:44-51."""
+        torch.save(models.state_dict(), os.path.join(path, 'ckp-{}.pth'.format(step)))
 
     # ------------------------------------------------------------------ rrnet_operator.py:42-84
     def criterion(self, outs, targets):
@@ -136,35 +182,92 @@ class RRNetOperator(object):
         np.savetxt(file_path, table, fmt=['%f', '%f', '%f', '%f', '%.4f', '%d', '%d', '%d'], delimiter=',')
 
     # ------------------------------------------------------------------ rrnet_operator.py:104-186
+    def _make_logger(self):
+        """The reference builds `Logger(cfg)` on the main process (:105-106); its module is used when importable
+        (tensorboard + ./log/<prefix>/log.txt).  A logger passed to the constructor wins."""
+        if self.logger is not None or not self.main_proc_flag:
+            return self.logger
+        try:
+            from utils.vis.logger import Logger                        # reference module (sys.path)
+        except ImportError:
+            return None
+        return Logger(self.cfg)
+
+    def _targets_on_device(self, imgs, annos, gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks):
+        """A batch from the reference's CPU `ToHeatmap` is used as it is.  A batch from `DeferredToHeatmap`
+        (dropin.install(gpu_targets=True): the worker only counted the objects) carries an empty heat-map: the
+        targets are rendered here, on the device, from the collated annotations (one `rr_render_targets` launch)."""
+        if gt_hms.numel() != 0:
+            return gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks
+        from ..datasets.transforms.functional import to_heatmap_batch
+        n_obj = gt_reg_masks.reshape(gt_reg_masks.size(0), -1).sum(1).int().contiguous()
+        return to_heatmap_batch(annos.float().contiguous(), n_obj, imgs.size(2), imgs.size(3),
+                                self.cfg.Train.scale_factor, self.cfg.num_classes)
+
+    def _log_images(self, outs, imgs, annos):
+        """:159-175 -- three pictures of image 0 (stage-1 boxes, stage-2 boxes after soft-NMS, ground truth) through the
+        reference's own drawing code; skipped when that code cannot be imported (cv2 / matplotlib missing)."""
+        try:
+            from datasets.transforms.functional import denormalize
+            from utils.vis.annotations import visualize
+        except ImportError:
+            return None
+        s1_pred_bbox, s2_pred_bbox = self.generate_bbox(outs, batch_idx=0)
+        img = (denormalize(imgs[0].cpu()).permute(1, 2, 0).cpu().numpy() * 255).astype(np.uint8)
+        s2_pred_bbox = self._ext_nms(s2_pred_bbox)
+        pics = [visualize(img.copy(), s1_pred_bbox.detach().cpu(), xywh=True, with_score=True),
+                visualize(img.copy(), s2_pred_bbox, xywh=True, with_score=True),
+                visualize(img.copy(), annos[0, :, :6].cpu(), xywh=False)]
+        return {'Train': [torch.from_numpy(p).permute(2, 0, 1).unsqueeze(0).float() / 255. for p in pics]}
+
     def training_process(self):
-        """forward -> criterion -> loss = hm + 0.1 wh + off + s2 (s2 only from step 2000 on, Appendix A.6) -> backward ->
-        optimiser step, with the scheduler stepped first like the reference (:117).  Running means of the five numbers
-        go to `logger` every cfg.Train.print_interval steps; image logging and checkpoints are the caller's."""
+        """:104-186 step for step: scheduler first (:117), zero_grad, batch (an out-of-memory batch is skipped, :120-126),
+        forward, criterion, loss = hm + 0.1 wh + off + s2 * (step >= 2000) (:132-136), backward, optimiser step; on the main
+        process running means + learning rate (+ pictures) go to the logger every cfg.Train.print_interval steps and a
+        checkpoint of model.module is written every cfg.Train.checkpoint_interval steps and after the last one (:184-186)."""
+        logger = self._make_logger()
         self.model.train()
         names = ('total_loss', 'hm_loss', 'wh_loss', 'off_loss', 's2_reg_loss')
         running = dict.fromkeys(names, 0.0)
         every = getattr(self.cfg.Train, 'print_interval', 0)
-        for step in range(self.cfg.Train.iter_num):
+        ckp_every = getattr(self.cfg.Train, 'checkpoint_interval', 0)
+        iter_num = self.cfg.Train.iter_num
+        for step in range(iter_num):
             self.lr_sch.step()
             self.optimizer.zero_grad()
             try:
                 batch = self.training_loader.get_batch()
-            except RuntimeError as e:                       # the reference skips a batch that does not fit (:121-124)
+            except RuntimeError as e:
                 if 'out of memory' in str(e):
                     print('WARNING: ran out of memory with exception at step {}.'.format(step))
                 continue
-            imgs, annos, gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks = batch[:7]
-            losses = self.criterion(self.model(imgs), (gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks, annos))
+            imgs, annos = batch[0], batch[1]
+            gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks = self._targets_on_device(imgs, annos, *batch[2:7])
+            outs = self.model(imgs)
+            losses = self.criterion(outs, (gt_hms, gt_whs, gt_inds, gt_offsets, gt_reg_masks, annos))
             hm_loss, wh_loss, off_loss, s2_loss = losses
-            loss = hm_loss + 0.1 * wh_loss + off_loss + (s2_loss if step >= 2000 else 0 * s2_loss)
+            s2_factor = 0 if step < 2000 else 1
+            loss = hm_loss + (0.1 * wh_loss) + off_loss + s2_loss * s2_factor
             loss.backward()
             self.optimizer.step()
             for key, value in zip(names, (loss, hm_loss, wh_loss, off_loss, s2_loss)):
                 running[key] += float(value)
+            if not self.main_proc_flag:
+                continue
             if every and step % every == every - 1:
-                if self.main_proc_flag and self.logger is not None:
-                    self.logger.log({'scalar': {'train/' + k: v / every for k, v in running.items()}}, step)
+                if logger is not None:
+                    log_data = {'scalar': {'train/' + k: v / every for k, v in running.items()}}
+                    log_data['scalar']['train/lr'] = self.optimizer.param_groups[-1]['lr']
+                    if getattr(self.cfg.Train, 'log_images', True):
+                        pics = self._log_images(outs, imgs, annos)
+                        if pics is not None:
+                            log_data['imgs'] = pics
+                    logger.log(log_data, step)
                 running = dict.fromkeys(names, 0.0)
+            if (ckp_every and step % ckp_every == ckp_every - 1) or step == iter_num - 1:
+                log_dir = getattr(logger, 'log_dir', None) or os.path.join('./log', str(getattr(self.cfg, 'log_prefix', 'rrnet')))
+                os.makedirs(log_dir, exist_ok=True)
+                self.save_ckp(self._unwrap(), step, log_dir)
         return running['total_loss']
 
     # ------------------------------------------------------------------ rrnet_operator.py:246-284, batched
@@ -223,10 +326,14 @@ class RRNetOperator(object):
         self.model.eval()
         model_path = getattr(self.cfg.Val, 'model_path', None)
         if model_path:
-            getattr(self.model, 'module', self.model).load_state_dict(torch.load(model_path, map_location='cpu'))
+            self._unwrap().load_state_dict(torch.load(model_path, map_location='cpu'))
+        os.makedirs(self.cfg.Val.result_dir, exist_ok=True)
+        step, all_step = 0, len(self.validation_loader)
         with torch.no_grad():
             for imgs, annos, names in self.validation_loader:
+                step += 1
                 dets = self.detect_multi_scale(imgs.cuda(), self.cfg.Val.scales, final_nms=not self.cfg.Val.auto_test)
                 for name, det in zip(names, dets):
                     self.save_result(os.path.join(self.cfg.Val.result_dir, name + '.txt'), det)
+                print("\r[{}/{}]".format(step, all_step), end='', flush=True)
         print('=> Evaluation Done!')

@@ -394,7 +394,7 @@ def ap_match(pred, n_pred, target, n_tgt, thresholds, cls_num=11):
 
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
-    Process-wide; grid sizes are fixed at launch / graph capture time."""
+    Per calling host thread; grid sizes are fixed at launch / graph capture time."""
     check(_lib.lib().rr_set_sm_reserve(int(n_sms)), "rr_set_sm_reserve")
 
 

@@ -37,8 +37,15 @@ def test_dropin_install_keeps_the_rest_of_the_reference_importable():
             assert getattr(LF, keep).__module__ == "modules.loss.functional", keep
         assert RL.RegL1Loss.__module__.startswith("rrnet_b200.host")
         import datasets.transforms.functional as TF, datasets.transforms.transforms as TT
-        assert TF.to_heatmap.__module__.startswith("rrnet_b200.host") and callable(TF.denormalize)
-        assert TT.ToHeatmap.__module__.startswith("rrnet_b200.host")
+        # the per-sample render runs in forked DataLoader workers: it stays the reference's CPU code by default
+        assert TF.to_heatmap.__module__ == "datasets.transforms.functional" and callable(TF.denormalize)
+        assert TT.ToHeatmap.__module__ == "datasets.transforms.transforms"
+        done2 = dropin.install(gpu_targets=True)
+        assert len(done2) == len(done) + len(dropin.GPU_TARGET_SYMBOLS)
+        assert TT.ToHeatmap.__name__ == "DeferredToHeatmap" and TT.ToHeatmap.__module__.startswith("rrnet_b200.host")
+        import torch
+        out = TT.ToHeatmap()((torch.zeros(3, 64, 64), torch.ones(5, 8)))          # CPU only, no CUDA in the worker
+        assert out[2].numel() == 0 and out[6].shape == (5, 1) and not any(t.is_cuda for t in out)
         import utils.metrics.metrics as UM
         assert UM.get_tp.__module__.startswith("rrnet_b200.host") and UM.calculate_ap_rc.__module__ == "utils.metrics.metrics"
         # an operator of the reference that is NOT on the path still imports, and gets the mirror's losses / NMS
