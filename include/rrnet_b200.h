@@ -54,6 +54,13 @@ uint64_t    rr_launch_count(void);
  * the short latency-bound kernels of ANOTHER batch on another stream can run next to them (bench.py --streams 2).
  * Per calling host thread (thread-local); read when that thread issues / captures the next launch. */
 int         rr_set_sm_reserve(int n_sms);
+/* Per-kernel device times for benchmarks (no reference counterpart; the reference has no timers on this path).
+ * After rr_kernel_trace_begin every kernel launched by the CALLING THREAD through this library records the next of
+ * the caller's `capacity` CUDA events (cudaEvent_t, timing enabled) on its launch stream; events[0] is recorded on
+ * `stream` by the call itself.  names[i] (optional, static strings) = kernel that ended at events[i].
+ * rr_kernel_trace_end() stops the trace and returns the number of events recorded.  Not for use under graph capture. */
+int         rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream);
+int         rr_kernel_trace_end(void);
 
 /* ------------------------------------------------------------------------------------------
  * Decode: replaces RRNet.transform_bbox + RRNet._topk + _gather_feat /

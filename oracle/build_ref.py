@@ -17,6 +17,12 @@ The resulting ``oracle/_ref/cpu_nms*.so`` travels to the GPU box with the snapsh
   * the checker for the legacy ("+1") NMS / soft-NMS semantics, and
   * the ``ext/nms`` leg of the CPU baseline in ``bench.py``.
 
+The reference's CUDA hard NMS (``ext/nms/nms/nms_kernel.cu:34-144``: ``nms_kernel`` + the ``_nms`` host driver)
+is compiled too, UNCHANGED and straight from ``/root/reference``, for sm_100a (the reference's ``setup.py:132``
+pins ``-arch=sm_35``, which nvcc 12.9 rejects) into ``oracle/_ref/libref_gpu_nms.so``.  ``_nms`` is a C++ symbol
+(``gpu_nms.hpp:1-2`` has no extern "C"): ``load_gpu_nms()`` binds its mangled name.  It is the "reference CUDA
+kernel" baseline that ``bench.py`` times next to ``rr_nms_legacy_host`` (same signature) on the GPU box.
+
 Usage:  python oracle/build_ref.py            (no-op when /root/reference is absent)
 """
 import glob
@@ -72,6 +78,48 @@ def build(force=False):
     return built()
 
 
+REF_CU = "/root/reference/ext/nms/nms/nms_kernel.cu"
+GPU_NMS_SO = os.path.join(REF_DIR, "libref_gpu_nms.so")
+_NMS_MANGLED = "_Z4_nmsPiS_PKfiifi"          # void _nms(int*, int*, const float*, int, int, float, int)
+
+
+def build_gpu_nms(force=False):
+    """nvcc -arch=sm_100a on the reference's nms_kernel.cu where it lies -> oracle/_ref/libref_gpu_nms.so."""
+    if os.path.exists(GPU_NMS_SO) and not force:
+        return True
+    if not os.path.exists(REF_CU):
+        return False
+    os.makedirs(REF_DIR, exist_ok=True)
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+    cmd = [nvcc] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + [
+        "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC", "-w",
+        "-I", os.path.dirname(REF_CU), REF_CU, "-o", GPU_NMS_SO, "-lcudart"]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return os.path.exists(GPU_NMS_SO)
+
+
+def load_gpu_nms():
+    """-> callable(dets_sorted float32 [n,5] numpy, thresh, device_id=0) -> int32 keep indices (into the sorted rows),
+    i.e. the reference's `_nms` (nms_kernel.cu:91-144) with its own malloc / H2D / mask D2H / CPU reduce, or None."""
+    if not os.path.exists(GPU_NMS_SO):
+        return None
+    import ctypes
+    import numpy as np
+    lib = ctypes.CDLL(GPU_NMS_SO)
+    fn = getattr(lib, _NMS_MANGLED)
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                   ctypes.c_int]
+
+    def _nms(dets_sorted, thresh, device_id=0):
+        d = np.ascontiguousarray(dets_sorted, dtype=np.float32)
+        keep = np.zeros(d.shape[0], dtype=np.int32)
+        num = np.zeros(1, dtype=np.int32)
+        fn(keep.ctypes.data, num.ctypes.data, d.ctypes.data, d.shape[0], d.shape[1], float(thresh), int(device_id))
+        return keep[: int(num[0])]
+    return _nms
+
+
 def load():
     """Import the compiled reference module (``cpu_nms``, ``cpu_soft_nms``) or None."""
     if not built():
@@ -87,3 +135,5 @@ def load():
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     print("oracle/_ref cpu_nms:", "built" if ok else "unavailable (no /root/reference)")
+    ok = build_gpu_nms(force="--force" in sys.argv)
+    print("oracle/_ref libref_gpu_nms.so:", "built" if ok else "unavailable (no /root/reference)")

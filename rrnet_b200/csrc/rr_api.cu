@@ -8,6 +8,7 @@ namespace rr {
 
 std::atomic<uint64_t> g_launches{0};
 thread_local int g_sm_reserve = 0;
+thread_local KernelTrace g_ktrace = {nullptr, nullptr, 0, 0};
 
 // implemented in the per-kernel translation units
 int decode_launch(const float*, const float*, const float*, int, int, int, int, int, int, float*, int64_t*,
@@ -50,6 +51,18 @@ RR_API int rr_set_sm_reserve(int n_sms) {
     if (n_sms < 0 || n_sms >= kSMs) return RR_E_BADARG;
     g_sm_reserve = n_sms;
     return 0;
+}
+
+RR_API int rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream) {
+    if (!events || capacity <= 0) return RR_E_BADARG;
+    g_ktrace = {events, names, capacity, 0};
+    ktrace_mark("begin", (cudaStream_t)stream);
+    return 0;
+}
+RR_API int rr_kernel_trace_end(void) {
+    const int n = g_ktrace.n;
+    g_ktrace = {nullptr, nullptr, 0, 0};
+    return n;
 }
 
 RR_API const char* rr_error_string(int code) {

@@ -173,6 +173,6 @@ RR_API int rr_ap_match(const float* pred, const int32_t* n_pred, const float* ta
     int rc = 0;
     ap_match_kernel<<<B, kApThreads, 0, (cudaStream_t)stream>>>(pred, n_pred, target, n_tgt, thresholds, M, N, T, cls_num,
                                                                order, tp, out_cls, target_count, in_img);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "ap_match_kernel", (cudaStream_t)stream);
     return rc;
 }

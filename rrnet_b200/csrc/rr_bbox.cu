@@ -39,7 +39,7 @@ int generate_bbox_launch(const float* bxyxy, const float* reg, const float* scor
     int rc = 0;
     int grid = (n_cap + 255) / 256;
     generate_bbox_kernel<<<grid, 256, 0, st>>>(bxyxy, reg, scores, clses, n_rois_dev, n_cap, scale, s1, s2);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "generate_bbox_kernel", st);
     return rc;
 }
 

@@ -20,6 +20,24 @@ extern std::atomic<uint64_t> g_launches;   // defined in rr_api.cu
         if (_e != cudaSuccess && (rc) == 0) (rc) = (int)_e;                \
     } while (0)
 
+// Optional per-kernel timing (rr_kernel_trace_begin / _end): the calling thread hands in CUDA events and every
+// launch it issues afterwards records the next one on the launch's stream, so that event[i] - event[i-1] is the
+// device time of kernel i when the queue never runs dry.  Off (events == nullptr) unless a bench asks for it.
+struct KernelTrace { void* const* events; const char** names; int cap; int n; };
+extern thread_local KernelTrace g_ktrace;   // defined in rr_api.cu
+inline void ktrace_mark(const char* name, cudaStream_t st) {
+    KernelTrace& t = g_ktrace;
+    if (t.events && t.n < t.cap) {
+        if (t.names) t.names[t.n] = name;
+        (void)cudaEventRecord((cudaEvent_t)t.events[t.n++], st);
+    }
+}
+#define RR_LAUNCHED_K(rc, name, st)                                        \
+    do {                                                                   \
+        RR_LAUNCHED(rc);                                                   \
+        ::rr::ktrace_mark(name, st);                                       \
+    } while (0)
+
 #define RR_CUDA(call, rc)                                                  \
     do {                                                                   \
         cudaError_t _e = (call);                                           \

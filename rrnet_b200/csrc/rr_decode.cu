@@ -486,14 +486,14 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     DecodeWs w = carve_decode(ws, B);
     const int N = C * H * W;
     decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "decode_sample_kernel", st);
     // fill the machine: ~8 CTAs of 256 threads per SM in total, at least one per image
     int per_img = max(1, (kSMs * 8 + B - 1) / B);
     int max_useful = max(1, (N / 4 + kCollectThreads - 1) / kCollectThreads);
     per_img = min(per_img, max_useful);
     dim3 gc((unsigned)per_img, (unsigned)B);
     decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "decode_collect_kernel", st);
     static OncePerDevice attr_once; int attr_dev;
     const size_t smem = (size_t)kCap * sizeof(unsigned long long);
     if (attr_once.need(&attr_dev)) {
@@ -502,7 +502,7 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     }
     decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
                                                          out_dets, (long long*)out_inds);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "decode_select_kernel", st);
     return rc;
 }
 

@@ -343,7 +343,7 @@ RR_API int rr_focal_forward(const float* logits, const float* gt, int64_t n, flo
     FocalWs w = carve_focal(ws);
     RR_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st), rc);
     focal_forward_kernel<<<focal_grid(n), kFocalThreads, 0, st>>>(logits, gt, n, w.partial, w.ticket, stats);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "focal_forward_kernel", st);
     return rc;
 }
 
@@ -354,7 +354,7 @@ RR_API int rr_focal_backward(const float* logits, const float* gt, int64_t n, co
     if (!stats || !grad) return RR_E_BADARG;
     if ((uintptr_t)grad & 15) return RR_E_ALIGN;
     focal_backward_kernel<<<focal_grid(n), kFocalThreads, 0, (cudaStream_t)stream>>>(logits, gt, n, stats, upstream, grad);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "focal_backward_kernel", (cudaStream_t)stream);
     return rc;
 }
 
@@ -378,7 +378,7 @@ RR_API int rr_focal_fwd_bwd(const float* logits, const float* gt, int64_t n, flo
     void* args[] = {(void*)&logits, (void*)&gt, (void*)&n_ll, (void*)&upstream, (void*)&w.partial,
                     (void*)&w.ticket, (void*)&stats, (void*)&grad};
     RR_CUDA(cudaLaunchCooperativeKernel((void*)focal_fwd_bwd_kernel, dim3(grid), dim3(kFocalThreads), args, 0, st), rc);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "focal_fwd_bwd_kernel", st);
     return rc;
 }
 
@@ -416,7 +416,7 @@ RR_API int rr_focal_render_forward(const float* logits, const float* annos, cons
     focal_render_forward_kernel<<<(unsigned)grid, kFocalThreads, 0, st>>>(logits, annos, n_obj, max_n, img_w, Hh, Wh,
                                                                          (float)scale_factor, cls_num, tiles,
                                                                          w.partial, w.ticket, stats, gt_out);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "focal_render_forward_kernel", st);
     return rc;
 }
 
@@ -430,6 +430,6 @@ RR_API int rr_focal_render_backward(const float* logits, const float* annos, con
     if (((uintptr_t)logits & 15) || ((uintptr_t)grad & 15)) return RR_E_ALIGN;
     focal_render_backward_kernel<<<(unsigned)grid, kFocalThreads, 0, (cudaStream_t)stream>>>(
         logits, annos, n_obj, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num, tiles, stats, upstream, grad);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "focal_render_backward_kernel", (cudaStream_t)stream);
     return rc;
 }

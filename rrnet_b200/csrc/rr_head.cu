@@ -278,7 +278,7 @@ int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, cons
     }
     const int grid = (n_cap + kHeadWarps - 1) / kHeadWarps;
     head_forward_kernel<<<grid, kHeadThreads, kHeadSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "head_forward_kernel", st);
     return rc;
 }
 
@@ -313,7 +313,7 @@ RR_API int rr_head_fold(const float* w1, const float* bn1, const float* w2, cons
     if (!w1 || !bn1 || !w2 || !bn2 || !w3 || !bn3 || !wr || !br || !folded) return RR_E_BADARG;
     int rc = 0;
     head_fold_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1, bn1, w2, bn2, w3, bn3, wr, br, folded);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "head_fold_kernel", (cudaStream_t)stream);
     const int r2 = head_fold_tc_launch(folded, (cudaStream_t)stream);     // (hi, lo) tf32 weight tiles for the tensor-core kernel
     return rc ? rc : r2;
 }

@@ -202,7 +202,7 @@ __global__ void head_fold_tc_kernel(float* __restrict__ f) {
 int head_fold_tc_launch(float* folded, cudaStream_t st) {
     int rc = 0;
     head_fold_tc_kernel<<<(kTcSteps * kTcTileFloats + 255) / 256, 256, 0, st>>>(folded);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "head_fold_tc_kernel", st);
     return rc;
 }
 
@@ -720,7 +720,7 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
     const int n_tiles = (n_cap + kTcRois - 1) / kTcRois;
     const int sms = sms_for_persistent();
     head_tc_kernel<<<n_tiles < sms ? n_tiles : sms, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "head_tc_kernel", st);
     return rc;
 }
 

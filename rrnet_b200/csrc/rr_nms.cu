@@ -335,7 +335,7 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
     dim3 gm((unsigned)pairs, (unsigned)G);
     nms_mask_kernel<<<gm, 64, 0, st>>>(sbox, slab, n, Kmax, W, T, thr, pixel_offset ? 1.0f : 0.0f,
                                        ge_cmp ? 1 : 0, mask);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "nms_mask_kernel", st);
     dim3 gs((unsigned)segs_per_group, (unsigned)G);
     size_t smem = (size_t)W * sizeof(unsigned long long);
     if (smem > 48 * 1024) {
@@ -343,7 +343,7 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
         RR_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     }
     nms_scan_kernel<<<gs, 1024, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, map, keep_out, keep_cnt);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "nms_scan_kernel", st);
     return rc;
 }
 
@@ -377,13 +377,13 @@ int stage1_nms_launch(const float* dets, int B, int K, int C, double thr, float*
     if (smem > 48 * 1024)
         RR_CUDA(cudaFuncSetAttribute(stage1_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     stage1_partition_kernel<<<B, 1024, smem, st>>>(dets, K, C, w.sbox, w.slab, w.ssrc, w.sscore, w.seg_off);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "stage1_partition_kernel", st);
     int r2 = launch_mask_scan(w.sbox, w.slab, w.seg_off, B, C, K, K, thr, 0, 0, w.mask, nullptr,
                               w.keep_pos, w.keep_cnt, st);
     if (rc == 0) rc = r2;
     stage1_compact_kernel<<<B, 1024, 0, st>>>(w.sbox, w.sscore, w.slab, w.seg_off, w.keep_pos, w.keep_cnt,
                                              B, K, C, out_bxyxy, out_scores, out_clses, out_counts);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "stage1_compact_kernel", st);
     return rc;
 }
 
@@ -444,7 +444,7 @@ RR_API int rr_nms_batched(const float* boxes, const float* scores, const int32_t
     if (ws_bytes < carve_generic(nullptr, M).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     GenericWs w = carve_generic(ws, M);
     rank_sort_kernel<<<(int)(((long long)M * kRankSplit + 255) / 256), 256, 0, st>>>(boxes, scores, seg_offsets, M, S, w.sbox, w.slab, w.ssrc);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "rank_sort_kernel", st);
     int r2 = launch_mask_scan(w.sbox, w.slab, seg_offsets, 1, S, M, M, thr, pixel_offset, ge_cmp, w.mask,
                               w.ssrc, keep_idx, keep_count, st);
     return rc ? rc : r2;
@@ -501,7 +501,7 @@ RR_API int rr_nms_legacy_host(int* keep_out_host, int* num_out_host, const float
     RR_CUDA(cudaMemcpyAsync(rows, boxes_host, (size_t)n * boxes_dim * sizeof(float), cudaMemcpyHostToDevice, st), rc);
     RR_CUDA(cudaMemcpyAsync(seg_off, segs, sizeof(segs), cudaMemcpyHostToDevice, st), rc);
     repack_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(rows, n, boxes_dim, w.sbox, w.slab);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "repack_rows_kernel", st);
     int r2 = launch_mask_scan(w.sbox, w.slab, seg_off, 1, 1, n, n, (double)nms_overlap_thresh, 1, 0, w.mask,
                               nullptr, keep, cnt, st);
     if (rc == 0) rc = r2;

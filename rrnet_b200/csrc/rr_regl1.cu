@@ -74,6 +74,6 @@ RR_API int rr_regl1_fwd_bwd(const float* output, const float* mask, const float*
     int rc = 0;
     if (grad) RR_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)B * c * H * W, st), rc);
     regl1_kernel<<<1, kRegThreads, 0, st>>>(output, mask, ind, target, B, c, H * W, max_n, grad_scale, loss, grad);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "regl1_kernel", st);
     return rc;
 }

@@ -62,6 +62,6 @@ RR_API int rr_render_targets(const float* annos, const int32_t* n_obj, int B, in
     const int grid = (int)((warps * 32 + 255) / 256);
     render_kernel<<<grid, 256, 0, st>>>(annos, n_obj, B, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num,
                                         hm, wh, ind, offset, reg_mask);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "render_kernel", st);
     return rc;
 }

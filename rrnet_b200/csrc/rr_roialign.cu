@@ -1109,14 +1109,14 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
     const int force_direct = algo == 1;
     roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
                                                     w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
     roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
                                                 w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
         roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
-        RR_LAUNCHED(rc);
+        RR_LAUNCHED_K(rc, "roi_fill_kernel", st);
         static OncePerDevice attr_once; int attr_dev;
         if (attr_once.need(&attr_dev)) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem), rc);
@@ -1132,21 +1132,22 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
             else
                 roi_tile_tma_kernel<false><<<sms_for_persistent(), kT2Threads, kT2Smem, st>>>(
                     tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial);
+            RR_LAUNCHED_K(rc, "roi_tile_tma_kernel", st);
         } else {                                                        // tiles staged through the load/store path
             roi_tile_kernel<<<2 * sms_for_persistent(), kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
                                                                       w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
                                                                       w.td, w.partial);
+            RR_LAUNCHED_K(rc, "roi_tile_kernel", st);
         }
-        RR_LAUNCHED(rc);
     }
     if (combine) {
         roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
             w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
-        RR_LAUNCHED(rc);
+        RR_LAUNCHED_K(rc, "roi_combine_kernel", st);
     }
     roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * sms_for_persistent(), kRoiThreads, 0, st>>>(
         feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_direct_kernel", st);
     return rc;
 }
 
@@ -1344,14 +1345,14 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
     const int force_direct = algo == 1;
     roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
                                                     w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
     roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
                                                 w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
         roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
-        RR_LAUNCHED(rc);
+        RR_LAUNCHED_K(rc, "roi_fill_kernel", st);
         static OncePerDevice attr_once; int attr_dev;
         if (attr_once.need(&attr_dev)) {
             RR_CUDA(cudaFuncSetAttribute(roi_tile_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), rc);
@@ -1360,10 +1361,10 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
         roi_tile_bwd_kernel<<<w.n_tiles * (C / kTC), kBwdThreads, kBwdSmem, st>>>(feat, grad_out, w.list, w.list_wx, w.list_wy,
                                                                               w.cnt, w.tile_off, w.tile_fill, C, H, W, relu,
                                                                               w.td, grad_feat);
-        RR_LAUNCHED(rc);
+        RR_LAUNCHED_K(rc, "roi_tile_bwd_kernel", st);
     }
     roi_direct_bwd_kernel<<<8 * kSMs, kRoiThreads, 0, st>>>(feat, rois, grad_out, w.direct_list, w.ctl, B, C, H, W, relu, grad_feat);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "roi_direct_bwd_kernel", st);
     return rc;
 }
 

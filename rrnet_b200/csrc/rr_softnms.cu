@@ -230,7 +230,7 @@ RR_API int rr_soft_nms_batched(float* boxes, const int32_t* seg_offsets, int M, 
     RR_CUDA(cudaFuncSetAttribute(soft_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     soft_nms_kernel<true><<<S, kSoftThreads, smem, st>>>(boxes, seg_offsets, sigma, Nt, threshold, method,
                                                         src_idx, nullptr, nullptr, keep_count);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "soft_nms_kernel", st);
     if (M > kSoftCap) {                                    // some segment may exceed the smem capacity
         if (!ws) return RR_E_BADARG;
         if (ws_bytes < rr_soft_nms_workspace_bytes(M) || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
@@ -239,7 +239,7 @@ RR_API int rr_soft_nms_batched(float* boxes, const int32_t* seg_offsets, int M, 
         int* list = cv.take<int>((size_t)M);
         soft_nms_kernel<false><<<S, kSoftThreads, 0, st>>>(boxes, seg_offsets, sigma, Nt, threshold, method,
                                                           src_idx, flag, list, keep_count);
-        RR_LAUNCHED(rc);
+        RR_LAUNCHED_K(rc, "soft_nms_kernel", st);
     }
     return rc;
 }

@@ -151,6 +151,6 @@ RR_API int rr_stage2_loss(const float* bxyxy, const int32_t* seg_offsets, const 
     stage2_loss_kernel<<<B, kS2Threads, smem, (cudaStream_t)stream>>>(bxyxy, seg_offsets, s2_reg, gt_xyxy, max_n, gt_stride,
                                                                       scale, 1.0f / (float)B, grad_scale, loss_parts,
                                                                       grad_reg, grad_box);
-    RR_LAUNCHED(rc);
+    RR_LAUNCHED_K(rc, "stage2_loss_kernel", (cudaStream_t)stream);
     return rc;
 }

@@ -392,6 +392,35 @@ def ap_match(pred, n_pred, target, n_tgt, thresholds, cls_num=11):
     return order, tp, cls, cnt, img
 
 
+class KernelTrace:
+    """Per-kernel device times of everything this thread launches through the library inside the `with` block
+    (rr_kernel_trace_begin / _end): CUDA events between consecutive launches.  So that launch overhead does not show
+    up as idle gaps, the stream is first held busy for `hold_ms` (torch.cuda._sleep) while the launches queue up.
+    -> .kernels = [(name, ms), ...] after the block (one host sync)."""
+
+    def __init__(self, capacity=64, hold_ms=2.0):
+        self.capacity, self.hold_ms = int(capacity), float(hold_ms)
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(self.capacity)]
+        self.kernels = []
+
+    def __enter__(self):
+        st = torch.cuda.current_stream()
+        for e in self.events:
+            e.record(st)                                   # torch creates the CUDA event lazily on first record
+        if self.hold_ms > 0:
+            torch.cuda._sleep(int(self.hold_ms * 1.9e6))   # ~cycles at 1.9 GHz
+        self._ev = (ctypes.c_void_p * self.capacity)(*[e.cuda_event for e in self.events])
+        self._names = (ctypes.c_char_p * self.capacity)()
+        check(_lib.lib().rr_kernel_trace_begin(self._ev, self._names, self.capacity, _stream()), "rr_kernel_trace_begin")
+        return self
+
+    def __exit__(self, *exc):
+        n = _lib.lib().rr_kernel_trace_end()
+        torch.cuda.synchronize()
+        self.kernels = [(self._names[i].decode(), self.events[i - 1].elapsed_time(self.events[i])) for i in range(1, n)]
+        return False
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Per calling host thread; grid sizes are fixed at launch / graph capture time."""
