@@ -45,6 +45,7 @@ extern "C" {
 #define RR_HEAD_MID        64
 #define RR_POOL            3     /* RoIAlign output is 3x3 (models/rrnet.py:51) */
 #define RR_DECODE_RAW_SCORES 0x100
+#define RR_DECODE_PRECOLLECTED 0x200 /* the candidate lists in `ws` were filled by rr_hm_tail_collect: skip sample + collect */
 
 int         rr_version(void);
 const char* rr_error_string(int code);
@@ -81,6 +82,21 @@ int rr_decode_topk(const float* hm, const float* wh, const float* off,
                    int B, int C, int H, int W, int K, int pool,
                    float* out_dets, int64_t* out_inds,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage-1 head tail fused with the decode's candidate collection: replaces the LAST layer of the
+ * heat-map head, nn.Conv2d(256, planes, (1,1)) with bias (detectors/centernet_detector.py:11-15, called from
+ * RRNet.forward_stage1, models/rrnet.py:140-153), plus decode's sample + streaming pass over the logits.
+ *   t       [B,Cin,H,W]  output of the head's 3x3 conv + ReLU (BasicCov, :81-93; stays with cuDNN)
+ *   weight  [Cout,Cin]   (the 1x1 kernel), bias [Cout];  Cout <= 16, Cin <= 1024
+ *   hm_out  [B,Cout,H,W] the heat-map logits (what the reference's head returns)
+ *   decode_ws: a workspace of rr_decode_workspace_bytes(B,..) bytes - or the START of an rr_eval_forward workspace
+ *           (its first region is the decode workspace); on return it holds the per-image candidate lists, and
+ *           rr_decode_topk / rr_eval_forward called with pool = RR_DECODE_PRECOLLECTED on (hm_out, same ws) go
+ *           straight to the top-K selection.  One pass over t; fp32 FMA (1e-5 against the reference's convolution).
+ * ---------------------------------------------------------------------------------------- */
+int rr_hm_tail_collect(const float* t, const float* weight, const float* bias, int B, int Cin, int Cout,
+                       int H, int W, int K, float* hm_out, void* decode_ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage-1 NMS: replaces RRNet.nms (default per-class branch, models/rrnet.py:56-72, i.e.

@@ -23,6 +23,7 @@ SIGNATURES = {
     "rr_kernel_trace_end": (c_int, []),
     "rr_decode_workspace_bytes": (c_size_t, [c_int] * 5),
     "rr_decode_topk": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "rr_hm_tail_collect": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
     "rr_stage1_nms_workspace_bytes": (c_size_t, [c_int] * 3),
     "rr_stage1_nms": (c_int, [P, c_int, c_int, c_int, c_double, P, P, P, P, P, c_size_t, P]),
     "rr_nms_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -23,6 +23,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 UNITS = {
     "rr_api.cu": [],
     "rr_decode.cu": ["--fmad=false"],
+    "rr_tail.cu": [],
     "rr_nms.cu": ["--fmad=false"],
     "rr_softnms.cu": ["--fmad=false"],
     "rr_roialign.cu": ["--fmad=false"],
@@ -63,7 +64,7 @@ def _digest(paths, flags):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(CSRC, "rr_gauss.cuh"), os.path.join(CSRC, "rr_head.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
+    headers = [os.path.join(CSRC, "rr_common.cuh"), os.path.join(CSRC, "rr_gauss.cuh"), os.path.join(CSRC, "rr_head.cuh"), os.path.join(CSRC, "rr_decode.cuh"), os.path.join(INCLUDE, "rrnet_b200.h")]
     nvcc = _nvcc()
     ccbin = _host_cc()
     objs, rebuilt = [], False

@@ -95,7 +95,7 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
         return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
     if (feat_ch != RR_HEAD_CH) return RR_E_RANGE;               // the head is 256-channel (fasterrcnn_detector.py:9)
-    if ((pool != 0 && pool != 3) || roi_algo < 0 || roi_algo > 7 || (roi_algo & 5) == 5) return RR_E_BADARG;
+    if ((pool != 0 && pool != 3 && pool != RR_DECODE_PRECOLLECTED) || roi_algo < 0 || roi_algo > 7 || (roi_algo & 5) == 5) return RR_E_BADARG;
     const int head_algo = (roi_algo >> 1) & 1;       // bit 1: fp32 FFMA head instead of the tcgen05 one
     roi_algo = (roi_algo & 1) ? 1 : ((roi_algo & 4) ? 2 : 0);   // bit 0: direct-gather RoIAlign, bit 2: tile path staged by loads (no TMA)
     if (C > RR_MAX_CLASSES || K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;

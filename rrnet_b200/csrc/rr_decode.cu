@@ -21,34 +21,11 @@
 //
 // HBM traffic: the logits once (B*C*H*W*4 bytes) + K*4 gathers + outputs.
 // Built with --fmad=false (box arithmetic must round like the reference's separate torch ops).
-#include "rr_common.cuh"
+#include "rr_decode.cuh"
 
 #include <math_constants.h>
 
 namespace rr {
-
-constexpr int kCap = 16384;          // candidate capacity per image (== RR_MAX_TOPK)
-constexpr int kSampleThreads = 1024;
-constexpr int kSamplesPerThread = 32;
-constexpr int kCollectThreads = 256;
-constexpr int kStage = 1024;         // per-CTA staging entries in decode_collect_kernel
-constexpr int kSelectThreads = 1024;
-
-struct DecodeWs {
-    unsigned int* thr_key;            // [B]
-    unsigned int* count;              // [B]
-    unsigned long long* cand;         // [B][kCap]   (key << 32) | ~flat_index
-    size_t bytes;
-};
-static DecodeWs carve_decode(void* ws, int B) {
-    Carver cv(ws);
-    DecodeWs w;
-    w.thr_key = cv.take<unsigned int>(B);
-    w.count = cv.take<unsigned int>(B);
-    w.cand = cv.take<unsigned long long>((size_t)B * kCap);
-    w.bytes = cv.off;
-    return w;
-}
 
 // value used for ranking: the logit, or -inf when pool=3 and the element is not a 3x3 peak
 // (operators/centernet_operator.py:204-210: keep = (maxpool3x3(heat) == heat)).
@@ -141,19 +118,6 @@ decode_sample_kernel(const float* __restrict__ hm, int H, int W, int N, int K, i
 // ---------------------------------------------------------------------------------------------
 // 2. streaming collect: grid (ctas_per_image, B)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void push_candidate(unsigned key, unsigned flat, unsigned long long* s_stage,
-                                               int* s_n, unsigned int* g_count,
-                                               unsigned long long* g_cand) {
-    unsigned long long e = ((unsigned long long)key << 32) | (unsigned long long)(~flat);
-    int slot = atomicAdd(s_n, 1);
-    if (slot < kStage) {
-        s_stage[slot] = e;
-    } else {                            // staging full (dense hits): go straight to global
-        unsigned pos = atomicAdd(g_count, 1u);
-        if (pos < (unsigned)kCap) g_cand[pos] = e;
-    }
-}
-
 __global__ void __launch_bounds__(kCollectThreads)
 decode_collect_kernel(const float* __restrict__ hm, int H, int W, int N, int pool,
                       const unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count,
@@ -485,15 +449,17 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     const int pool = mode & 0xff, raw = (mode & RR_DECODE_RAW_SCORES) ? 1 : 0;
     DecodeWs w = carve_decode(ws, B);
     const int N = C * H * W;
-    decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
-    RR_LAUNCHED_K(rc, "decode_sample_kernel", st);
-    // fill the machine: ~8 CTAs of 256 threads per SM in total, at least one per image
-    int per_img = max(1, (kSMs * 8 + B - 1) / B);
-    int max_useful = max(1, (N / 4 + kCollectThreads - 1) / kCollectThreads);
-    per_img = min(per_img, max_useful);
-    dim3 gc((unsigned)per_img, (unsigned)B);
-    decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
-    RR_LAUNCHED_K(rc, "decode_collect_kernel", st);
+    if (!(mode & RR_DECODE_PRECOLLECTED)) {        // else: rr_hm_tail_collect already left count / cand in the workspace
+        decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
+        RR_LAUNCHED_K(rc, "decode_sample_kernel", st);
+        // fill the machine: ~8 CTAs of 256 threads per SM in total, at least one per image
+        int per_img = max(1, (kSMs * 8 + B - 1) / B);
+        int max_useful = max(1, (N / 4 + kCollectThreads - 1) / kCollectThreads);
+        per_img = min(per_img, max_useful);
+        dim3 gc((unsigned)per_img, (unsigned)B);
+        decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
+        RR_LAUNCHED_K(rc, "decode_collect_kernel", st);
+    }
     static OncePerDevice attr_once; int attr_dev;
     const size_t smem = (size_t)kCap * sizeof(unsigned long long);
     if (attr_once.need(&attr_dev)) {
@@ -524,8 +490,9 @@ RR_API int rr_decode_topk(const float* hm, const float* wh, const float* off,
                           void* ws, size_t ws_bytes, void* stream) {
     if (!hm || !out_dets || !ws) return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
-    const int pl = pool & ~RR_DECODE_RAW_SCORES;
+    const int pl = pool & ~(RR_DECODE_RAW_SCORES | RR_DECODE_PRECOLLECTED);
     if (pl != 0 && pl != 3) return RR_E_BADARG;
+    if ((pool & RR_DECODE_PRECOLLECTED) && pl != 0) return RR_E_BADARG;      // the fused tail has no 3x3 peak pooling
     if (!(pool & RR_DECODE_RAW_SCORES) && (!wh || !off)) return RR_E_BADARG;   // wh/off optional only for plain top-K
     if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
     if (K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;   // torch.topk raises (:96)

@@ -1,0 +1,269 @@
+// Stage-1 head tail fused with the decode's candidate collection, for sm_100a.
+//
+// The reference's heat-map head is  relu(feat) -> 3x3 conv 256->256 + ReLU -> 1x1 conv 256->C (+bias)
+// (detectors/centernet_detector.py:6-23, called from RRNet.forward_stage1, models/rrnet.py:140-153), and the
+// decode then reads the C x H x W logit map it wrote.  The 3x3 convolution stays with cuDNN (out of scope); this
+// file takes its output `t` [B,Cin,H,W] and does the LAST layer and the decode's streaming pass in one kernel:
+//
+//   tail_sample_kernel   a few hundred pseudo-random lines of 32 consecutive pixels per image: the 1x1 conv of those
+//                        pixels only (all classes), per-lane maxima folded into 1024 slots per image (atomicMax);
+//   tail_thresh_kernel   one warp per image: the r-th largest of the 1024 slot maxima = the candidate threshold
+//                        (same estimator as decode_sample_kernel, rr_decode.cu);
+//   tail_conv_collect_kernel   ONE pass over t (Cin*H*W*4 bytes per image, the only large read): every thread
+//                        owns 4 consecutive pixels, walks the Cin channel planes with 128-bit loads (8 in flight),
+//                        keeps 4 x C accumulators in registers (weights: broadcast 128-bit shared-memory reads),
+//                        adds the bias, writes the logits (kept: the reference returns `hms`, and the exact fallback
+//                        of decode_select reads them) and appends every logit >= threshold to the image's candidate
+//                        list - exactly what decode_collect_kernel produces, so decode_select runs unchanged
+//                        (rr_decode_topk / rr_eval_forward with RR_DECODE_PRECOLLECTED).
+//
+// HBM traffic: t once (1.07 GB at config 2) + the logit map written once (42 MB) instead of cuDNN's 1x1 conv
+// (same read, same write) followed by decode's re-read of the map.  fp32 FMA in channel order; 1e-5 relative to the
+// reference's convolution (different summation order), top-K / boxes bit-exact against the oracle applied to the
+// logits this kernel wrote.
+#include "rr_decode.cuh"
+
+namespace rr {
+
+constexpr int kTailThreads = 256;
+constexpr int kTailPx = 4;                     // pixels per thread
+constexpr int kTailUnroll = 8;                 // channel planes in flight per thread
+constexpr int kTailMaxCout = 16;
+constexpr int kTailSlots = 1024;               // folded sample maxima per image
+constexpr int kTailMaxCin = 1024;
+
+// weights -> shared memory as [Cin][4 * NV] (zero padded), NV = float4 vectors per input channel
+template <int NV>
+__device__ __forceinline__ void tail_stage_weights(const float* __restrict__ w, int Cin, int Cout, float* s_w) {
+    for (int i = threadIdx.x; i < Cin * 4 * NV; i += blockDim.x) {
+        const int k = i / (4 * NV), n = i - k * (4 * NV);
+        s_w[i] = n < Cout ? __ldg(w + (size_t)n * Cin + k) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. sample: grid (ceil(n_lines / 8), B), one warp per sampled line of 32 consecutive pixels
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kTailThreads)
+tail_sample_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ bias,
+                   int Cin, int Cout, int HW, int n_lines, unsigned int* __restrict__ maxima) {
+    extern __shared__ float s_w[];
+    const int b = blockIdx.y, lane = lane_id();
+    tail_stage_weights<NV>(w, Cin, Cout, s_w);
+    __syncthreads();
+    const int line = blockIdx.x * (kTailThreads / 32) + warp_id();
+    if (line >= n_lines) return;
+    const unsigned nl = (unsigned)((HW + 31) / 32);
+    const unsigned pl = __umulhi((unsigned)line * 2654435761u + 12345u, nl);       // hash -> [0, nl)
+    const int p = min((int)(pl * 32u) + lane, HW - 1);
+    const float* src = t + (size_t)b * Cin * HW + p;
+    float acc[4 * NV];
+#pragma unroll
+    for (int n = 0; n < 4 * NV; ++n) acc[n] = 0.f;
+    for (int k0 = 0; k0 < Cin; k0 += kTailUnroll) {
+        float x[kTailUnroll];
+#pragma unroll
+        for (int j = 0; j < kTailUnroll; ++j) x[j] = (k0 + j < Cin) ? __ldg(src + (size_t)(k0 + j) * HW) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kTailUnroll; ++j) {
+            if (k0 + j < Cin) {
+                const float4* wk = reinterpret_cast<const float4*>(s_w + (size_t)(k0 + j) * 4 * NV);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 ww = wk[v];
+                    acc[4 * v + 0] = fmaf(ww.x, x[j], acc[4 * v + 0]);
+                    acc[4 * v + 1] = fmaf(ww.y, x[j], acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(ww.z, x[j], acc[4 * v + 2]);
+                    acc[4 * v + 3] = fmaf(ww.w, x[j], acc[4 * v + 3]);
+                }
+            }
+        }
+    }
+    unsigned m = 0u;
+#pragma unroll
+    for (int n = 0; n < 4 * NV; ++n)
+        if (n < Cout) m = max(m, f2key(acc[n] + __ldg(bias + n)));
+    atomicMax(maxima + (size_t)b * kTailSlots + ((line * 32 + lane) & (kTailSlots - 1)), m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. threshold: grid B, one warp: largest t with #{slots : max >= t} >= r (MSB-first descent, 32 values per lane)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+tail_thresh_kernel(const unsigned int* __restrict__ maxima, int r, int no_threshold,
+                   unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (lane == 0) count[b] = 0;
+    if (no_threshold) {                              // the whole image fits in the candidate list
+        if (lane == 0) thr_key[b] = 0u;
+        return;
+    }
+    unsigned mine[kTailSlots / 32];
+#pragma unroll
+    for (int q = 0; q < kTailSlots / 32; ++q) mine[q] = maxima[(size_t)b * kTailSlots + q * 32 + lane];
+    unsigned t = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned trial = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < kTailSlots / 32; ++q) c += (mine[q] >= trial);
+        if (__reduce_add_sync(0xffffffffu, c) >= r) t = trial;
+    }
+    if (lane == 0) thr_key[b] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. 1x1 conv + bias -> logits + candidates: grid (ceil(HW / 1024), B)
+// ---------------------------------------------------------------------------------------------
+template <int NV, bool kVec>
+__global__ void __launch_bounds__(kTailThreads)
+tail_conv_collect_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ bias,
+                         int Cin, int Cout, int HW, const unsigned int* __restrict__ thr_key,
+                         unsigned int* __restrict__ count, unsigned long long* __restrict__ cand,
+                         float* __restrict__ hm_out) {
+    extern __shared__ float s_w[];                   // [Cin][4 * NV]
+    __shared__ unsigned long long s_stage[kStage];
+    __shared__ int s_n;
+    __shared__ unsigned s_base;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    tail_stage_weights<NV>(w, Cin, Cout, s_w);
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int p0 = (blockIdx.x * kTailThreads + tid) * kTailPx;
+    const unsigned thr = thr_key[b];
+    unsigned int* g_count = count + b;
+    unsigned long long* g_cand = cand + (size_t)b * kCap;
+    if (p0 < HW) {
+        const float* src = t + (size_t)b * Cin * HW + p0;
+        float acc[kTailPx][4 * NV];
+#pragma unroll
+        for (int q = 0; q < kTailPx; ++q)
+#pragma unroll
+            for (int n = 0; n < 4 * NV; ++n) acc[q][n] = 0.f;
+        // pixels past the end of the plane (only when HW % 4 != 0) are loaded from the last valid one and dropped
+        int po[kTailPx];
+#pragma unroll
+        for (int q = 0; q < kTailPx; ++q) po[q] = min(q, HW - 1 - p0);
+        for (int k0 = 0; k0 < Cin; k0 += kTailUnroll) {
+            float4 x[kTailUnroll];
+#pragma unroll
+            for (int j = 0; j < kTailUnroll; ++j) {
+                const int k = min(k0 + j, Cin - 1);              // Cin % 8 != 0: the surplus planes repeat the last (weight 0 below)
+                const float* pk = src + (size_t)k * HW;
+                if (kVec) {
+                    x[j] = ld_stream_f4(reinterpret_cast<const float4*>(pk));
+                } else {
+                    x[j] = make_float4(__ldg(pk + po[0]), __ldg(pk + po[1]), __ldg(pk + po[2]), __ldg(pk + po[3]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kTailUnroll; ++j) {
+                if (k0 + j < Cin) {
+                    const float4* wk = reinterpret_cast<const float4*>(s_w + (size_t)(k0 + j) * 4 * NV);
+                    const float xv[kTailPx] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const float4 ww = wk[v];                  // warp-uniform address: one broadcast wavefront
+#pragma unroll
+                        for (int q = 0; q < kTailPx; ++q) {
+                            acc[q][4 * v + 0] = fmaf(ww.x, xv[q], acc[q][4 * v + 0]);
+                            acc[q][4 * v + 1] = fmaf(ww.y, xv[q], acc[q][4 * v + 1]);
+                            acc[q][4 * v + 2] = fmaf(ww.z, xv[q], acc[q][4 * v + 2]);
+                            acc[q][4 * v + 3] = fmaf(ww.w, xv[q], acc[q][4 * v + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        float* dst = hm_out + (size_t)b * Cout * HW + p0;
+#pragma unroll
+        for (int n = 0; n < 4 * NV; ++n) {
+            if (n < Cout) {
+                const float bn = __ldg(bias + n);
+                float o[kTailPx];
+#pragma unroll
+                for (int q = 0; q < kTailPx; ++q) o[q] = acc[q][n] + bn;
+                if (kVec) {
+                    *reinterpret_cast<float4*>(dst + (size_t)n * HW) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kTailPx; ++q)
+                        if (p0 + q < HW) dst[(size_t)n * HW + q] = o[q];
+                }
+#pragma unroll
+                for (int q = 0; q < kTailPx; ++q) {
+                    const unsigned key = f2key(o[q]);
+                    if (key >= thr && p0 + q < HW)
+                        push_candidate(key, (unsigned)(n * HW + p0 + q), s_stage, &s_n, g_count, g_cand);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_st = min(s_n, kStage);
+    if (n_st == 0) return;
+    if (tid == 0) s_base = atomicAdd(g_count, (unsigned)n_st);
+    __syncthreads();
+    const unsigned base = s_base;
+    for (int k = tid; k < n_st; k += blockDim.x) {
+        const unsigned pos = base + k;
+        if (pos < (unsigned)kCap) g_cand[pos] = s_stage[k];
+    }
+}
+
+template <int NV>
+static int tail_launch_nv(const float* t, const float* w, const float* bias, int B, int Cin, int Cout, int HW, int K,
+                          float* hm_out, DecodeWs& ws, cudaStream_t st) {
+    int rc = 0;
+    const size_t smem = (size_t)Cin * 4 * NV * sizeof(float);
+    const long long N = (long long)Cout * HW;
+    const int no_thr = N <= kCap;
+    // same target population as decode_sample_kernel; lines so that the sample rank of the threshold is ~128
+    int target = max(2 * K, K + 1300);
+    target = min(target, (K + kCap) / 2);
+    int n_lines = (int)((128ll * HW + 32ll * target - 1) / (32ll * target));
+    n_lines = min(max(n_lines, 32), 512);
+    int r = (int)(((long long)target * n_lines * 32 + HW - 1) / HW);   // = target * (lanes sampled) / HW
+    r = min(max(r, 8), kTailSlots / 2);
+    if (!no_thr) {
+        RR_CUDA(cudaMemsetAsync(ws.maxima, 0, sizeof(unsigned int) * (size_t)B * kTailSlots, st), rc);
+        dim3 gs((unsigned)((n_lines + kTailThreads / 32 - 1) / (kTailThreads / 32)), (unsigned)B);
+        tail_sample_kernel<NV><<<gs, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, n_lines, ws.maxima);
+        RR_LAUNCHED_K(rc, "tail_sample_kernel", st);
+    }
+    tail_thresh_kernel<<<B, 32, 0, st>>>(ws.maxima, r, no_thr, ws.thr_key, ws.count);
+    RR_LAUNCHED_K(rc, "tail_thresh_kernel", st);
+    dim3 gc((unsigned)((HW + kTailThreads * kTailPx - 1) / (kTailThreads * kTailPx)), (unsigned)B);
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(hm_out) & 15) == 0);
+    if (vec)
+        tail_conv_collect_kernel<NV, true><<<gc, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
+                                                                          ws.cand, hm_out);
+    else
+        tail_conv_collect_kernel<NV, false><<<gc, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
+                                                                           ws.cand, hm_out);
+    RR_LAUNCHED_K(rc, "tail_conv_collect_kernel", st);
+    return rc;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+RR_API int rr_hm_tail_collect(const float* t, const float* weight, const float* bias, int B, int Cin, int Cout,
+                              int H, int W, int K, float* hm_out, void* decode_ws, size_t ws_bytes, void* stream) {
+    if (!t || !weight || !bias || !hm_out || !decode_ws) return RR_E_BADARG;
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
+    if (Cout > kTailMaxCout || Cin > kTailMaxCin) return RR_E_RANGE;
+    if ((long long)Cout * H * W >= (1LL << 31) || (long long)Cin * H * W >= (1LL << 31)) return RR_E_RANGE;
+    if (K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;
+    if (ws_bytes < carve_decode(nullptr, B).bytes || ((uintptr_t)decode_ws & 255)) return RR_E_WORKSPACE;
+    DecodeWs ws = carve_decode(decode_ws, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H * W;
+    if (Cout <= 4) return tail_launch_nv<1>(t, weight, bias, B, Cin, Cout, HW, K, hm_out, ws, st);
+    if (Cout <= 8) return tail_launch_nv<2>(t, weight, bias, B, Cin, Cout, HW, K, hm_out, ws, st);
+    if (Cout <= 12) return tail_launch_nv<3>(t, weight, bias, B, Cin, Cout, HW, K, hm_out, ws, st);
+    return tail_launch_nv<4>(t, weight, bias, B, Cin, Cout, HW, K, hm_out, ws, st);
+}

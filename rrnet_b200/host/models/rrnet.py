@@ -45,14 +45,22 @@ class RRNet(nn.Module):
     # ------------------------------------------------------------------ models/rrnet.py:25-54
     def forward(self, x, k=1500):
         pre_feat = self.backbone(x)
-        hms, whs, offsets = self.forward_stage1(pre_feat)
         feat = pre_feat[-1]
         fused = (not self.training) and not torch.is_grad_enabled() and self.nms_type != 'soft_nms' \
             and self.nms_per_class and feat.size(1) == 256
+        tail = self._hm_tail() if (fused and self.fuse_hm_tail) else None
+        hms, whs, offsets = self.forward_stage1(pre_feat, skip_last_hm=tail is not None)
         if fused:
             # decode -> per-class NMS -> RoIAlign(+ReLU) -> head in one C-ABI call, one host sync for N
-            path = self._eval_path(hms[-1].shape, k, feat.device)
-            path.forward(hms[-1], whs[-1], offsets[-1], feat)
+            path = self._eval_path((feat.size(0), self.num_classes, feat.size(2), feat.size(3)), k, feat.device)
+            if tail is not None:
+                # the heat-map head's last 1x1 conv is fused with the decode's pass over the logits: the
+                # map is written once for the caller (`hms`) and never read back
+                body, last = tail
+                t = body(torch.relu(pre_feat[self.num_stacks - 1]))
+                hms.append(path.forward_from_tail(t, last.weight, last.bias, whs[-1], offsets[-1], feat).clone())
+            else:
+                path.forward(hms[-1], whs[-1], offsets[-1], feat)
             r = path.results()
             # the path's buffers are reused by the next forward of the same shape: hand out copies (a few hundred KB)
             return hms, whs, offsets, r["reg"].clone(), r["bxyxy"].clone(), r["scores"].clone(), r["clses"].clone()
@@ -71,6 +79,23 @@ class RRNet(nn.Module):
         roi_feat = _RoIAlignReLU.apply(feat, bxyxys)
         stage2_reg = self.forward_stage2(roi_feat)
         return hms, whs, offsets, stage2_reg, bxyxys, scores, clses
+
+    fuse_hm_tail = True           # eval: fuse the heat-map head's final 1x1 conv into the decode (when the head has that shape)
+
+    def _hm_tail(self):
+        """(3x3 conv + ReLU module, final nn.Conv2d 1x1) of the last stack's heat-map head when it is the reference's
+        CenterNetDetector layout (detectors/centernet_detector.py:11-15) and fits rr_hm_tail_collect, else None."""
+        layers = getattr(self.hm, 'detect_layer', None)
+        if layers is None or len(layers) < self.num_stacks:
+            return None
+        seq = layers[self.num_stacks - 1]
+        if not isinstance(seq, nn.Sequential) or len(seq) != 2:
+            return None
+        body, last = seq[0], seq[1]
+        ok = isinstance(last, nn.Conv2d) and tuple(last.kernel_size) == (1, 1) and tuple(last.stride) == (1, 1) \
+            and last.groups == 1 and last.bias is not None and last.out_channels == self.num_classes \
+            and last.out_channels <= 16 and last.in_channels <= 1024 and last.weight.is_cuda
+        return (body, last) if ok else None
 
     _EVAL_PATH_SLOTS = 8          # multi-scale test: one pre-allocated path per scale (cfg.Val.scales has 6)
 
@@ -161,11 +186,13 @@ class RRNet(nn.Module):
         return dets
 
     # ------------------------------------------------------------------ models/rrnet.py:140-157
-    def forward_stage1(self, feats):
+    def forward_stage1(self, feats, skip_last_hm=False):
+        """skip_last_hm: the caller produces the last stack's heat map itself (fused tail, `forward`)."""
         hms, whs, offsets = [], [], []
         for i in range(self.num_stacks):
             feat = torch.relu(feats[i])
-            hms.append(self.hm(feat, i))
+            if not (skip_last_hm and i == self.num_stacks - 1):
+                hms.append(self.hm(feat, i))
             whs.append(self.wh(feat, i))
             offsets.append(self.offset_reg(feat, i))
         return hms, whs, offsets

@@ -49,9 +49,13 @@ def _ws(nbytes, device):
 DECODE_RAW_SCORES = 0x100
 
 
-def decode_topk(hm, wh, off, K, pool=0, want_inds=True, raw_scores=False):
+PRECOLLECTED = 0x200          # RR_DECODE_PRECOLLECTED
+
+
+def decode_topk(hm, wh, off, K, pool=0, want_inds=True, raw_scores=False, precollected_ws=None):
     """models/rrnet.py:117-138 on logits.  -> dets [B,K,6] (x1,y1,x2,y2,score,cls), inds [B,K] int64.
-    raw_scores=True: hm already holds scores (RRNet._topk alone, :93-109); wh/off may then be None."""
+    raw_scores=True: hm already holds scores (RRNet._topk alone, :93-109); wh/off may then be None.
+    precollected_ws: the workspace hm_tail_collect filled for this hm (skips the sample + collect passes)."""
     hm = _f32(hm, "hm", 4)
     B, C, H, W = hm.shape
     if raw_scores and wh is None and off is None:
@@ -65,13 +69,40 @@ def decode_topk(hm, wh, off, K, pool=0, want_inds=True, raw_scores=False):
     L = _lib.lib()
     dets = torch.empty(B, K, 6, dtype=torch.float32, device=hm.device)
     inds = torch.empty(B, K, dtype=torch.int64, device=hm.device) if want_inds else None
-    ws = _ws(L.rr_decode_workspace_bytes(B, C, H, W, K), hm.device)
+    if precollected_ws is not None:
+        ws, pool = precollected_ws, int(pool) | PRECOLLECTED
+    else:
+        ws = _ws(L.rr_decode_workspace_bytes(B, C, H, W, K), hm.device)
     check(L.rr_decode_topk(_ptr(hm), _ptr(wh), _ptr(off), B, C, H, W, int(K), int(pool), _ptr(dets), _ptr(inds),
                            _ptr(ws), ws.numel(), _stream()), "rr_decode_topk")
     return dets, inds
 
 
 # --------------------------------------------------------------------------------- NMS
+
+
+def hm_tail_collect(t, weight, bias, K, ws=None, hm_out=None):
+    """Last layer of the heat-map head (1x1 conv 256 -> C + bias, detectors/centernet_detector.py:11-15) fused with
+    the decode's candidate collection: t [B,Cin,H,W] (after the head's 3x3 conv + ReLU), weight [C,Cin] or [C,Cin,1,1],
+    bias [C] -> (hm logits [B,C,H,W], ws).  `ws` (a decode workspace, or EvalPath.ws) then holds the candidate lists:
+    pass it with precollected=True to decode_topk / EvalPath.forward."""
+    t = _f32(t, "t", 4)
+    B, Cin, H, W = t.shape
+    weight = _f32(weight.reshape(weight.shape[0], -1), "weight", 2)
+    bias = _f32(bias, "bias", 1)
+    C = weight.shape[0]
+    if weight.shape[1] != Cin or bias.numel() != C:
+        raise RRNetB200Error("hm_tail_collect: weight %s / bias %s do not match t %s" % (tuple(weight.shape), tuple(bias.shape), tuple(t.shape)))
+    L = _lib.lib()
+    if ws is None:
+        ws = _ws(L.rr_decode_workspace_bytes(B, C, H, W, K), t.device)
+    if hm_out is None:
+        hm_out = torch.empty(B, C, H, W, dtype=torch.float32, device=t.device)
+    check(L.rr_hm_tail_collect(_ptr(t), _ptr(weight), _ptr(bias), B, Cin, C, H, W, int(K), _ptr(hm_out), _ptr(ws),
+                               ws.numel(), _stream()), "rr_hm_tail_collect")
+    return hm_out, ws
+
+
 def stage1_nms(dets, num_classes, thr=0.7):
     """RRNet.nms + the per-image loop of RRNet.forward for the batch, no host sync.
     -> bxyxy [B*K,5], scores [B*K], clses [B*K] (capacity rows), counts [B+1] int32 (device)."""
@@ -288,7 +319,20 @@ class EvalPath:
         self.roi_feat = torch.empty(n, feat_ch, 3, 3, **f32) if keep_roi_feat else None
         self.ws = _ws(L.rr_eval_workspace_bytes(B, C, H, W, K, feat_ch), dev)
 
-    def forward(self, hm, wh, off, feat, stage_events=None):
+    def forward_from_tail(self, t_hm, hm_weight, hm_bias, wh, off, feat, hm_out=None, stage_events=None):
+        """The same path with the heat-map head's last layer fused in: t_hm [B,Cin,H,W] is the output of
+        the head's 3x3 conv + ReLU; the 1x1 conv, the logit map and the candidate lists come from ONE pass over it
+        (rr_hm_tail_collect), then rr_eval_forward starts at the top-K selection.  -> the logits [B,C,H,W]."""
+        B, C, H, W, K, Cf = self.shape
+        if hm_out is None:
+            if getattr(self, "hm_buf", None) is None:
+                self.hm_buf = torch.empty(B, C, H, W, dtype=torch.float32, device=self.ws.device)
+            hm_out = self.hm_buf
+        hm_tail_collect(t_hm, hm_weight, hm_bias, K, ws=self.ws, hm_out=hm_out)
+        self.forward(hm_out, wh, off, feat, stage_events=stage_events, precollected=True)
+        return hm_out
+
+    def forward(self, hm, wh, off, feat, stage_events=None, precollected=False):
         """stage_events: optional list of 6 torch.cuda.Event(enable_timing=True) recorded by the library
         before decode and after each of decode / NMS / RoIAlign / head / bbox."""
         B, C, H, W, K, Cf = self.shape
@@ -301,7 +345,7 @@ class EvalPath:
         if tuple(hm.shape) != (B, C, H, W) or tuple(feat.shape) != (B, Cf, H, W):
             raise RRNetB200Error("EvalPath was built for hm %s / feat %s" % ((B, C, H, W), (B, Cf, H, W)))
         check(_lib.lib().rr_eval_forward(
-            _ptr(hm), _ptr(wh), _ptr(off), _ptr(feat), B, C, H, W, K, Cf, self.pool, self.nms_thr,
+            _ptr(hm), _ptr(wh), _ptr(off), _ptr(feat), B, C, H, W, K, Cf, (PRECOLLECTED if precollected else self.pool), self.nms_thr,
             self.roi_algo, _ptr(self.folded), self.scale, _ptr(self.dets), _ptr(self.inds), _ptr(self.bxyxy), _ptr(self.scores),
             _ptr(self.clses), _ptr(self.counts), _ptr(self.reg), _ptr(self.s1), _ptr(self.s2), _ptr(self.roi_feat),
             _ptr(self.ws), self.ws.numel(), _stream(), ev), "rr_eval_forward")

@@ -354,6 +354,78 @@ def test_head_tile_counts_and_device_count(ops, oracle_mod, n):
     assert (reg[live:] == 12345.0).all()
 
 
+# ===================================================================== stage-1 head tail fused with decode (f4)
+def _tail_inputs(B, Cin, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.relu(torch.randn(B, Cin, H, W, generator=g))                      # output of the head's 3x3 conv + ReLU
+    w = torch.randn(C, Cin, 1, 1, generator=g) * (2.0 / Cin ** 0.5)
+    b = torch.full((C,), -2.19) + 0.1 * torch.randn(C, generator=g)             # centernet_detector.py:18 bias init
+    return t, w, b
+
+
+@pytest.mark.parametrize("B,Cin,C,H,W,K", [
+    (2, 256, 10, 48, 64, 200),       # the reference's head: 256 -> 10
+    (1, 256, 10, 128, 128, 500),     # config-1 size
+    (3, 40, 2, 13, 11, 50),          # H*W % 4 != 0 (scalar loads), Cin % 8 != 0, planes = 2 (the offset head's shape)
+    (1, 64, 16, 20, 36, 300),        # the widest supported head, K close to H*W
+    (2, 32, 7, 8, 8, 64),            # whole image fits the candidate list: no threshold
+])
+def test_hm_tail_collect_vs_reference_conv_and_decode(ops, oracle_mod, B, Cin, C, H, W, K):
+    """rr_hm_tail_collect: logits against the reference layer itself (nn.Conv2d(256, planes, 1) on the CPU, fp32) at 1e-5,
+    and the decode that starts from its candidate lists bit-exact against the oracle applied to the logits it wrote."""
+    t, w, b = _tail_inputs(B, Cin, C, H, W, seed=B * 1000 + C)
+    conv = torch.nn.Conv2d(Cin, C, (1, 1))
+    with torch.no_grad():
+        conv.weight.copy_(w); conv.bias.copy_(b)
+        ref = conv(t).numpy()
+    hm, ws = ops.hm_tail_collect(dev(t), dev(w), dev(b), K)
+    assert rel_err(npy(hm), ref, floor=1e-2) < TOL                 # |logit| ~ 2..6: 1e-5 of max(|ref|, 1e-2 max|ref|)
+    x = synth.wh_offset(B, H, W, seed=7)
+    dets, inds = ops.decode_topk(hm, dev(x[0]), dev(x[1]), K, precollected_ws=ws)
+    o_dets, o_inds, _ = oracle_mod.decode(npy(hm), x[0].numpy(), x[1].numpy(), K)
+    np.testing.assert_array_equal(npy(inds), o_inds)
+    np.testing.assert_array_equal(npy(dets)[..., [0, 1, 2, 3, 5]], o_dets[..., [0, 1, 2, 3, 5]])
+    assert rel_err(npy(dets)[..., 4], o_dets[..., 4]) < TOL
+    # and it is what the unfused decode makes of the same map
+    d2, i2 = ops.decode_topk(hm, dev(x[0]), dev(x[1]), K)
+    np.testing.assert_array_equal(npy(i2), npy(inds))
+    np.testing.assert_array_equal(npy(d2), npy(dets))
+
+
+def test_hm_tail_rejects_bad_arguments(ops):
+    t, w, b = _tail_inputs(1, 32, 17, 8, 8, seed=1)
+    with pytest.raises(Exception):
+        ops.hm_tail_collect(dev(t), dev(w), dev(b), 10)            # more than 16 output planes
+    t, w, b = _tail_inputs(1, 32, 4, 8, 8, seed=1)
+    with pytest.raises(Exception):
+        ops.hm_tail_collect(dev(t), dev(w[:, :16]), dev(b), 10)    # weight does not match t
+
+
+def test_eval_path_from_tail_full_size(ops):
+    """Config-2 size: the fused entry (tail -> selection -> NMS -> RoIAlign -> head -> boxes) gives bit-identical
+    results to the unfused path fed with the logit map the tail wrote."""
+    B, C, H, W, K = 8, 10, 272, 480, 1500
+    t, w, b = _tail_inputs(B, 256, C, H, W, seed=99)
+    x = synth.eval_inputs(B, H, W, K, synth.SEED_C2)
+    hp = synth.head_params(synth.SEED_C2)
+    folded = ops.head_fold({k: v.cuda() for k, v in hp.items()})
+    td, wd, bd = dev(t), dev(w), dev(b)
+    del t
+    whd, offd, featd = dev(x["wh"]), dev(x["off"]), dev(x["feat"])
+    fused = ops.EvalPath(B, C, H, W, K, folded)
+    hm = fused.forward_from_tail(td, wd, bd, whd, offd, featd)
+    rf = fused.results()
+    ref = torch.nn.functional.conv2d(td.cpu(), w, b).numpy()
+    assert rel_err(npy(hm), ref, floor=1e-2) < TOL
+    plain = ops.EvalPath(B, C, H, W, K, folded)
+    plain.forward(hm, whd, offd, featd)
+    rp = plain.results()
+    assert rf["n"] == rp["n"] and rf["counts"] == rp["counts"] and rf["n"] > 1000
+    for key in ("bxyxy", "scores", "clses", "reg", "s1", "s2"):
+        np.testing.assert_array_equal(npy(rf[key]), npy(rp[key]))
+    np.testing.assert_array_equal(npy(fused.inds), npy(plain.inds))
+
+
 # ===================================================================== whole eval path (a1..a8)
 def test_eval_path_golden(ops):
     g = load_golden("pipeline")

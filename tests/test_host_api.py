@@ -239,16 +239,66 @@ def test_criterion_golden(host):
     targets = (gt_hms, gt_whs, gt_inds, gt_offs, gt_masks, annos.clone())
     hm_l, wh_l, off_l, s2_l = op.criterion(outs, targets)
     got = np.array([float(hm_l), float(wh_l), float(off_l), float(s2_l)])
-    assert np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])) < 2e-5, (got, g["losses"])
+    assert np.max(np.abs(got - g["losses"]) / np.abs(g["losses"])) < TOL, (got, g["losses"])      # measured: 1.2e-7
     # the fused form of the heat-map term (target rendered on the fly inside the loss) gives the same number
     from rrnet_b200.host.modules.loss.functional import focal_loss_for_hm_from_annos
     hm2 = x["hm"].clone().requires_grad_(True)
     fused = focal_loss_for_hm_from_annos(hm2, torch.from_numpy(g["annos"]).cuda(), n_obj, H * 4, W * 4)
-    assert abs(float(fused) - g["losses"][0]) / g["losses"][0] < 2e-5
+    assert abs(float(fused) - g["losses"][0]) / g["losses"][0] < TOL
     (hm_l + 0.1 * wh_l + off_l + s2_l).backward()
-    assert rel_err(npy(hm.grad), g["grad_hm"], floor=1e-3) < 1e-4
-    assert rel_err(npy(wh.grad), g["grad_wh"], floor=1e-3) < 1e-4
-    assert rel_err(npy(off.grad), g["grad_off"], floor=1e-3) < 1e-4
+    # 1e-5 of max(|ref element|, 1e-3 max|ref|): elements far below the largest gradient come out of cancelling sums
+    # (measured on the B200: 5.8e-7 / 7.0e-7 / 4.1e-7; tools/criterion_err_probe.py prints the per-element figures)
+    assert rel_err(npy(hm.grad), g["grad_hm"], floor=1e-3) < TOL
+    assert rel_err(npy(wh.grad), g["grad_wh"], floor=1e-3) < TOL
+    assert rel_err(npy(off.grad), g["grad_off"], floor=1e-3) < TOL
+
+
+class _HmHead(nn.Module):
+    """The reference's CenterNetDetector layout (detectors/centernet_detector.py:6-23): per stack
+    Sequential(3x3 conv + ReLU, 1x1 conv with bias)."""
+
+    class _Cov(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(256, 256, 3, padding=1)
+
+        def forward(self, x):
+            return torch.relu(self.conv(x))
+
+    def __init__(self, planes, num_stacks=2):
+        super().__init__()
+        self.detect_layer = nn.ModuleList([nn.Sequential(self._Cov(), nn.Conv2d(256, planes, (1, 1)))
+                                           for _ in range(num_stacks)])
+        for seq in self.detect_layer:
+            seq[-1].bias.data.fill_(-2.19)
+
+    def forward(self, x, index):
+        return self.detect_layer[index](x)
+
+
+def test_forward_with_fused_hm_tail_matches_unfused(host):
+    """RRNet.forward in eval mode with a heat-map head of the reference's shape: the fused tail (rr_hm_tail_collect)
+    and the plain head + decode give the same detections; the returned heat map is the head's output at 1e-5."""
+    torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, K = 2, 48, 64, 300
+    x = synth.eval_inputs(B, H, W, K, 77)
+    hm_head = _HmHead(10).cuda()
+    net = host.RRNet(CFG, backbone=_Identity(), hm=hm_head, wh=_Fixed(x["wh"].cuda()), offset_reg=_Fixed(x["off"].cuda())).cuda().eval()
+    net.load_state_dict({k: v.cuda() for k, v in synth.head_state_dict(synth.head_params(77)).items()}, strict=False)
+    feats = [x["feat"].cuda(), x["feat"].cuda()]
+    assert net._hm_tail() is not None
+    with torch.no_grad():
+        net.fuse_hm_tail = True
+        fused = net(feats, k=K)
+        net.fuse_hm_tail = False
+        plain = net(feats, k=K)
+    assert len(fused[0]) == 2 and rel_err(npy(fused[0][-1]), npy(plain[0][-1]), floor=1e-2) < TOL
+    # logits differ in the last bits (summation order), so a near-tie at the K-th place may flip: compare as sets of rows
+    assert abs(fused[4].shape[0] - plain[4].shape[0]) <= 2
+    a = {tuple(r) for r in npy(fused[4]).round(3).tolist()}
+    b = {tuple(r) for r in npy(plain[4]).round(3).tolist()}
+    assert len(a ^ b) <= 4
 
 
 def test_get_tp_mirror_golden(host):
