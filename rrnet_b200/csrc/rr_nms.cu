@@ -134,9 +134,32 @@ __global__ void repack_rows_kernel(const float* __restrict__ rows, int n, int di
 }
 
 // --------------------------------------------------------------------------------------------
-// Suppression mask, one 64x64 upper-triangle tile per CTA (64 threads, one row each).
+// Suppression mask, one 64x64 upper-triangle tile per CTA of 4 warps, by warp ballot: a lane owns two COLUMN
+// boxes of the tile (columns lane and lane + 32: box, area and label stay in registers for the whole tile), a warp
+// walks 16 ROW boxes (one broadcast shared-memory read per row, not per pair), every lane decides its two pairs
+// and two __ballot_sync calls assemble the row's 64-bit word, which lane (row & 15) keeps and stores.  No
+// shared-memory traffic per pair and no serial per-thread column loop (the reference's mapping, nms_kernel.cu:34-78,
+// is one thread per row looping over 64 columns).  Decision arithmetic: one IEEE divide, no contraction (--fmad=false).
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+constexpr int kMaskThreads = 128;
+// words per mask row: one per 64-box tile, padded to a multiple of 4 so that a row's words [4b, 4b+3] are one aligned
+// 32-byte sector (the pullers of the greedy scan fetch four columns of a row with one sector)
+static inline int mask_row_words(int kmax) { return ((kmax + 63) / 64 + 3) & ~3; }
+
+__device__ __forceinline__ bool nms_pair(const float4& a, float area_a, const float4& q, float area_q, float o,
+                                         double thr, int ge, bool zero_hits) {
+    float w = __fadd_rn(__fsub_rn(fminf(a.z, q.z), fmaxf(a.x, q.x)), o);
+    float h = __fadd_rn(__fsub_rn(fminf(a.w, q.w), fmaxf(a.y, q.y)), o);
+    w = fmaxf(w, 0.0f);
+    h = fmaxf(h, 0.0f);
+    const float inter = __fmul_rn(w, h);
+    if (!(inter > 0.0f || zero_hits)) return false;
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_q), inter);
+    const double iou = (double)__fdiv_rn(inter, uni);
+    return ge ? (iou >= thr) : (iou > thr);
+}
+
+__global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ sbox, const int* __restrict__ slab,
                 int n, int Kmax, int W, int T, double thr, float o, int ge,
                 unsigned long long* __restrict__ mask) {
@@ -155,56 +178,121 @@ nms_mask_kernel(const float4* __restrict__ sbox, const int* __restrict__ slab,
     // labels ascend along the list: the tiles share a label iff last(row tile) >= first(col tile)
     if (lb[min(rt * 64 + 63, n - 1)] < lb[ct * 64]) return;
 
-    __shared__ float4 c_box[64];
-    __shared__ float c_area[64];
-    __shared__ int c_lab[64];
-    const int tid = threadIdx.x;
-    const int col_n = min(64, n - ct * 64);
-    if (tid < col_n) {
-        float4 q = bx[ct * 64 + tid];
-        c_box[tid] = q;
-        c_area[tid] = __fmul_rn(__fadd_rn(__fsub_rn(q.z, q.x), o), __fadd_rn(__fsub_rn(q.w, q.y), o));
-        c_lab[tid] = lb[ct * 64 + tid];
+    __shared__ float4 r_box[64];
+    __shared__ float2 r_al[64];                       // (area, label bits) of the row boxes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) {
+        const int i = rt * 64 + tid;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int la = -1;                                   // rows past the list never match a label
+        if (i < n) { a = bx[i]; la = lb[i]; }
+        r_box[tid] = a;
+        r_al[tid] = make_float2(__fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), o), __fadd_rn(__fsub_rn(a.w, a.y), o)),
+                                __int_as_float(la));
+    }
+    // this lane's two column boxes
+    float4 q[2];
+    float area_q[2];
+    int lq[2], jq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        jq[h] = ct * 64 + 32 * h + lane;
+        q[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        lq[h] = -2;                                    // columns past the list never match either
+        if (jq[h] < n) { q[h] = bx[jq[h]]; lq[h] = lb[jq[h]]; }
+        area_q[h] = __fmul_rn(__fadd_rn(__fsub_rn(q[h].z, q[h].x), o), __fadd_rn(__fsub_rn(q[h].w, q[h].y), o));
     }
     __syncthreads();
-    const int i = rt * 64 + tid;
-    if (i >= n) return;
-    const float4 a = bx[i];
-    const int la = lb[i];
-    const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), o), __fadd_rn(__fsub_rn(a.w, a.y), o));
     // IoU of a pair with empty intersection is 0/u: suppresses only if 0 cmp thr holds
     const bool zero_hits = ge ? (0.0 >= thr) : (0.0 > thr);
-    unsigned long long bits = 0;
-    const int start = (rt == ct) ? tid + 1 : 0;
-    for (int j = start; j < col_n; ++j) {
-        if (c_lab[j] != la) continue;
-        const float4 q = c_box[j];
-        float w = __fadd_rn(__fsub_rn(fminf(a.z, q.z), fmaxf(a.x, q.x)), o);
-        float h = __fadd_rn(__fsub_rn(fminf(a.w, q.w), fmaxf(a.y, q.y)), o);
-        w = fmaxf(w, 0.0f);
-        h = fmaxf(h, 0.0f);
-        const float inter = __fmul_rn(w, h);
-        if (inter > 0.0f || zero_hits) {
-            const float uni = __fsub_rn(__fadd_rn(area_a, c_area[j]), inter);
-            const double iou = (double)__fdiv_rn(inter, uni);
-            if (ge ? (iou >= thr) : (iou > thr)) bits |= 1ull << j;
-        }
+    unsigned long long mine = 0ull;
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r) {
+        const int rl = warp * 16 + r, i = rt * 64 + rl;
+        const float4 a = r_box[rl];                    // warp-uniform address: broadcast
+        const float2 al = r_al[rl];
+        const int la = __float_as_int(al.y);
+        const bool hit0 = lq[0] == la && jq[0] > i && nms_pair(a, al.x, q[0], area_q[0], o, thr, ge, zero_hits);
+        const bool hit1 = lq[1] == la && jq[1] > i && nms_pair(a, al.x, q[1], area_q[1], o, thr, ge, zero_hits);
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit0), m1 = __ballot_sync(0xffffffffu, hit1);
+        if (lane == r) mine = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
     }
-    mask[((size_t)g * Kmax + i) * W + ct] = bits;
+    const int i = rt * 64 + warp * 16 + lane;
+    if (lane < 16 && i < n) mask[((size_t)g * Kmax + i) * W + ct] = mine;
 }
 
 // --------------------------------------------------------------------------------------------
 // Greedy reduce of one segment (one CTA).  keep_out[g*Kmax + s0 + t] = t-th accepted box of
 // the segment: its list position, or map[position] when `map` is given.
+//
+// The chain over the segment's 64-box tiles is serial by nature; what it must NOT contain is a memory round trip
+// per tile.  Three roles, hand-over through flags in shared memory:
+//   * warp 0, the RESOLVER: for tile t it takes the tile's diagonal words and the words of the next kNear columns
+//     from a shared-memory ring, walks the not-yet-suppressed bits in order (one shared-memory read per KEPT box)
+//     and folds the kept rows' near words into the removal words of the next kNear tiles with warp OR-reductions.
+//   * warps 1..7, the LOADERS: run up to kRing tiles ahead and copy those (1 + kNear) x 64 words per tile from the
+//     mask into the ring, so the L2 latency never sits on the chain.
+//   * warps 8..31, the PULLERS: a warp owns a column word w (round robin) and ORs, over all tiles t <= w - kNear - 1
+//     as they get resolved, the words [row][w] of the kept rows - many independent loads in flight, one writer per
+//     removal word, no atomics; the resolver needs the word kNear + 1 steps after the last tile it depends on.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+#ifdef RR_SCAN_TRACE
+__device__ long long g_scan_trace[8];
+#define SCAN_LAP(i) do { const long long n_ = clock64(); tr_[i] += n_ - lap_; lap_ = n_; } while (0)
+#else
+#define SCAN_LAP(i) do { } while (0)
+#endif
+constexpr int kScanThreads2 = 640;                      // 102 registers per thread: the resolver keeps a tile's diagonal words in registers
+constexpr int kNear = 3;                 // columns t+1 .. t+kNear come from the ring
+constexpr int kRing = 16;                // tiles the loaders may run ahead
+constexpr int kRingWords = 64 * (1 + kNear);
+// Warp w issues from scheduler w % 4.  The resolver's chain is latency bound, so it gets scheduler 0 to itself: warps
+// 4, 8, .. exit at once and the polling roles live on the other three schedulers.
+constexpr int kWorkerWarps = (kScanThreads2 / 32) * 3 / 4;   // 15 warps with w % 4 != 0
+constexpr int kLoaderWarps = 4;
+constexpr int kPullerWarps = kWorkerWarps - kLoaderWarps;
+
+// Hand-over between the roles: data first, then the flag, both as volatile shared-memory stores of ONE thread (or plain
+// stores of a warp, __syncwarp, then the flag).  Shared-memory accesses of a warp are performed in issue order and there
+// is no cache in between, so a reader that sees the flag sees the data; the compiler keeps volatile accesses in order.
+// A memory fence here (__threadfence_block = MEMBAR.SC.CTA, or fence.acq_rel.cta) also waits for the thread's GLOBAL
+// stores in flight (the keep list): measured 5-6 k cycles per tile, i.e. the whole chain.  -DRR_SCAN_FENCE restores it.
+__device__ __forceinline__ void scan_release() {
+#ifdef RR_SCAN_FENCE
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
+    asm volatile("" ::: "memory");
+#endif
+}
+
+// back-off of a polling worker lane: an ALU-only delay.  NANOSLEEP stalls the resolver (see the kernel comment).
+__device__ __forceinline__ void scan_backoff() {
+#ifdef RR_SCAN_NANOSLEEP
+    __nanosleep(100);
+#else
+    const long long t = clock64();
+    while (clock64() - t < 150) { }
+#endif
+}
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kScanThreads2, 1)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ seg_off,
-                int segs_per_group, int Kmax, int W, const int* __restrict__ map,
+                int segs_per_group, int Kmax, int W,
                 int* __restrict__ keep_out, int* __restrict__ keep_cnt) {
-    extern __shared__ unsigned long long s_remv[];       // [W]
-    __shared__ unsigned long long s_diag[64];
-    __shared__ unsigned long long s_kept;
-    const int g = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ unsigned long long s_dyn[];        // remv [W] | kept [W] | colflag [W] (int)
+    __shared__ unsigned long long s_ring[kRing][kRingWords];      // [slot][row][0 = diagonal, 1.. = near columns]
+    __shared__ int s_ready[kRing];                       // tile index + 1 whose words sit in the slot
+    __shared__ int s_done;                               // tiles resolved
+    unsigned long long* s_remv = s_dyn;
+    unsigned long long* s_kept = s_dyn + W;
+    int* s_colflag = reinterpret_cast<int*>(s_dyn + 2 * W);
+    const int g = blockIdx.y, s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s0 = seg_off[g * (segs_per_group + 1) + s];
     const int s1 = seg_off[g * (segs_per_group + 1) + s + 1];
     if (s1 <= s0) {
@@ -212,69 +300,198 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
         return;
     }
     const unsigned long long* m = mask + (size_t)g * Kmax * W;
-    const int t0 = s0 >> 6, t1 = (s1 - 1) >> 6;
-    for (int w = t0 + tid; w <= t1; w += blockDim.x) s_remv[w] = 0ull;
-    int nk = 0;                                           // meaningful in warp 0
-    for (int t = t0; t <= t1; ++t) {
-        const int row0 = t << 6;
-        if (tid < 64) {
-            int r = row0 + tid;
-            s_diag[tid] = (r >= s0 && r < s1) ? m[(size_t)r * W + t] : 0ull;
-        }
-        __syncthreads();
-        if (tid < 32) {
+    const int t0 = s0 >> 6, t1 = (s1 - 1) >> 6, ntile = t1 - t0 + 1;
+    for (int w = t0 + tid; w <= t1; w += blockDim.x) { s_remv[w] = 0ull; s_colflag[w] = 0; }
+    if (tid < kRing) s_ready[tid] = 0;
+    if (tid == 0) s_done = 0;
+    __syncthreads();
+    volatile int* v_done = &s_done;
+    volatile int* v_ready = s_ready;
+    volatile int* v_colflag = s_colflag;
+
+    if (warp == 0) {
+        // ------------------------------ resolver ------------------------------
+        // Everything below is executed by all 32 lanes in lock step (uniform polls, no `if (lane == 0)` branches): a warp
+        // that reaches a collective in a diverged state takes the slow BRA.DIV path (measured: ~2 k cycles per collective).
+        unsigned long long carry[kNear];                 // near contributions to tiles t, t+1, .. (from earlier tiles)
+#pragma unroll
+        for (int j = 0; j < kNear; ++j) carry[j] = 0ull;
+        int nk = 0;
+#ifdef RR_SCAN_TRACE
+        long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lap_ = clock64();
+#endif
+        for (int k = 0; k < ntile; ++k) {
+            const int t = t0 + k, row0 = t << 6, slot = k % kRing;
+            SCAN_LAP(5);
+            while (v_ready[slot] != k + 1) { }
+            SCAN_LAP(0);
+            if (k > kNear) { while (v_colflag[t] == 0) { } }
+            asm volatile("" ::: "memory");
+            SCAN_LAP(1);
             const int lo = max(s0, row0) - row0, hi = min(s1, row0 + 64) - row0;   // live bit range
-            unsigned long long valid = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
-            unsigned long long cur = s_remv[t] | ~valid;
-            unsigned long long kept = 0ull;
-#pragma unroll 8
+            const unsigned long long valid = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&s_remv[t]) | carry[0] | ~valid;
+            // the 64 diagonal words -> registers (broadcast reads, all issued before the chain), then 64 steps with
+            // compile-time bit positions on registers only: test / predicated OR, no memory access on the chain
+            unsigned d_lo[64], d_hi[64];
+            const unsigned long long* ringp = s_ring[slot];
+#pragma unroll
             for (int bit = 0; bit < 64; ++bit) {
-                if (!((cur >> bit) & 1ull)) {
-                    kept |= 1ull << bit;
-                    cur |= s_diag[bit];
-                }
+                const unsigned long long dd = ringp[bit * (1 + kNear)];
+                d_lo[bit] = (unsigned)dd; d_hi[bit] = (unsigned)(dd >> 32);
+                asm volatile("" : "+r"(d_lo[bit]), "+r"(d_hi[bit]));          // materialise now: not sunk into the chain below
             }
-            if (tid == 0) s_kept = kept;
+            unsigned c_lo = (unsigned)cur, c_hi = (unsigned)(cur >> 32), k_lo = 0u, k_hi = 0u;
+#pragma unroll
+            for (int bit = 0; bit < 32; ++bit) {                              // two dependent operations per step
+                if (!(c_lo & (1u << bit))) { k_lo |= 1u << bit; c_lo |= d_lo[bit]; c_hi |= d_hi[bit]; }
+            }
+#pragma unroll
+            for (int bit = 0; bit < 32; ++bit) {                              // rows 32..63 only suppress boxes 33..63
+                if (!(c_hi & (1u << bit))) { k_hi |= 1u << bit; c_hi |= d_hi[32 + bit]; }
+            }
+            const unsigned long long kept = ((unsigned long long)k_hi << 32) | k_lo;
+            SCAN_LAP(2);
+            // near columns: the kept rows' words of columns t+1 .. t+kNear (lane l owns rows l and l + 32), OR-reduced over
+            // the warp with a shuffle butterfly (the three reductions interleave)
+            const bool k0 = (kept >> lane) & 1ull, k1 = (kept >> (lane + 32)) & 1ull;
+            unsigned long long nearw[kNear];
+#pragma unroll
+            for (int j = 0; j < kNear; ++j) {
+                const unsigned long long a = ringp[lane * (1 + kNear) + 1 + j], b2 = ringp[(lane + 32) * (1 + kNear) + 1 + j];
+                nearw[j] = (k0 ? a : 0ull) | (k1 ? b2 : 0ull);
+            }
+            SCAN_LAP(6);
+            asm volatile("" ::: "memory");
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&s_kept[t]) = kept;
+            if (lane == 0) *v_done = k + 1;                           // pullers may use the tile, loaders may reuse the slot
+            SCAN_LAP(7);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < kNear; ++j) nearw[j] |= __shfl_xor_sync(0xffffffffu, nearw[j], o);
+#pragma unroll
+            for (int j = 0; j < kNear; ++j) carry[j] = (j + 1 < kNear ? carry[j + 1] : 0ull) | nearw[j];
+            SCAN_LAP(3);
             int* out = keep_out + (size_t)g * Kmax + s0 + nk;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                int bit = tid + 32 * half;
+                const int bit = lane + 32 * half;
                 if ((kept >> bit) & 1ull) {
-                    int idx = __popcll(kept & ((1ull << bit) - 1ull));
-                    int pos = row0 + bit;
-                    out[idx] = map ? map[(size_t)g * Kmax + pos] : pos;
+                    const int idx = __popcll(kept & ((1ull << bit) - 1ull));
+                    out[idx] = row0 + bit;       // list position; nms_map_kernel translates afterwards (a global LOAD here sat on the chain)
                 }
             }
             nk += __popcll(kept);
+            SCAN_LAP(4);
         }
-        __syncthreads();
-        const unsigned long long kept = s_kept;
-        // OR the kept rows' mask words into remv for every later tile.  The 64 rows are split in 4 groups of
-        // 16 bits handled by different threads (up to 16 independent loads in flight each) and merged with a
-        // shared-memory atomicOr, so a tile costs one or two L2 round trips instead of eight.
-        const int nw = t1 - t;                               // words t+1 .. t1
-        for (int it = tid; it < nw * 4; it += blockDim.x) {
-            const int w = t + 1 + (it >> 2), grp = it & 3;
-            unsigned long long kk = (kept >> (16 * grp)) & 0xffffull;
-            if (!kk) continue;
-            unsigned long long v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                v[u] = 0ull;
-                if (kk) {
-                    int bit = __ffsll((long long)kk) - 1;
-                    kk &= kk - 1ull;
-                    v[u] = m[(size_t)(row0 + 16 * grp + bit) * W + w];
-                }
-            }
-            unsigned long long acc = 0ull;
-#pragma unroll
-            for (int u = 0; u < 16; ++u) acc |= v[u];
-            if (acc) atomicOr(&s_remv[w], acc);
-        }
-        // the next iteration's first barrier orders these s_remv writes before they are read
+#ifdef RR_SCAN_TRACE
+        if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { for (int i = 0; i < 8; ++i) g_scan_trace[i] = tr_[i]; g_scan_trace[5] = ntile; }
+#endif
+        if (lane == 0) keep_cnt[g * segs_per_group + s] = nk;
+        return;
     }
-    if (tid == 0) keep_cnt[g * segs_per_group + s] = nk;
+
+    if ((warp & 3) == 0) return;                          // scheduler 0 belongs to the resolver
+    const int wk = warp - 1 - (warp >> 2);                // 0 .. kWorkerWarps-1 over the warps with w % 4 != 0
+    if (wk < kLoaderWarps) {
+        // ------------------------------ loaders ------------------------------
+        for (int k = wk; k < ntile; k += kLoaderWarps) {
+            const int t = t0 + k, slot = k % kRing;
+            if (k >= kRing) {                                         // the slot's previous tile must be resolved
+                while (*v_done < k - kRing + 1) scan_backoff();
+            }
+            unsigned long long v[2][1 + kNear];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = (t << 6) + 32 * h + lane;
+                const bool on = r >= s0 && r < s1;
+                const unsigned long long* row = m + (size_t)r * W + t;
+#pragma unroll
+                for (int j = 0; j <= kNear; ++j) v[h][j] = (on && t + j <= t1) ? __ldcg(row + j) : 0ull;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j <= kNear; ++j)
+                    *reinterpret_cast<volatile unsigned long long*>(&s_ring[slot][(32 * h + lane) * (1 + kNear) + j]) = v[h][j];
+            __syncwarp();
+            if (lane == 0) {
+                scan_release();
+                v_ready[slot] = k + 1;
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ pullers ------------------------------
+    // A warp owns a block of four consecutive column words [4b, 4b+3]: the four words of a mask row are one aligned
+    // 32-byte sector.  Column w takes its far contributions from the tiles t <= w - kNear - 1, so the block first
+    // accumulates the tiles that all four columns need, then one more tile per column, publishing each column as soon
+    // as its own range is complete.
+    auto pull_tiles = [&](int ta, int tb, int w4, unsigned long long (&acc)[4]) {      // tiles ta..tb (<= 4 of them)
+        ulonglong2 v[4][2][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = ta + u;
+            unsigned long long kept = 0ull;
+            if (t <= tb) kept = *reinterpret_cast<volatile unsigned long long*>(&s_kept[t]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool on = (kept >> (lane + 32 * h)) & 1ull;
+                const ulonglong2* src = reinterpret_cast<const ulonglong2*>(m + ((size_t)(t << 6) + lane + 32 * h) * W + w4);
+                v[u][h][0] = on ? __ldcg(src) : make_ulonglong2(0ull, 0ull);
+                v[u][h][1] = on ? __ldcg(src + 1) : make_ulonglong2(0ull, 0ull);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                acc[0] |= v[u][h][0].x; acc[1] |= v[u][h][0].y; acc[2] |= v[u][h][1].x; acc[3] |= v[u][h][1].y;
+            }
+    };
+    auto publish = [&](int w, unsigned long long a) {
+        a |= __shfl_xor_sync(0xffffffffu, a, 16); a |= __shfl_xor_sync(0xffffffffu, a, 8); a |= __shfl_xor_sync(0xffffffffu, a, 4);
+        a |= __shfl_xor_sync(0xffffffffu, a, 2); a |= __shfl_xor_sync(0xffffffffu, a, 1);
+        if (lane == 0 && w <= t1 && w >= t0 + kNear + 1) {
+            *reinterpret_cast<volatile unsigned long long*>(&s_remv[w]) = a;
+            scan_release();
+            v_colflag[w] = 1;
+        }
+    };
+    for (int blk = ((t0 + kNear + 1) >> 2) + (wk - kLoaderWarps); 4 * blk <= t1; blk += kPullerWarps) {
+        const int w4 = 4 * blk;
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        const int common = w4 - kNear - 1;                            // last tile that all four columns need
+        for (int ta = t0; ta <= common; ta += 4) {
+            const int tb = min(ta + 3, common);
+            while (*v_done < tb - t0 + 1) scan_backoff();
+            pull_tiles(ta, tb, w4, acc);
+        }
+        publish(w4, acc[0]);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {                                 // column w4 + j also needs tile common + j
+            const int t = common + j;
+            if (t >= t0 && t <= t1) {
+                while (*v_done < t - t0 + 1) scan_backoff();
+                pull_tiles(t, t, w4, acc);
+            }
+            publish(w4 + j, acc[j]);
+        }
+    }
+}
+
+// keep_out[g*Kmax + s0 + i] (i < keep_cnt of the segment): list position -> map[position]
+__global__ void __launch_bounds__(256)
+nms_map_kernel(const int* __restrict__ seg_off, int segs_per_group, int Kmax, const int* __restrict__ map,
+               int* __restrict__ keep_out, const int* __restrict__ keep_cnt) {
+    const int g = blockIdx.z, s = blockIdx.y;
+    const int s0 = seg_off[g * (segs_per_group + 1) + s];
+    const int n = keep_cnt[g * segs_per_group + s];
+    int* out = keep_out + (size_t)g * Kmax + s0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = map[(size_t)g * Kmax + out[i]];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -329,21 +546,26 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
                             int ge_cmp, unsigned long long* mask, const int* map, int* keep_out,
                             int* keep_cnt, cudaStream_t st) {
     int rc = 0;
-    const int W = (Kmax + 63) / 64, T = W;
+    const int T = (Kmax + 63) / 64, W = mask_row_words(Kmax);
     const long long pairs = (long long)T * (T + 1) / 2;
     if (pairs > 0x7fffffffLL) return RR_E_RANGE;
     dim3 gm((unsigned)pairs, (unsigned)G);
-    nms_mask_kernel<<<gm, 64, 0, st>>>(sbox, slab, n, Kmax, W, T, thr, pixel_offset ? 1.0f : 0.0f,
+    nms_mask_kernel<<<gm, kMaskThreads, 0, st>>>(sbox, slab, n, Kmax, W, T, thr, pixel_offset ? 1.0f : 0.0f,
                                        ge_cmp ? 1 : 0, mask);
     RR_LAUNCHED_K(rc, "nms_mask_kernel", st);
     dim3 gs((unsigned)segs_per_group, (unsigned)G);
-    size_t smem = (size_t)W * sizeof(unsigned long long);
-    if (smem > 48 * 1024) {
+    size_t smem = (size_t)W * (2 * sizeof(unsigned long long) + sizeof(int));
+    if (smem > 16 * 1024) {
         if (smem > 200 * 1024) return RR_E_RANGE;
         RR_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     }
-    nms_scan_kernel<<<gs, 1024, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, map, keep_out, keep_cnt);
+    nms_scan_kernel<<<gs, kScanThreads2, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, keep_out, keep_cnt);
     RR_LAUNCHED_K(rc, "nms_scan_kernel", st);
+    if (map) {                                       // kept list positions -> the caller's row indices
+        dim3 gmap((unsigned)min((n + 255) / 256, 64), (unsigned)segs_per_group, (unsigned)G);
+        nms_map_kernel<<<gmap, 256, 0, st>>>(seg_off, segs_per_group, Kmax, map, keep_out, keep_cnt);
+        RR_LAUNCHED_K(rc, "nms_map_kernel", st);
+    }
     return rc;
 }
 
@@ -362,7 +584,7 @@ static Stage1Ws carve_stage1(void* ws, int B, int K, int C) {
     w.seg_off = cv.take<int>((size_t)B * (C + 1));
     w.keep_pos = cv.take<int>((size_t)B * K);
     w.keep_cnt = cv.take<int>((size_t)B * C);
-    w.mask = cv.take<unsigned long long>((size_t)B * K * ((K + 63) / 64));
+    w.mask = cv.take<unsigned long long>((size_t)B * K * mask_row_words(K));
     w.bytes = cv.off;
     return w;
 }
@@ -398,7 +620,7 @@ static GenericWs carve_generic(void* ws, int M) {
     w.sbox = cv.take<float4>((size_t)M);
     w.slab = cv.take<int>((size_t)M);
     w.ssrc = cv.take<int>((size_t)M);
-    w.mask = cv.take<unsigned long long>((size_t)M * ((M + 63) / 64));
+    w.mask = cv.take<unsigned long long>((size_t)M * mask_row_words(M));
     w.bytes = cv.off;
     return w;
 }
@@ -449,6 +671,10 @@ RR_API int rr_nms_batched(const float* boxes, const float* scores, const int32_t
                               w.ssrc, keep_idx, keep_count, st);
     return rc ? rc : r2;
 }
+
+#ifdef RR_SCAN_TRACE
+RR_API int rr_debug_scan_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, rr::g_scan_trace, sizeof(long long) * 8); }
+#endif
 
 // ---- legacy `_nms` ABI (ext/nms/nms/gpu_nms.hpp:1-2) -----------------------------------------
 namespace {

@@ -379,7 +379,17 @@ def test_hm_tail_collect_vs_reference_conv_and_decode(ops, oracle_mod, B, Cin, C
         conv.weight.copy_(w); conv.bias.copy_(b)
         ref = conv(t).numpy()
     hm, ws = ops.hm_tail_collect(dev(t), dev(w), dev(b), K)
-    assert rel_err(npy(hm), ref, floor=1e-2) < TOL                 # |logit| ~ 2..6: 1e-5 of max(|ref|, 1e-2 max|ref|)
+    # a logit is a 256-term sum that partly cancels (|logit| <= ~6, sum of |terms| ~ 10): the fp32 rounding error scales
+    # with the terms, not with the result, so it is measured against max(|ref|, 0.1 max|ref|).  The CPU convolution sums in
+    # blocked order, this kernel in channel order - like cuDNN's fp32 kernel, against which it is bit-identical
+    assert rel_err(npy(hm), ref, floor=0.1) < TOL
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref_gpu = torch.nn.functional.conv2d(dev(t), dev(w), dev(b))
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert rel_err(npy(hm), npy(ref_gpu), floor=0.1) < 2e-6
     x = synth.wh_offset(B, H, W, seed=7)
     dets, inds = ops.decode_topk(hm, dev(x[0]), dev(x[1]), K, precollected_ws=ws)
     o_dets, o_inds, _ = oracle_mod.decode(npy(hm), x[0].numpy(), x[1].numpy(), K)
@@ -416,7 +426,7 @@ def test_eval_path_from_tail_full_size(ops):
     hm = fused.forward_from_tail(td, wd, bd, whd, offd, featd)
     rf = fused.results()
     ref = torch.nn.functional.conv2d(td.cpu(), w, b).numpy()
-    assert rel_err(npy(hm), ref, floor=1e-2) < TOL
+    assert rel_err(npy(hm), ref, floor=0.1) < TOL
     plain = ops.EvalPath(B, C, H, W, K, folded)
     plain.forward(hm, whd, offd, featd)
     rp = plain.results()

@@ -293,7 +293,7 @@ def test_forward_with_fused_hm_tail_matches_unfused(host):
         fused = net(feats, k=K)
         net.fuse_hm_tail = False
         plain = net(feats, k=K)
-    assert len(fused[0]) == 2 and rel_err(npy(fused[0][-1]), npy(plain[0][-1]), floor=1e-2) < TOL
+    assert len(fused[0]) == 2 and rel_err(npy(fused[0][-1]), npy(plain[0][-1]), floor=0.1) < TOL
     # logits differ in the last bits (summation order), so a near-tie at the K-th place may flip: compare as sets of rows
     assert abs(fused[4].shape[0] - plain[4].shape[0]) <= 2
     a = {tuple(r) for r in npy(fused[4]).round(3).tolist()}
