@@ -257,12 +257,14 @@ int rr_focal_fwd_bwd(const float* logits, const float* gt, int64_t n, float upst
 
 /* ------------------------------------------------------------------------------------------
  * Fused target render + heat-map focal loss: rr_render_targets' heat-map (to_heatmap,
- * datasets/transforms/functional.py:230-262) is evaluated on the fly inside the focal loss
+ * datasets/transforms/functional.py:230-262) is rendered tile by tile in shared memory inside the focal loss
  * (modules/loss/functional.py:25-51 + operators/rrnet_operator.py:55) and never written to
  * memory -- the training step's heat-map term straight from the padded annotations.
  *   logits [B,cls_num,img_h/sf,img_w/sf] (img_w/sf a multiple of 4), annos [B,max_n,8], n_obj [B]
  *   forward : stats [4] = loss, pos_sum, neg_sum, num_pos; gt_out (optional, may be NULL) receives
  *             the rendered heat-map as well.      backward: grad = upstream * dloss/dlogits.
+ *   fwd_bwd : both in ONE pass over the logits (stats and grad = upstream * dloss/dlogits): num_pos, which scales
+ *             the gradient, is counted from the annotations first (distinct (class, centre cell) pairs).
  * ---------------------------------------------------------------------------------------- */
 size_t rr_focal_render_workspace_bytes(int B, int cls_num, int img_h, int img_w, int scale_factor);
 int rr_focal_render_forward(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
@@ -271,6 +273,9 @@ int rr_focal_render_forward(const float* logits, const float* annos, const int32
 int rr_focal_render_backward(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
                              int img_h, int img_w, int scale_factor, int cls_num,
                              const float* stats, float upstream, float* grad, void* stream);
+int rr_focal_render_fwd_bwd(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
+                            int img_h, int img_w, int scale_factor, int cls_num, float upstream,
+                            float* stats, float* grad, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of rr_roi_align (training; SURVEY 8b `_backward`): grad_feat [B,C,H,W] = d loss / d feat of

@@ -48,6 +48,7 @@ SIGNATURES = {
     "rr_focal_fwd_bwd": (c_int, [P, P, c_int64, c_float, P, P, P, c_size_t, P]),
     "rr_focal_render_workspace_bytes": (c_size_t, [c_int] * 5),
     "rr_focal_render_forward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "rr_focal_render_fwd_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, c_size_t, P]),
     "rr_ap_match": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "rr_stage2_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P, P]),
     "rr_regl1_fwd_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P]),

@@ -23,6 +23,7 @@ constexpr float kLo = 1e-4f, kHi = 1.0f - 1e-4f;
 struct FocalWs {
     double* partial;        // [grid][3]
     unsigned int* ticket;   // [1]
+    int* num_pos;           // [1]  centre count of the fused render + focal forward+backward
     size_t bytes;
 };
 static int focal_grid(long long n) {
@@ -35,6 +36,7 @@ static FocalWs carve_focal(void* ws, size_t max_grid = (size_t)kSMs * 8) {
     FocalWs w;
     w.partial = cv.take<double>(max_grid * 3);
     w.ticket = cv.take<unsigned int>(1);
+    w.num_pos = cv.take<int>(1);
     w.bytes = cv.off;
     return w;
 }
@@ -211,40 +213,45 @@ focal_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__
 }
 
 // --------------------------------------------------------------------------------------------
-// Fused target render + focal loss: the ground-truth heat-map is never materialised.
-// A CTA owns kFusedPix consecutive pixels of one (image, class) plane.  It filters the image's
-// annotation rows for its class into shared memory (geometry as rr_render.cu), every thread
-// evaluates gt = max over those objects' Gaussians for its 16 pixels in registers and feeds the
-// focal term (forward) or its derivative (backward).  HBM traffic: the logits once per pass
-// (+ the gradient write), B*max_n*32 bytes of annotations -- versus rendering the map (1 write)
-// and reading it back twice in the unfused sequence.
+// Fused target render + focal loss: the ground-truth heat-map never reaches HBM.
+// A CTA owns kFusedPix consecutive pixels of one (image, class) plane as a TILE IN SHARED MEMORY.  It filters the
+// image's annotation rows for its class into shared memory (geometry as rr_render.cu), its warps splat the windows
+// of those objects into the tile (one warp per object, hm = max(hm, G) by atomicMax on the uint bit pattern: the same
+// values and the same order independence as render_kernel) - only window pixels are evaluated, like the stand-alone
+// render - and then every thread takes its 16 pixels through the focal term and / or its derivative.
+//   forward            : logits once                      (B*C*h*w*4 bytes)
+//   backward           : logits once + gradient write
+//   forward + backward : ONE pass, logits once + gradient write (42 MB at config 3, against 84 MB for render -> focal
+//                        fwd+bwd): the gradient scale -1/num_pos is known up front because num_pos = the number of
+//                        distinct (class, centre cell) pairs among the drawn objects (a Gaussian is 1 at its centre
+//                        and nowhere else), counted by focal_count_pos_kernel from the annotations alone.
 // --------------------------------------------------------------------------------------------
 constexpr int kFusedPix = 4096;                    // pixels per CTA (16 per thread, four float4)
 constexpr int kFusedObj = 256;                     // objects staged per round
+constexpr int kCountMax = 2048;                    // objects per image the centre count stages in shared memory
 
 struct FusedObj { float cxi, cyi, denom; int xa, xb, ya, yb; };
 
-template <bool kBackward>
+enum { kFusedFwd = 0, kFusedBwd = 1, kFusedBoth = 2 };
+
+template <int kMode>
 __device__ __forceinline__ void fused_body(const float* __restrict__ logits, const float* __restrict__ annos,
                                            const int* __restrict__ n_obj, int max_n, int img_w, int Hh, int Wh,
                                            float sf, int cls_num, int tiles, float scale, float* __restrict__ grad,
                                            float* __restrict__ gt_out, float& pos, float& neg, int& npos) {
+    __shared__ unsigned int s_gt[kFusedPix];
     __shared__ FusedObj s_obj[kFusedObj];
     __shared__ int s_nobj;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int plane_id = blockIdx.x / tiles, tile = blockIdx.x - plane_id * tiles;     // plane = b * cls_num + c
     const int b = plane_id / cls_num, c = plane_id - b * cls_num;
     const int HW = Hh * Wh;
-    const int p0 = tile * kFusedPix + tid * 4;                                        // first of 4 consecutive pixels
-    const int row_lo = (tile * kFusedPix) / Wh, row_hi = min(tile * kFusedPix + kFusedPix - 1, HW - 1) / Wh;
-    float gt[4][4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) gt[q][e] = 0.f;
+    const int base_px = tile * kFusedPix;
+    const int row_lo = base_px / Wh, row_hi = min(base_px + kFusedPix - 1, HW - 1) / Wh;
+    for (int i = tid; i < kFusedPix; i += kFocalThreads) s_gt[i] = 0u;
     const int nb = min(n_obj[b], max_n);
     for (int base = 0; base < nb; base += kFusedObj) {
-        __syncthreads();
+        __syncthreads();                                                              // tile zeroed / previous round drawn
         if (tid == 0) s_nobj = 0;
         __syncthreads();
         const int k = base + tid;
@@ -253,46 +260,44 @@ __device__ __forceinline__ void fused_body(const float* __restrict__ logits, con
             // keep the objects of this class whose window meets this CTA's rows
             if (o.cls == c && o.xb > o.xa && o.yb > o.ya && o.yb > row_lo && o.ya <= row_hi) {
                 const int slot = atomicAdd(&s_nobj, 1);
-                s_obj[slot] = {o.cxi, o.cyi, o.denom, o.xa, o.xb, o.ya, o.yb};
+                s_obj[slot] = {o.cxi, o.cyi, o.denom, o.xa, o.xb, max(o.ya, row_lo), min(o.yb, row_hi + 1)};
             }
         }
         __syncthreads();
         const int n = s_nobj;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int p = p0 + q * (kFusedPix / 4);                                   // float4 index stride keeps loads coalesced
-            if (p >= HW) continue;
-            const int y = p / Wh, x0 = p - y * Wh;                                    // Wh % 4 == 0: the 4 pixels share a row
-            for (int j = 0; j < n; ++j) {
-                const FusedObj o = s_obj[j];
-                if (y < o.ya || y >= o.yb || x0 + 3 < o.xa || x0 >= o.xb) continue;   // quick reject for the whole group
-                const float dy = (float)y - o.cyi, dy2 = __fmul_rn(dy, dy);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int x = x0 + e;
-                    if (x >= o.xa && x < o.xb) {
-                        const float dx = (float)x - o.cxi;
-                        gt[q][e] = fmaxf(gt[q][e], expf(-__fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), dy2), o.denom)));
-                    }
+        for (int j = warp; j < n; j += kFocalThreads / 32) {                          // one warp per object window
+            const FusedObj o = s_obj[j];
+            const int ww = o.xb - o.xa, total = ww * (o.yb - o.ya);
+            for (int t = lane; t < total; t += 32) {
+                const int y = o.ya + t / ww, x = o.xa + t - (t / ww) * ww;
+                const int idx = y * Wh + x - base_px;
+                if ((unsigned)idx < (unsigned)kFusedPix) {                            // first / last row of a tile may be partial
+                    const float dx = (float)x - o.cxi, dy = (float)y - o.cyi;
+                    const float v = expf(-__fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), o.denom));   // == obj_value
+                    atomicMax(&s_gt[idx], __float_as_uint(v));
                 }
             }
         }
     }
+    __syncthreads();
     const float* zp = logits + (size_t)plane_id * HW;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int p = p0 + q * (kFusedPix / 4);
+        const int lp = tid * 4 + q * (kFusedPix / 4), p = base_px + lp;               // float4 index stride keeps loads coalesced
         if (p >= HW) continue;                                                        // HW % 4 == 0 (checked by the host)
         const float4 z = __ldg(reinterpret_cast<const float4*>(zp + p));
-        if (gt_out) *reinterpret_cast<float4*>(gt_out + (size_t)plane_id * HW + p) = make_float4(gt[q][0], gt[q][1], gt[q][2], gt[q][3]);
-        if (kBackward) {
+        const uint4 gu = *reinterpret_cast<const uint4*>(&s_gt[lp]);
+        const float g0 = __uint_as_float(gu.x), g1 = __uint_as_float(gu.y), g2 = __uint_as_float(gu.z), g3 = __uint_as_float(gu.w);
+        if (gt_out) *reinterpret_cast<float4*>(gt_out + (size_t)plane_id * HW + p) = make_float4(g0, g1, g2, g3);
+        if (kMode != kFusedFwd) {
             float4 o;
-            o.x = focal_grad(z.x, gt[q][0], scale); o.y = focal_grad(z.y, gt[q][1], scale);
-            o.z = focal_grad(z.z, gt[q][2], scale); o.w = focal_grad(z.w, gt[q][3], scale);
+            o.x = focal_grad(z.x, g0, scale); o.y = focal_grad(z.y, g1, scale);
+            o.z = focal_grad(z.z, g2, scale); o.w = focal_grad(z.w, g3, scale);
             __stcs(reinterpret_cast<float4*>(grad + (size_t)plane_id * HW + p), o);
-        } else {
-            focal_term(z.x, gt[q][0], pos, neg, npos); focal_term(z.y, gt[q][1], pos, neg, npos);
-            focal_term(z.z, gt[q][2], pos, neg, npos); focal_term(z.w, gt[q][3], pos, neg, npos);
+        }
+        if (kMode != kFusedBwd) {
+            focal_term(z.x, g0, pos, neg, npos); focal_term(z.y, g1, pos, neg, npos);
+            focal_term(z.z, g2, pos, neg, npos); focal_term(z.w, g3, pos, neg, npos);
         }
     }
 }
@@ -304,7 +309,7 @@ focal_render_forward_kernel(const float* __restrict__ logits, const float* __res
                             float* __restrict__ stats, float* __restrict__ gt_out) {
     float pos = 0.f, neg = 0.f;
     int npos = 0;
-    fused_body<false>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, 0.f, nullptr, gt_out, pos, neg, npos);
+    fused_body<kFusedFwd>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, 0.f, nullptr, gt_out, pos, neg, npos);
     if (focal_block_reduce(pos, neg, npos, partial, ticket)) {
         __threadfence();
         focal_finish(partial, stats);
@@ -321,7 +326,53 @@ focal_render_backward_kernel(const float* __restrict__ logits, const float* __re
     const float scale = upstream * ((np == 0.f) ? -1.0f : -1.0f / np);
     float pos = 0.f, neg = 0.f;
     int npos = 0;
-    fused_body<true>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, scale, grad, nullptr, pos, neg, npos);
+    fused_body<kFusedBwd>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, scale, grad, nullptr, pos, neg, npos);
+}
+
+// num_pos from the annotations: one CTA per image counts the drawn objects whose (class, centre cell) no earlier drawn
+// object of the image shares.  An object is drawn iff its class is valid and its clipped window is not empty; the
+// window then contains the centre (rr_gauss.cuh: ya <= cyi < yb, xa <= cxi < xb), where the Gaussian is exactly 1.
+__global__ void __launch_bounds__(kFocalThreads)
+focal_count_pos_kernel(const float* __restrict__ annos, const int* __restrict__ n_obj, int max_n, int img_w,
+                       int Hh, int Wh, float sf, int cls_num, int* __restrict__ num_pos) {
+    __shared__ int s_key[kCountMax];                 // (class * Hh + cy) * Wh + cx of a drawn object, -1 otherwise
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nb = min(min(n_obj[b], max_n), kCountMax);
+    for (int k = tid; k < nb; k += kFocalThreads) {
+        const ObjGauss o = obj_gauss(annos + ((size_t)b * max_n + k) * 8, img_w, Hh, Wh, sf, cls_num);
+        const int cx = (int)o.cxi, cy = (int)o.cyi;
+        const bool drawn = o.cls >= 0 && o.xb > o.xa && o.yb > o.ya && cy >= o.ya && cy < o.yb && cx >= o.xa && cx < o.xb;
+        s_key[k] = drawn ? (o.cls * Hh + cy) * Wh + cx : -1;
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int k = tid; k < nb; k += kFocalThreads) {
+        const int key = s_key[k];
+        if (key < 0) continue;
+        bool first = true;
+        for (int j = 0; j < k; ++j) first &= (s_key[j] != key);
+        mine += first;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((tid & 31) == 0 && mine) atomicAdd(num_pos, mine);
+}
+
+__global__ void __launch_bounds__(kFocalThreads)
+focal_render_fwd_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ annos,
+                            const int* __restrict__ n_obj, int max_n, int img_w, int Hh, int Wh, float sf,
+                            int cls_num, int tiles, const int* __restrict__ num_pos, float upstream,
+                            double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                            float* __restrict__ stats, float* __restrict__ grad) {
+    const int np = *num_pos;
+    const float scale = upstream * ((np == 0) ? -1.0f : -1.0f / (float)np);
+    float pos = 0.f, neg = 0.f;
+    int npos = 0;
+    fused_body<kFusedBoth>(logits, annos, n_obj, max_n, img_w, Hh, Wh, sf, cls_num, tiles, scale, grad, nullptr, pos, neg, npos);
+    if (focal_block_reduce(pos, neg, npos, partial, ticket)) {
+        __threadfence();
+        focal_finish(partial, stats);                             // stats[3] = the gt == 1 elements seen: equals *num_pos
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
 }
 
 }  // namespace rr
@@ -441,5 +492,40 @@ RR_API int rr_focal_render_backward(const float* logits, const float* annos, con
     focal_render_backward_kernel<<<(unsigned)grid, kFocalThreads, 0, (cudaStream_t)stream>>>(
         logits, annos, n_obj, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num, tiles, stats, upstream, grad);
     RR_LAUNCHED_K(rc, "focal_render_backward_kernel", (cudaStream_t)stream);
+    return rc;
+}
+
+RR_API int rr_focal_render_fwd_bwd(const float* logits, const float* annos, const int32_t* n_obj, int B, int max_n,
+                                   int img_h, int img_w, int scale_factor, int cls_num, float upstream,
+                                   float* stats, float* grad, void* ws, size_t ws_bytes, void* stream) {
+    int Hh, Wh, tiles; long long grid;
+    int rc = fused_dims(B, cls_num, img_h, img_w, scale_factor, &Hh, &Wh, &tiles, &grid);
+    if (rc) return rc;
+    if (!logits || !stats || !grad || !ws || !n_obj || max_n < 0 || (max_n > 0 && !annos)) return RR_E_BADARG;
+    if (((uintptr_t)logits & 15) || ((uintptr_t)grad & 15)) return RR_E_ALIGN;
+    if (ws_bytes < carve_focal(nullptr, (size_t)grid).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    FocalWs w = carve_focal(ws, (size_t)grid);
+    RR_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st), rc);
+    if (max_n > kCountMax) {           // more objects per image than the centre count stages: two passes (forward, then backward)
+        focal_render_forward_kernel<<<(unsigned)grid, kFocalThreads, 0, st>>>(logits, annos, n_obj, max_n, img_w, Hh, Wh,
+                                                                             (float)scale_factor, cls_num, tiles,
+                                                                             w.partial, w.ticket, stats, nullptr);
+        RR_LAUNCHED_K(rc, "focal_render_forward_kernel", st);
+        focal_render_backward_kernel<<<(unsigned)grid, kFocalThreads, 0, st>>>(
+            logits, annos, n_obj, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num, tiles, stats, upstream, grad);
+        RR_LAUNCHED_K(rc, "focal_render_backward_kernel", st);
+        return rc;
+    }
+    RR_CUDA(cudaMemsetAsync(w.num_pos, 0, sizeof(int), st), rc);
+    if (max_n > 0) {
+        focal_count_pos_kernel<<<B, kFocalThreads, 0, st>>>(annos, n_obj, max_n, img_w, Hh, Wh, (float)scale_factor, cls_num,
+                                                            w.num_pos);
+        RR_LAUNCHED_K(rc, "focal_count_pos_kernel", st);
+    }
+    focal_render_fwd_bwd_kernel<<<(unsigned)grid, kFocalThreads, 0, st>>>(logits, annos, n_obj, max_n, img_w, Hh, Wh,
+                                                                         (float)scale_factor, cls_num, tiles, w.num_pos,
+                                                                         upstream, w.partial, w.ticket, stats, grad);
+    RR_LAUNCHED_K(rc, "focal_render_fwd_bwd_kernel", st);
     return rc;
 }

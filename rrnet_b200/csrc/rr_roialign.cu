@@ -1185,10 +1185,16 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
     const int ngroups = C / kTC;
     const int t = blockIdx.x / ngroups, g = blockIdx.x - t * ngroups;
     const int n_p = tile_fill[t];
-    if (n_p == 0) return;                                            // the map was zero-filled
     const int img = t / td.tiles_per_img, trem = t - img * td.tiles_per_img;
     const int ty = trem / td.ntx, tx = trem - ty * td.ntx;
     const int px0 = tx * kTW, py0 = ty * kTH;
+    if (n_p == 0) {                                                  // no RoI touches the tile: its gradient is zero.  Every
+        const int gy = py0 + y, gx = px0 + lane;                     // element of the map is written by exactly one CTA, so
+        if (gy < H && gx < W)                                        // the map needs no memset (1.07 GB at config 2)
+            for (int c = 0; c < kTC; ++c)
+                grad_feat[(((size_t)img * C + (size_t)g * kTC + c) * H + gy) * W + gx] = 0.f;
+        return;
+    }
     float acc[kTW];
 #pragma unroll
     for (int x = 0; x < kTW; ++x) acc[x] = 0.f;
@@ -1340,9 +1346,10 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
     int rc = 0;
     RoiWs w = carve_roi(ws, n_cap, B, C, H, W);
     RR_CUDA(cudaMemsetAsync(w.zeroed, 0, w.zeroed_bytes, st), rc);
-    RR_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st), rc);
-    if (rc) return rc;
     const int force_direct = algo == 1;
+    if (force_direct || C % kTC != 0)              // the tile kernel (which writes every element, zeros included) does not run
+        RR_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st), rc);
+    if (rc) return rc;
     roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
                                                     w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
     RR_LAUNCHED_K(rc, "roi_prep_kernel", st);

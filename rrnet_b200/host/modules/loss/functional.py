@@ -40,20 +40,20 @@ def focal_loss_for_hm(pred, gt):
 
 class _FocalHMFromAnnos(torch.autograd.Function):
     """Heat-map focal loss from the padded annotations: target render fused into the loss kernels, the
-    [B,cls,h,w] target map is never materialised (rr_focal_render_forward / _backward)."""
+    [B,cls,h,w] target map is never materialised (rr_focal_render_fwd_bwd, or _forward when no gradient is needed)."""
 
     @staticmethod
     def forward(ctx, logits, annos, n_obj, img_h, img_w, scale_factor):
-        stats = ops.focal_render_forward(logits.detach(), annos, n_obj, img_h, img_w, scale_factor)
-        ctx.save_for_backward(logits, annos, n_obj, stats)
-        ctx.dims = (img_h, img_w, scale_factor)
+        if logits.requires_grad:       # loss and gradient in one pass over the logits (rr_focal_render_fwd_bwd)
+            stats, grad = ops.focal_render_fwd_bwd(logits.detach(), annos, n_obj, img_h, img_w, 1.0, scale_factor)
+            ctx.save_for_backward(grad)
+        else:
+            stats = ops.focal_render_forward(logits.detach(), annos, n_obj, img_h, img_w, scale_factor)
         return stats[0].clone()
 
     @staticmethod
     def backward(ctx, g):
-        logits, annos, n_obj, stats = ctx.saved_tensors
-        img_h, img_w, sf = ctx.dims
-        grad = ops.focal_render_backward(logits.detach(), annos, n_obj, img_h, img_w, stats, 1.0, sf)
+        (grad,) = ctx.saved_tensors
         return grad * g, None, None, None, None, None
 
 

@@ -543,6 +543,23 @@ def focal_render_forward(logits, annos, n_obj, img_h, img_w, scale_factor=4, wan
     return (stats, gt) if want_gt else stats
 
 
+def focal_render_fwd_bwd(logits, annos, n_obj, img_h, img_w, upstream=1.0, scale_factor=4):
+    """Loss AND gradient of the heat-map focal term from the padded annotations in one pass over the logits (the target
+    is rendered tile by tile in shared memory).  -> (stats [4] = loss, pos_sum, neg_sum, num_pos; grad like logits)."""
+    logits, annos, n_obj = _f32(logits, "logits", 4), _f32(annos, "annos", 3), _i32(n_obj, "n_obj")
+    B, C, h, w = logits.shape
+    if h != img_h // scale_factor or w != img_w // scale_factor or annos.shape[0] != B or annos.shape[2] != 8:
+        raise RRNetB200Error("logits must be [B,cls,img_h/sf,img_w/sf] and annos [B,max_n,8]")
+    L = _lib.lib()
+    stats = torch.empty(4, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits)
+    ws = _ws(L.rr_focal_render_workspace_bytes(B, C, int(img_h), int(img_w), int(scale_factor)), logits.device)
+    check(L.rr_focal_render_fwd_bwd(_ptr(logits), _ptr(annos), _ptr(n_obj), B, annos.shape[1], int(img_h), int(img_w),
+                                    int(scale_factor), C, float(upstream), _ptr(stats), _ptr(grad), _ptr(ws), ws.numel(),
+                                    _stream()), "rr_focal_render_fwd_bwd")
+    return stats, grad
+
+
 def focal_render_backward(logits, annos, n_obj, img_h, img_w, stats, upstream=1.0, scale_factor=4):
     logits, annos, n_obj = _f32(logits, "logits", 4), _f32(annos, "annos", 3), _i32(n_obj, "n_obj")
     B, C, h, w = logits.shape

@@ -794,6 +794,38 @@ def test_focal_render_fused_vs_unfused_and_oracle(ops, oracle_mod):
     loss, _, gref = oracle_mod.focal(z.numpy(), gts, want_grad=True)
     assert abs(float(stats_f[0]) - loss) / abs(loss) < TOL
     assert rel_err(npy(grad_f) / 0.5, gref, floor=1e-3) < TOL
+    # loss and gradient in ONE pass (num_pos counted from the annotations first): same numbers
+    stats_1, grad_1 = ops.focal_render_fwd_bwd(zd, ad, nd, img, img, 0.5)
+    assert float(stats_1[3]) == float(stats_u[3])
+    assert abs(float(stats_1[0]) - float(stats_u[0])) <= 1e-6 * abs(float(stats_u[0]))
+    assert torch.equal(grad_1, grad_f)
+
+
+@pytest.mark.parametrize("img_h,img_w", [(512, 512), (96, 176), (40, 48)])
+def test_focal_render_fwd_bwd_center_count(ops, img_h, img_w):
+    """The single-pass form needs num_pos before it has seen the map: objects sharing a centre cell and class count once,
+    objects of different classes on the same cell count twice, undrawn rows (class 0 = 'ignored', padding) not at all;
+    tile rows that do not start on a row boundary (176/4 = 44 pixels per row, 4096 % 44 != 0)."""
+    B, C = 3, 10
+    g = torch.Generator().manual_seed(img_h + img_w)
+    lists = synth.train_annos(B, img_h, img_w, 91, n_range=(8, 24))
+    a0 = lists[0]
+    dup = a0[:3].clone()                           # same boxes again: same class, same centre
+    other = a0[:2].clone(); other[:, 5] = (other[:, 5] % 10) + 1     # same centre, another class
+    ignored = a0[:2].clone(); ignored[:, 5] = 0    # class 0: python index -1 -> the last plane (functional.py:249)
+    lists[0] = torch.cat([a0, dup, other, ignored])
+    annos, n_obj = synth.pad_annos(lists)
+    z = torch.randn(B, C, img_h // 4, img_w // 4, generator=g) * 2.5 - 2.0
+    zd, ad, nd = dev(z), dev(annos), dev(n_obj)
+    gt = ops.render_targets(ad, nd, img_h, img_w)[0]
+    stats_u, grad_u = ops.focal_fwd_bwd(zd, gt, 1.0)
+    assert float(stats_u[3]) == float((gt == 1).sum())
+    stats_1, grad_1 = ops.focal_render_fwd_bwd(zd, ad, nd, img_h, img_w, 1.0)
+    assert float(stats_1[3]) == float(stats_u[3])
+    assert abs(float(stats_1[0]) - float(stats_u[0])) <= 1e-6 * abs(float(stats_u[0]))
+    assert rel_err(npy(grad_1), npy(grad_u), floor=1e-3) < 1e-6
+    _, gt_f = ops.focal_render_forward(zd, ad, nd, img_h, img_w, want_gt=True)
+    assert torch.equal(gt_f, gt)
 
 
 def test_focal_render_no_objects_and_odd_plane(ops):
@@ -803,6 +835,10 @@ def test_focal_render_no_objects_and_odd_plane(ops):
     stats = ops.focal_render_forward(z, annos, n_obj, 40, 48)
     ref = ops.focal_forward(z, torch.zeros_like(z))
     assert float(stats[3]) == 0.0 and abs(float(stats[0]) - float(ref[0])) <= 1e-6 * abs(float(ref[0]))
+    stats_1, grad_1 = ops.focal_render_fwd_bwd(z, annos, n_obj, 40, 48)
+    ref_s, ref_g = ops.focal_fwd_bwd(z, torch.zeros_like(z))
+    assert float(stats_1[3]) == 0.0 and abs(float(stats_1[0]) - float(ref_s[0])) <= 1e-6 * abs(float(ref_s[0]))
+    assert rel_err(npy(grad_1), npy(ref_g), floor=1e-3) < 1e-6
     with pytest.raises(Exception):
         ops.focal_render_forward(torch.zeros(1, 1, 4, 5).cuda(), annos[:1], n_obj[:1], 16, 20)   # row length 5: not a multiple of 4
 
