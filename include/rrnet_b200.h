@@ -60,6 +60,8 @@ int         rr_set_sm_reserve(int n_sms);
  * the caller's `capacity` CUDA events (cudaEvent_t, timing enabled) on its launch stream; events[0] is recorded on
  * `stream` by the call itself.  names[i] (optional, static strings) = kernel that ended at events[i].
  * rr_kernel_trace_end() stops the trace and returns the number of events recorded.  Not for use under graph capture. */
+/* Programmatic dependent launch between the kernels of the eval path (default on): 0 = ordinary stream order. */
+int         rr_set_pdl(int enabled);
 int         rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream);
 int         rr_kernel_trace_end(void);
 

@@ -11,6 +11,7 @@ generate_bbox_kernel(const float* __restrict__ bxyxy, const float* __restrict__ 
                      const float* __restrict__ scores, const float* __restrict__ clses,
                      const int* __restrict__ n_rois_dev, int n_cap, float scale,
                      float* __restrict__ s1, float* __restrict__ s2) {
+    RR_PDL_PROLOGUE();
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < live; i += gridDim.x * blockDim.x) {
         const float* r = bxyxy + (size_t)i * 5;
@@ -38,7 +39,7 @@ int generate_bbox_launch(const float* bxyxy, const float* reg, const float* scor
                          cudaStream_t st) {
     int rc = 0;
     int grid = (n_cap + 255) / 256;
-    generate_bbox_kernel<<<grid, 256, 0, st>>>(bxyxy, reg, scores, clses, n_rois_dev, n_cap, scale, s1, s2);
+    launch_pdl(generate_bbox_kernel, dim3(grid), dim3(256), 0, st, bxyxy, reg, scores, clses, n_rois_dev, n_cap, scale, s1, s2);
     RR_LAUNCHED_K(rc, "generate_bbox_kernel", st);
     return rc;
 }

@@ -44,6 +44,28 @@ inline void ktrace_mark(const char* name, cudaStream_t st) {
         if (_e != cudaSuccess && (rc) == 0) (rc) = (int)_e;                \
     } while (0)
 
+// Programmatic dependent launch (PDL) along the eval chain: a kernel launched with launch_pdl() may be scheduled while
+// its predecessor on the stream is still running; its threads block in pdl_wait() - the first statement of every such
+// kernel - until the predecessor grid has completed and its writes are visible.  pdl_wait() is a no-op in a kernel that
+// was launched the ordinary way, and pdl_trigger() (called right after it) lets the NEXT kernel's blocks be staged as
+// soon as all blocks of this grid are resident, so the launch latency between the ~14 short kernels of a step overlaps
+// with their execution.  Captured into CUDA graphs as programmatic dependency edges.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define RR_PDL_PROLOGUE() do { ::rr::pdl_wait(); ::rr::pdl_trigger(); } while (0)
+
+extern int g_pdl_enabled;                  // rr_set_pdl (default 1), defined in rr_api.cu
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // the launch status is picked up by RR_LAUNCHED
+}
+
 constexpr int kSMs = 148;   // B200
 // SMs the persistent kernels leave free (rr_set_sm_reserve).  Per calling host thread: the value is read when a
 // launch is issued (or captured into a graph) by that thread, so two threads driving two streams do not interfere.

@@ -52,6 +52,7 @@ __device__ __forceinline__ float pooled_value(const float* __restrict__ img, int
 __global__ void __launch_bounds__(kSampleThreads)
 decode_sample_kernel(const float* __restrict__ hm, int H, int W, int N, int K, int pool,
                      unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count) {
+    RR_PDL_PROLOGUE();
     const int b = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) count[b] = 0;
     if (N <= kCap) {                   // everything fits in the candidate list: no threshold
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kCollectThreads)
 decode_collect_kernel(const float* __restrict__ hm, int H, int W, int N, int pool,
                       const unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count,
                       unsigned long long* __restrict__ cand) {
+    RR_PDL_PROLOGUE();
     __shared__ unsigned long long s_stage[kStage];
     __shared__ int s_n;
     __shared__ unsigned s_base;
@@ -387,6 +389,7 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
                      const float* __restrict__ off, int C, int H, int W, int K, int pool, int raw,
                      const unsigned int* __restrict__ count, const unsigned long long* __restrict__ cand,
                      float* __restrict__ out_dets, long long* __restrict__ out_inds) {
+    RR_PDL_PROLOGUE();
     extern __shared__ unsigned long long s_e[];          // [P], P = pow2 >= candidates
     __shared__ int s_red[kSelectThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -450,14 +453,14 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     DecodeWs w = carve_decode(ws, B);
     const int N = C * H * W;
     if (!(mode & RR_DECODE_PRECOLLECTED)) {        // else: rr_hm_tail_collect already left count / cand in the workspace
-        decode_sample_kernel<<<B, kSampleThreads, 0, st>>>(hm, H, W, N, K, pool, w.thr_key, w.count);
+        launch_pdl(decode_sample_kernel, dim3(B), dim3(kSampleThreads), 0, st, hm, H, W, N, K, pool, w.thr_key, w.count);
         RR_LAUNCHED_K(rc, "decode_sample_kernel", st);
         // fill the machine: ~8 CTAs of 256 threads per SM in total, at least one per image
         int per_img = max(1, (kSMs * 8 + B - 1) / B);
         int max_useful = max(1, (N / 4 + kCollectThreads - 1) / kCollectThreads);
         per_img = min(per_img, max_useful);
         dim3 gc((unsigned)per_img, (unsigned)B);
-        decode_collect_kernel<<<gc, kCollectThreads, 0, st>>>(hm, H, W, N, pool, w.thr_key, w.count, w.cand);
+        launch_pdl(decode_collect_kernel, dim3(gc), dim3(kCollectThreads), 0, st, hm, H, W, N, pool, w.thr_key, w.count, w.cand);
         RR_LAUNCHED_K(rc, "decode_collect_kernel", st);
     }
     static OncePerDevice attr_once; int attr_dev;
@@ -466,7 +469,7 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
         RR_CUDA(cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
         if (rc == 0) attr_once.mark(attr_dev);
     }
-    decode_select_kernel<<<B, kSelectThreads, smem, st>>>(hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
+    launch_pdl(decode_select_kernel, dim3(B), dim3(kSelectThreads), smem, st, hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
                                                          out_dets, (long long*)out_inds);
     RR_LAUNCHED_K(rc, "decode_select_kernel", st);
     return rc;

@@ -103,6 +103,7 @@ __device__ __forceinline__ void stage_weights(float* dst, const float* __restric
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_forward_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     const float* __restrict__ f, float* __restrict__ reg) {
+    RR_PDL_PROLOGUE();
     extern __shared__ float4 s_raw[];
     float* s_w = reinterpret_cast<float*>(s_raw);                       // [2][kWChunk]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -277,7 +278,7 @@ int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, cons
         if (rc == 0) attr_once.mark(attr_dev);
     }
     const int grid = (n_cap + kHeadWarps - 1) / kHeadWarps;
-    head_forward_kernel<<<grid, kHeadThreads, kHeadSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
+    launch_pdl(head_forward_kernel, dim3(grid), dim3(kHeadThreads), kHeadSmem, st, src, n_rois_dev, n_cap, folded, reg);
     RR_LAUNCHED_K(rc, "head_forward_kernel", st);
     return rc;
 }

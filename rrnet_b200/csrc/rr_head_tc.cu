@@ -240,6 +240,7 @@ __device__ __forceinline__ float4 ld_global_f4(const float* p) {      // coheren
 __global__ void __launch_bounds__(kTcBlock, 1)
 head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                const float* __restrict__ f, float* __restrict__ reg) {
+    RR_PDL_PROLOGUE();
     extern __shared__ uint8_t s_dyn[];
     __shared__ __align__(8) unsigned long long s_full_a[kAStages];   // conv1 A stage filled (one arrival per worker warp)
     __shared__ __align__(8) unsigned long long s_free_a[kAStages];   // ... consumed (tcgen05.commit)
@@ -719,7 +720,7 @@ int head_tc_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const 
     if (src.partial && !src.scratch) return RR_E_BADARG;
     const int n_tiles = (n_cap + kTcRois - 1) / kTcRois;
     const int sms = sms_for_persistent();
-    head_tc_kernel<<<n_tiles < sms ? n_tiles : sms, kTcBlock, kTcSmem, st>>>(src, n_rois_dev, n_cap, folded, reg);
+    launch_pdl(head_tc_kernel, dim3(n_tiles < sms ? n_tiles : sms), dim3(kTcBlock), kTcSmem, st, src, n_rois_dev, n_cap, folded, reg);
     RR_LAUNCHED_K(rc, "head_tc_kernel", st);
     return rc;
 }

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(1024)
 stage1_partition_kernel(const float* __restrict__ dets, int K, int C,
                         float4* __restrict__ sbox, int* __restrict__ slab, int* __restrict__ ssrc,
                         float* __restrict__ sscore, int* __restrict__ seg_off) {
+    RR_PDL_PROLOGUE();
     extern __shared__ unsigned short s_cnt[];       // [nch][C] per-chunk class counts -> prefixes
     __shared__ int s_base[RR_MAX_CLASSES + 1];
     const int b = blockIdx.x;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256)
 rank_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                  const int* __restrict__ seg_offsets, int M, int S,
                  float4* __restrict__ sbox, int* __restrict__ slab, int* __restrict__ ssrc) {
+    RR_PDL_PROLOGUE();
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gt / kRankSplit, part = gt % kRankSplit;     // the kRankSplit threads of an element sit in one warp
     const bool on = i < M;
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ sbox, const int* __restrict__ slab,
                 int n, int Kmax, int W, int T, double thr, float o, int ge,
                 unsigned long long* __restrict__ mask) {
+    RR_PDL_PROLOGUE();
     const int g = blockIdx.y;
     // blockIdx.x -> (rt, ct), ct >= rt, row-major over the upper triangle of a T x T grid
     const long long p = blockIdx.x;
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(kScanThreads2, 1)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ seg_off,
                 int segs_per_group, int Kmax, int W,
                 int* __restrict__ keep_out, int* __restrict__ keep_cnt) {
+    RR_PDL_PROLOGUE();
     extern __shared__ unsigned long long s_dyn[];        // remv [W] | kept [W] | colflag [W] (int)
     __shared__ unsigned long long s_ring[kRing][kRingWords];      // [slot][row][0 = diagonal, 1.. = near columns]
     __shared__ int s_ready[kRing];                       // tile index + 1 whose words sit in the slot
@@ -486,6 +490,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
 __global__ void __launch_bounds__(256)
 nms_map_kernel(const int* __restrict__ seg_off, int segs_per_group, int Kmax, const int* __restrict__ map,
                int* __restrict__ keep_out, const int* __restrict__ keep_cnt) {
+    RR_PDL_PROLOGUE();
     const int g = blockIdx.z, s = blockIdx.y;
     const int s0 = seg_off[g * (segs_per_group + 1) + s];
     const int n = keep_cnt[g * segs_per_group + s];
@@ -505,6 +510,7 @@ stage1_compact_kernel(const float4* __restrict__ sbox, const float* __restrict__
                       int B, int K, int C,
                       float* __restrict__ out_bxyxy, float* __restrict__ out_scores,
                       float* __restrict__ out_clses, int* __restrict__ out_counts) {
+    RR_PDL_PROLOGUE();
     __shared__ int s_cls_base[RR_MAX_CLASSES + 1];
     __shared__ int s_img_base;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -550,7 +556,7 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
     const long long pairs = (long long)T * (T + 1) / 2;
     if (pairs > 0x7fffffffLL) return RR_E_RANGE;
     dim3 gm((unsigned)pairs, (unsigned)G);
-    nms_mask_kernel<<<gm, kMaskThreads, 0, st>>>(sbox, slab, n, Kmax, W, T, thr, pixel_offset ? 1.0f : 0.0f,
+    launch_pdl(nms_mask_kernel, dim3(gm), dim3(kMaskThreads), 0, st, sbox, slab, n, Kmax, W, T, thr, pixel_offset ? 1.0f : 0.0f,
                                        ge_cmp ? 1 : 0, mask);
     RR_LAUNCHED_K(rc, "nms_mask_kernel", st);
     dim3 gs((unsigned)segs_per_group, (unsigned)G);
@@ -559,11 +565,11 @@ static int launch_mask_scan(const float4* sbox, const int* slab, const int* seg_
         if (smem > 200 * 1024) return RR_E_RANGE;
         RR_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
     }
-    nms_scan_kernel<<<gs, kScanThreads2, smem, st>>>(mask, seg_off, segs_per_group, Kmax, W, keep_out, keep_cnt);
+    launch_pdl(nms_scan_kernel, dim3(gs), dim3(kScanThreads2), smem, st, mask, seg_off, segs_per_group, Kmax, W, keep_out, keep_cnt);
     RR_LAUNCHED_K(rc, "nms_scan_kernel", st);
     if (map) {                                       // kept list positions -> the caller's row indices
         dim3 gmap((unsigned)min((n + 255) / 256, 64), (unsigned)segs_per_group, (unsigned)G);
-        nms_map_kernel<<<gmap, 256, 0, st>>>(seg_off, segs_per_group, Kmax, map, keep_out, keep_cnt);
+        launch_pdl(nms_map_kernel, dim3(gmap), dim3(256), 0, st, seg_off, segs_per_group, Kmax, map, keep_out, keep_cnt);
         RR_LAUNCHED_K(rc, "nms_map_kernel", st);
     }
     return rc;
@@ -598,12 +604,12 @@ int stage1_nms_launch(const float* dets, int B, int K, int C, double thr, float*
     size_t smem = (size_t)nch * C * sizeof(unsigned short);
     if (smem > 48 * 1024)
         RR_CUDA(cudaFuncSetAttribute(stage1_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
-    stage1_partition_kernel<<<B, 1024, smem, st>>>(dets, K, C, w.sbox, w.slab, w.ssrc, w.sscore, w.seg_off);
+    launch_pdl(stage1_partition_kernel, dim3(B), dim3(1024), smem, st, dets, K, C, w.sbox, w.slab, w.ssrc, w.sscore, w.seg_off);
     RR_LAUNCHED_K(rc, "stage1_partition_kernel", st);
     int r2 = launch_mask_scan(w.sbox, w.slab, w.seg_off, B, C, K, K, thr, 0, 0, w.mask, nullptr,
                               w.keep_pos, w.keep_cnt, st);
     if (rc == 0) rc = r2;
-    stage1_compact_kernel<<<B, 1024, 0, st>>>(w.sbox, w.sscore, w.slab, w.seg_off, w.keep_pos, w.keep_cnt,
+    launch_pdl(stage1_compact_kernel, dim3(B), dim3(1024), 0, st, w.sbox, w.sscore, w.slab, w.seg_off, w.keep_pos, w.keep_cnt,
                                              B, K, C, out_bxyxy, out_scores, out_clses, out_counts);
     RR_LAUNCHED_K(rc, "stage1_compact_kernel", st);
     return rc;
@@ -665,7 +671,7 @@ RR_API int rr_nms_batched(const float* boxes, const float* scores, const int32_t
     if (!boxes || !scores || !keep_idx || !ws) return RR_E_BADARG;
     if (ws_bytes < carve_generic(nullptr, M).bytes || ((uintptr_t)ws & 255)) return RR_E_WORKSPACE;
     GenericWs w = carve_generic(ws, M);
-    rank_sort_kernel<<<(int)(((long long)M * kRankSplit + 255) / 256), 256, 0, st>>>(boxes, scores, seg_offsets, M, S, w.sbox, w.slab, w.ssrc);
+    launch_pdl(rank_sort_kernel, dim3((int)(((long long)M * kRankSplit + 255) / 256)), dim3(256), 0, st, boxes, scores, seg_offsets, M, S, w.sbox, w.slab, w.ssrc);
     RR_LAUNCHED_K(rc, "rank_sort_kernel", st);
     int r2 = launch_mask_scan(w.sbox, w.slab, seg_offsets, 1, S, M, M, thr, pixel_offset, ge_cmp, w.mask,
                               w.ssrc, keep_idx, keep_count, st);

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kRoiThreads)
 roi_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
                   const int* __restrict__ direct_list, const int* __restrict__ ctl,
                   int B, int C, int H, int W, int relu, float* __restrict__ out) {
+    RR_PDL_PROLOGUE();
     __shared__ float s_ax[RR_POOL][kMaxWin];
     __shared__ float s_ay[RR_POOL][kMaxWin];
     __shared__ AxisGeom s_g[2];
@@ -310,6 +311,7 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
                 int B, int C, int H, int W, int force_direct, TileDims td,
                 RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ cnt_arr, float* __restrict__ wx,
                 float4* __restrict__ wy4, int* __restrict__ tile_count) {
+    RR_PDL_PROLOGUE();
     __shared__ AxisTable s_tab[8][2];
     const int lane = lane_id();
     const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
@@ -406,6 +408,7 @@ roi_scan_kernel(const int* __restrict__ meta, const int* __restrict__ n_rois_dev
                 int n_tiles, int slot_cap, const int* __restrict__ tile_count,
                 int* __restrict__ slot, int* __restrict__ tile_off, int4* __restrict__ items,
                 int* __restrict__ direct_list, int* __restrict__ ctl) {
+    RR_PDL_PROLOGUE();
     __shared__ int s_warp[33];
     __shared__ int s_direct;
     const int tid = threadIdx.x;
@@ -481,6 +484,7 @@ roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
                 const int* __restrict__ n_rois_dev, int n_cap, TileDims td,
                 const int* __restrict__ tile_off, int* __restrict__ tile_fill,
                 int4* __restrict__ list, float* __restrict__ list_wx, float4* __restrict__ list_wy) {
+    RR_PDL_PROLOGUE();
     const int lane = lane_id();
     const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();      // one warp per RoI
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
@@ -590,6 +594,7 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
                 const int4* __restrict__ items, const int* __restrict__ tile_off,
                 const int* __restrict__ tile_fill, int* __restrict__ ctl,
                 int C, int H, int W, int relu, TileDims td, float* __restrict__ partial) {
+    RR_PDL_PROLOGUE();
     extern __shared__ float s_tile[];              // [kTC][kChStride] | int4 s_desc[kChunk][2] | float4 s_wy[kChunk][kTH]
     __shared__ int s_work[2][8];                   // ticket decode: g, list start, pieces (-1: done), px0, py0, img
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -796,6 +801,7 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                     const int4* __restrict__ items, const int* __restrict__ tile_off,
                     const int* __restrict__ tile_fill, int* __restrict__ ctl,
                     int C, TileDims td, float* __restrict__ partial) {
+    RR_PDL_PROLOGUE();
     extern __shared__ unsigned char s_raw[];
     __shared__ int s_work[2][4];                   // g, list start, pieces (-1: no more tickets)
     __shared__ int s_next[2];                      // unit counter of the ticket in buffer b
@@ -1020,6 +1026,7 @@ __global__ void __launch_bounds__(256)
 roi_combine_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
                    const int* __restrict__ n_rois_dev, int n_cap, int C,
                    const float* __restrict__ partial, float* __restrict__ out) {
+    RR_PDL_PROLOGUE();
     extern __shared__ float s_out[];               // [C][9]
     const int n = blockIdx.x;
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
@@ -1107,14 +1114,14 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
     RR_CUDA(cudaMemsetAsync(w.zeroed, 0, w.zeroed_bytes, st), rc);
     if (rc) return rc;
     const int force_direct = algo == 1;
-    roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
+    launch_pdl(roi_prep_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
                                                     w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
     RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
-    roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
+    launch_pdl(roi_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
                                                 w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
     RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
-        roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
+        launch_pdl(roi_fill_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
         RR_LAUNCHED_K(rc, "roi_fill_kernel", st);
         static OncePerDevice attr_once; int attr_dev;
@@ -1127,25 +1134,25 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
         CUtensorMap tm;
         if (algo != 2 && make_tile_tmap(feat, B, C, H, W, &tm)) {      // TMA-staged tiles (needs 16-byte rows)
             if (relu)
-                roi_tile_tma_kernel<true><<<sms_for_persistent(), kT2Threads, kT2Smem, st>>>(
+                launch_pdl(roi_tile_tma_kernel<true>, dim3(sms_for_persistent()), dim3(kT2Threads), kT2Smem, st, 
                     tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial);
             else
-                roi_tile_tma_kernel<false><<<sms_for_persistent(), kT2Threads, kT2Smem, st>>>(
+                launch_pdl(roi_tile_tma_kernel<false>, dim3(sms_for_persistent()), dim3(kT2Threads), kT2Smem, st, 
                     tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial);
             RR_LAUNCHED_K(rc, "roi_tile_tma_kernel", st);
         } else {                                                        // tiles staged through the load/store path
-            roi_tile_kernel<<<2 * sms_for_persistent(), kTileThreads, kTileSmem, st>>>(feat, w.list, w.list_wx, w.list_wy, w.items,
+            launch_pdl(roi_tile_kernel, dim3(2 * sms_for_persistent()), dim3(kTileThreads), kTileSmem, st, feat, w.list, w.list_wx, w.list_wy, w.items,
                                                                       w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
                                                                       w.td, w.partial);
             RR_LAUNCHED_K(rc, "roi_tile_kernel", st);
         }
     }
     if (combine) {
-        roi_combine_kernel<<<n_cap, 256, (size_t)C * RR_POOL * RR_POOL * sizeof(float), st>>>(
+        launch_pdl(roi_combine_kernel, dim3(n_cap), dim3(256), (size_t)C * RR_POOL * RR_POOL * sizeof(float), st, 
             w.prep, w.slot, n_rois_dev, n_cap, C, w.partial, out);
         RR_LAUNCHED_K(rc, "roi_combine_kernel", st);
     }
-    roi_direct_kernel<<<force_direct ? 8 * kSMs : 2 * sms_for_persistent(), kRoiThreads, 0, st>>>(
+    launch_pdl(roi_direct_kernel, dim3(force_direct ? 8 * kSMs : 2 * sms_for_persistent()), dim3(kRoiThreads), 0, st, 
         feat, rois, w.direct_list, w.ctl, B, C, H, W, relu, out);
     RR_LAUNCHED_K(rc, "roi_direct_kernel", st);
     return rc;
@@ -1350,14 +1357,14 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
     if (force_direct || C % kTC != 0)              // the tile kernel (which writes every element, zeros included) does not run
         RR_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st), rc);
     if (rc) return rc;
-    roi_prep_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
+    launch_pdl(roi_prep_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
                                                     w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
     RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
-    roi_scan_kernel<<<1, kScanThreads, 0, st>>>(w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
+    launch_pdl(roi_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
                                                 w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
     RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
-        roi_fill_kernel<<<(n_cap + 7) / 8, 256, 0, st>>>(w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
+        launch_pdl(roi_fill_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
         RR_LAUNCHED_K(rc, "roi_fill_kernel", st);
         static OncePerDevice attr_once; int attr_dev;

@@ -48,6 +48,7 @@ template <int NV>
 __global__ void __launch_bounds__(kTailThreads)
 tail_sample_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ bias,
                    int Cin, int Cout, int HW, int n_lines, unsigned int* __restrict__ maxima) {
+    RR_PDL_PROLOGUE();
     extern __shared__ float s_w[];
     const int b = blockIdx.y, lane = lane_id();
     tail_stage_weights<NV>(w, Cin, Cout, s_w);
@@ -93,6 +94,7 @@ tail_sample_kernel(const float* __restrict__ t, const float* __restrict__ w, con
 __global__ void __launch_bounds__(32)
 tail_thresh_kernel(const unsigned int* __restrict__ maxima, int r, int no_threshold,
                    unsigned int* __restrict__ thr_key, unsigned int* __restrict__ count) {
+    RR_PDL_PROLOGUE();
     const int b = blockIdx.x, lane = threadIdx.x;
     if (lane == 0) count[b] = 0;
     if (no_threshold) {                              // the whole image fits in the candidate list
@@ -122,6 +124,7 @@ tail_conv_collect_kernel(const float* __restrict__ t, const float* __restrict__ 
                          int Cin, int Cout, int HW, const unsigned int* __restrict__ thr_key,
                          unsigned int* __restrict__ count, unsigned long long* __restrict__ cand,
                          float* __restrict__ hm_out) {
+    RR_PDL_PROLOGUE();
     extern __shared__ float s_w[];                   // [Cin][4 * NV]
     __shared__ unsigned long long s_stage[kStage];
     __shared__ int s_n;
@@ -229,19 +232,19 @@ static int tail_launch_nv(const float* t, const float* w, const float* bias, int
     if (!no_thr) {
         RR_CUDA(cudaMemsetAsync(ws.maxima, 0, sizeof(unsigned int) * (size_t)B * kTailSlots, st), rc);
         dim3 gs((unsigned)((n_lines + kTailThreads / 32 - 1) / (kTailThreads / 32)), (unsigned)B);
-        tail_sample_kernel<NV><<<gs, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, n_lines, ws.maxima);
+        launch_pdl(tail_sample_kernel<NV>, dim3(gs), dim3(kTailThreads), smem, st, t, w, bias, Cin, Cout, HW, n_lines, ws.maxima);
         RR_LAUNCHED_K(rc, "tail_sample_kernel", st);
     }
-    tail_thresh_kernel<<<B, 32, 0, st>>>(ws.maxima, r, no_thr, ws.thr_key, ws.count);
+    launch_pdl(tail_thresh_kernel, dim3(B), dim3(32), 0, st, ws.maxima, r, no_thr, ws.thr_key, ws.count);
     RR_LAUNCHED_K(rc, "tail_thresh_kernel", st);
     dim3 gc((unsigned)((HW + kTailThreads * kTailPx - 1) / (kTailThreads * kTailPx)), (unsigned)B);
     const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(hm_out) & 15) == 0);
     if (vec)
-        tail_conv_collect_kernel<NV, true><<<gc, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
+        launch_pdl(tail_conv_collect_kernel<NV, true>, dim3(gc), dim3(kTailThreads), smem, st, t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
                                                                           ws.cand, hm_out);
     else
-        tail_conv_collect_kernel<NV, false><<<gc, kTailThreads, smem, st>>>(t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
+        launch_pdl(tail_conv_collect_kernel<NV, false>, dim3(gc), dim3(kTailThreads), smem, st, t, w, bias, Cin, Cout, HW, ws.thr_key, ws.count,
                                                                            ws.cand, hm_out);
     RR_LAUNCHED_K(rc, "tail_conv_collect_kernel", st);
     return rc;

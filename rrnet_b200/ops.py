@@ -465,6 +465,11 @@ class KernelTrace:
         return False
 
 
+def set_pdl(enabled):
+    """Programmatic dependent launch between the kernels of the eval path (default on)."""
+    check(_lib.lib().rr_set_pdl(int(bool(enabled))), "rr_set_pdl")
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Per calling host thread; grid sizes are fixed at launch / graph capture time."""
