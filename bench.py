@@ -691,7 +691,7 @@ def run_product(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ops._lib.lib()
-    ops.set_pdl(not args.no_pdl)
+    ops.set_pdl(args.pdl)
 
     cfg = CONFIGS[args.config]
     w = WORKLOAD
@@ -752,6 +752,9 @@ def run_product(args):
     pipes = []
     if n_streams > 1:
         ops.set_sm_reserve(args.sm_reserve)         # grid sizes are baked in at capture
+        # the cluster selection (8 CTAs x 144 KB per image) cannot be placed while the other batch's persistent kernels
+        # hold 140 SMs: with two batches in flight the one-CTA-per-image selection fits into the reserved SMs instead
+        ops.set_option(ops.OPT_SELECT_SINGLE_CTA, 1)
         for _ in range(n_streams):
             st = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(st):
@@ -760,6 +763,7 @@ def run_product(args):
                 xx = Exchange()
             pipes.append((st, pp, gg, xx))
         ops.set_sm_reserve(0)
+        ops.set_option(ops.OPT_SELECT_SINGLE_CTA, 0)
         torch.cuda.synchronize()
 
     def step(events=None):
@@ -982,7 +986,7 @@ def run_product(args):
                        "l2": "inputs larger than L2 (features %.2f GB per step)" % (B * Cf * H * W * 4 / 1e9),
                        "submission": "eager launches" if args.no_graph else "CUDA graph replay of the step (memset + %d kernels)" % launches_per_step,
                        "batches_in_flight": max(1, len(pipes)), "sm_reserve": args.sm_reserve if pipes else 0,
-                       "programmatic_dependent_launch": not args.no_pdl,
+                       "programmatic_dependent_launch": bool(args.pdl),
                        "rois_per_step": r["n"]},
             "clocks": clocks, "gpu_launches": int(launches) * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -1004,7 +1008,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configuration: 2 eval path B=8 K=1500 (default; weak-scaled with --gpus), 3 training loss "
                          "path B=32 at 512x512, 4 eval batch 64 SPLIT over the GPUs (strong scaling), 5 dense scene B=16 K=5000")
-    ap.add_argument("--no-pdl", action="store_true", help="ordinary stream order between the kernels of a step (no programmatic dependent launch)")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels of a step (measured: no gain for one batch at a time, slower with two in flight)")
     ap.add_argument("--gather-every", type=int, default=8,
                     help="multi-GPU: all-gather the detections of that many steps with one collective (device ring buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -62,6 +62,12 @@ int         rr_set_sm_reserve(int n_sms);
  * rr_kernel_trace_end() stops the trace and returns the number of events recorded.  Not for use under graph capture. */
 /* Programmatic dependent launch between the kernels of the eval path (default on): 0 = ordinary stream order. */
 int         rr_set_pdl(int enabled);
+/* Process-wide switches between equivalent implementations (same results), for measurements:
+ *   RR_OPT_PDL                as rr_set_pdl
+ *   RR_OPT_SELECT_SINGLE_CTA  1 = the decode's top-K selection by ONE CTA per image instead of a cluster of 8 */
+#define RR_OPT_PDL 1
+#define RR_OPT_SELECT_SINGLE_CTA 2
+int         rr_set_option(int option, int value);
 int         rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream);
 int         rr_kernel_trace_end(void);
 

@@ -20,6 +20,7 @@ SIGNATURES = {
     "rr_launch_count": (ctypes.c_uint64, []),
     "rr_set_sm_reserve": (c_int, [c_int]),
     "rr_set_pdl": (c_int, [c_int]),
+    "rr_set_option": (c_int, [c_int, c_int]),
     "rr_kernel_trace_begin": (c_int, [P, P, c_int, P]),
     "rr_kernel_trace_end": (c_int, []),
     "rr_decode_workspace_bytes": (c_size_t, [c_int] * 5),

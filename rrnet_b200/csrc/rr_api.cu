@@ -8,6 +8,7 @@ namespace rr {
 
 std::atomic<uint64_t> g_launches{0};
 thread_local int g_sm_reserve = 0;
+extern int g_select_single_cta;   // rr_decode.cu
 int g_pdl_enabled = 0;          // measured on the B200: no gain for one batch at a time (0.771 ms either way), -7 % with two batches in flight
 thread_local KernelTrace g_ktrace = {nullptr, nullptr, 0, 0};
 
@@ -57,6 +58,13 @@ RR_API int rr_set_sm_reserve(int n_sms) {
 RR_API int rr_set_pdl(int enabled) {
     g_pdl_enabled = enabled ? 1 : 0;
     return 0;
+}
+RR_API int rr_set_option(int option, int value) {
+    switch (option) {
+        case RR_OPT_PDL: g_pdl_enabled = value ? 1 : 0; return 0;
+        case RR_OPT_SELECT_SINGLE_CTA: g_select_single_cta = value ? 1 : 0; return 0;
+        default: return RR_E_BADARG;
+    }
 }
 
 RR_API int rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream) {

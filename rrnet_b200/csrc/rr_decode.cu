@@ -23,7 +23,9 @@
 // Built with --fmad=false (box arithmetic must round like the reference's separate torch ops).
 #include "rr_decode.cuh"
 
+#include <cooperative_groups.h>
 #include <math_constants.h>
+namespace cg = cooperative_groups;
 
 namespace rr {
 
@@ -384,6 +386,33 @@ __device__ void bitonic_sort_desc(unsigned long long* s_e, int P) {
     }
 }
 
+// one output row: candidate entry e at rank k of image b -> box assembly (models/rrnet.py:117-138) + index
+__device__ __forceinline__ void decode_emit(unsigned long long e, int k, int b, const float* __restrict__ whb,
+                                            const float* __restrict__ ofb, int HW, int W, int K, int raw,
+                                            float* __restrict__ out_dets, long long* __restrict__ out_inds) {
+    const unsigned key = (unsigned)(e >> 32);
+    const unsigned flat = ~(unsigned)(e & 0xffffffffull);
+    const int cls = flat / HW, ind = flat - cls * HW;
+    const int yi = ind / W, xi = ind - yi * W;                  // models/rrnet.py:99-100
+    const float logit = key2f(key);
+    // raw: the map already holds scores (RRNet._topk on its own, :93-109); a pooled-out entry is heat*0
+    const float score = (logit == -CUDART_INF_F) ? 0.0f : (raw ? logit : sigmoid_f32(logit));   // :119
+    const float xs = ofb ? __fadd_rn((float)xi, __ldg(ofb + ind)) : (float)xi;         // :126
+    const float ys = ofb ? __fadd_rn((float)yi, __ldg(ofb + HW + ind)) : (float)yi;    // :127
+    float w = whb ? __ldg(whb + ind) : 0.f, h = whb ? __ldg(whb + HW + ind) : 0.f;
+    w = (w < 0.0f) ? 0.0f : w;                                   // :128 clamp(min=0), NaN passes
+    h = (h < 0.0f) ? 0.0f : h;
+    const float px = __fsub_rn(xs, __fmul_rn(w, 0.5f));          // :133 (w/2 is exact)
+    const float py = __fsub_rn(ys, __fmul_rn(h, 0.5f));          // :134
+    float* o = out_dets + ((size_t)b * K + k) * 6;
+    o[0] = px; o[1] = py;
+    o[2] = __fadd_rn(w, px);                                     // :137 pred_w + pred_x
+    o[3] = __fadd_rn(h, py);
+    o[4] = score;
+    o[5] = (float)cls;
+    if (out_inds) out_inds[(size_t)b * K + k] = ind;
+}
+
 __global__ void __launch_bounds__(kSelectThreads)
 decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
                      const float* __restrict__ off, int C, int H, int W, int K, int pool, int raw,
@@ -420,31 +449,86 @@ decode_select_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
 
     const float* whb = wh ? wh + (size_t)b * 2 * HW : nullptr;
     const float* ofb = off ? off + (size_t)b * 2 * HW : nullptr;
-    for (int k = tid; k < K; k += blockDim.x) {
-        const unsigned long long e = s_e[k];
-        const unsigned key = (unsigned)(e >> 32);
-        const unsigned flat = ~(unsigned)(e & 0xffffffffull);
-        const int cls = flat / HW, ind = flat - cls * HW;
-        const int yi = ind / W, xi = ind - yi * W;                  // models/rrnet.py:99-100
-        const float logit = key2f(key);
-        // raw: the map already holds scores (RRNet._topk on its own, :93-109); a pooled-out entry is heat*0
-        const float score = (logit == -CUDART_INF_F) ? 0.0f : (raw ? logit : sigmoid_f32(logit));   // :119
-        const float xs = ofb ? __fadd_rn((float)xi, __ldg(ofb + ind)) : (float)xi;         // :126
-        const float ys = ofb ? __fadd_rn((float)yi, __ldg(ofb + HW + ind)) : (float)yi;    // :127
-        float w = whb ? __ldg(whb + ind) : 0.f, h = whb ? __ldg(whb + HW + ind) : 0.f;
-        w = (w < 0.0f) ? 0.0f : w;                                   // :128 clamp(min=0), NaN passes
-        h = (h < 0.0f) ? 0.0f : h;
-        const float px = __fsub_rn(xs, __fmul_rn(w, 0.5f));          // :133 (w/2 is exact)
-        const float py = __fsub_rn(ys, __fmul_rn(h, 0.5f));          // :134
-        float* o = out_dets + ((size_t)b * K + k) * 6;
-        o[0] = px; o[1] = py;
-        o[2] = __fadd_rn(w, px);                                     // :137 pred_w + pred_x
-        o[3] = __fadd_rn(h, py);
-        o[4] = score;
-        o[5] = (float)cls;
-        if (out_inds) out_inds[(size_t)b * K + k] = ind;
+    for (int k = tid; k < K; k += blockDim.x) decode_emit(s_e[k], k, b, whb, ofb, HW, W, K, raw, out_dets, out_inds);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3b. the same selection by a CLUSTER of kSelCtas CTAs per image (default).  One CTA per image is a latency chain
+// (load, radix cut, 2048-element bitonic sort, gather: 38 us at config 2 on 8 of 148 SMs).  Here every CTA of the
+// cluster takes an eighth of the image's candidates, sorts it in shared memory, the CTAs exchange their sorted runs
+// through distributed shared memory, and every element finds its global rank = its own position + the number of larger
+// elements in each of the other runs (bisection: entries are unique 64-bit values, so ranks are a permutation).  Rank
+// < K is the output row.  No cut to K, no merge passes.  A candidate count outside [K, kCap] (the sample threshold
+// misfired) is handled by rank 0 alone with the exact single-CTA path above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelCtas = 8;
+constexpr int kSelThreads = 512;
+constexpr int kSelRun = kCap / kSelCtas;             // largest run per CTA (2048 entries)
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+decode_select_cluster_kernel(const float* __restrict__ hm, const float* __restrict__ wh,
+                             const float* __restrict__ off, int C, int H, int W, int K, int pool, int raw,
+                             const unsigned int* __restrict__ count, const unsigned long long* __restrict__ cand,
+                             float* __restrict__ out_dets, long long* __restrict__ out_inds) {
+    RR_PDL_PROLOGUE();
+    extern __shared__ unsigned long long s_all[];        // [kCap] all runs after the exchange (also the fallback's buffer)
+    __shared__ int s_red[kSelectThreads / 32];
+    unsigned long long* s_run = s_all + kCap;            // [kSelRun] this CTA's sorted run
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / kSelCtas, tid = threadIdx.x;
+    const int HW = H * W, N = C * HW;
+    const unsigned cnt = count[b];
+    const float* whb = wh ? wh + (size_t)b * 2 * HW : nullptr;
+    const float* ofb = off ? off + (size_t)b * 2 * HW : nullptr;
+    if (!(cnt >= (unsigned)K && cnt <= (unsigned)kCap)) {          // cluster-uniform
+        if (rank == 0) {                                           // exact selection over the whole image by one CTA
+            exact_select(hm + (size_t)b * N, H, W, N, K, pool, s_all, s_red);
+            int P = 1;
+            while (P < K) P <<= 1;
+            __syncthreads();
+            for (int i = K + tid; i < P; i += blockDim.x) s_all[i] = 0ull;
+            __syncthreads();
+            bitonic_sort_desc(s_all, P);
+            for (int k = tid; k < K; k += blockDim.x) decode_emit(s_all[k], k, b, whb, ofb, HW, W, K, raw, out_dets, out_inds);
+        }
+        return;                                                    // no CTA touches another one's shared memory on this path
+    }
+    const int n = (int)cnt;
+    const int per = (n + kSelCtas - 1) / kSelCtas;                 // run length (the last run may be shorter)
+    const int lo = min(rank * per, n), mine = min(per, n - lo);
+    int P = 32;
+    while (P < per) P <<= 1;
+    const unsigned long long* src = cand + (size_t)b * kCap + lo;
+    for (int i = tid; i < P; i += blockDim.x) s_run[i] = i < mine ? src[i] : 0ull;     // 0 is below every real entry
+    __syncthreads();
+    bitonic_sort_desc(s_run, P);
+    cluster.sync();                                                // every run is sorted
+    for (int r = 0; r < kSelCtas; ++r) {                           // gather the runs (own one included) into s_all
+        const unsigned long long* remote = cluster.map_shared_rank(s_run, r);
+        const int nr = min(per, max(n - r * per, 0));
+        for (int i = tid; i < nr; i += blockDim.x) s_all[r * per + i] = remote[i];
+    }
+    cluster.sync();                                                // all remote reads are done: CTAs may run ahead / exit
+    for (int j = tid; j < mine; j += blockDim.x) {
+        const unsigned long long e = s_all[rank * per + j];
+        int rk = j;
+#pragma unroll 1
+        for (int r = 0; r < kSelCtas; ++r) {
+            if (r == rank) continue;
+            const unsigned long long* run = s_all + r * per;
+            int a = 0, z = min(per, max(n - r * per, 0));          // first index with run[idx] < e  (= entries larger than e)
+            while (a < z) {
+                const int mid = (a + z) >> 1;
+                if (run[mid] > e) a = mid + 1; else z = mid;
+            }
+            rk += a;
+        }
+        if (rk < K) decode_emit(e, rk, b, whb, ofb, HW, W, K, raw, out_dets, out_inds);
     }
 }
+
+int g_select_single_cta = 0;     // rr_set_option("select_single_cta", 1): the one-CTA-per-image selection kernel
 
 int decode_launch(const float* hm, const float* wh, const float* off, int B, int C, int H, int W,
                   int K, int mode, float* out_dets, int64_t* out_inds, void* ws, cudaStream_t st) {
@@ -465,13 +549,29 @@ int decode_launch(const float* hm, const float* wh, const float* off, int B, int
     }
     static OncePerDevice attr_once; int attr_dev;
     const size_t smem = (size_t)kCap * sizeof(unsigned long long);
+    const size_t smem_c = (size_t)(kCap + kSelRun) * sizeof(unsigned long long);
     if (attr_once.need(&attr_dev)) {
         RR_CUDA(cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), rc);
+        RR_CUDA(cudaFuncSetAttribute(decode_select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c), rc);
         if (rc == 0) attr_once.mark(attr_dev);
     }
-    launch_pdl(decode_select_kernel, dim3(B), dim3(kSelectThreads), smem, st, hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
-                                                         out_dets, (long long*)out_inds);
-    RR_LAUNCHED_K(rc, "decode_select_kernel", st);
+    if (g_select_single_cta) {
+        launch_pdl(decode_select_kernel, dim3(B), dim3(kSelectThreads), smem, st, hm, wh, off, C, H, W, K, pool, raw, w.count, w.cand,
+                   out_dets, (long long*)out_inds);
+        RR_LAUNCHED_K(rc, "decode_select_kernel", st);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * kSelCtas)); cfg.blockDim = dim3(kSelThreads); cfg.dynamicSmemBytes = smem_c; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kSelCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const unsigned int* cnt_p = w.count;
+        const unsigned long long* cand_p = w.cand;
+        long long* inds_p = (long long*)out_inds;
+        (void)cudaLaunchKernelEx(&cfg, decode_select_cluster_kernel, hm, wh, off, C, H, W, K, pool, raw, cnt_p, cand_p, out_dets, inds_p);
+        RR_LAUNCHED_K(rc, "decode_select_cluster_kernel", st);
+    }
     return rc;
 }
 

@@ -28,9 +28,9 @@
 //    ([slot][9][C], coalesced stores) and a combine kernel adds them in a fixed order, so the
 //    result is deterministic (no floating-point atomics).  Each feature element is read from
 //    HBM once per step (tiles without RoIs are never read).
-//    Supporting kernels: roi_prep (geometry, separable weights, per-tile piece counts),
-//    roi_scan (one CTA: partial-slot offsets, tile list offsets, work items), roi_fill (tile
-//    lists), roi_combine.
+//    Supporting kernels: roi_prep (geometry, separable weights, partial-slot and direct-list
+//    allocation, per-tile piece counts; its last CTA lays out the tile lists and work items),
+//    roi_fill (tile lists), roi_combine.
 //
 //  * DIRECT path.  One CTA per RoI walks the RoI window straight from global memory with
 //    lanes on consecutive columns.  Used for RoIs whose window exceeds 64 pixels on an axis,
@@ -63,7 +63,7 @@ constexpr int kMaxPieces = 12;       // ceil-spans of a 64-window: 3 tile column
 constexpr int kSlotsPerRoi = 4;      // partial-slot budget: kSlotsPerRoi * n_cap + #tiles
 
 enum { kFlagTile = 0, kFlagDirect = 1, kFlagZero = 2 };
-enum { kCtlItems = 0, kCtlTicket = 1, kCtlDirect = 2, kCtlWords = 8 };
+enum { kCtlItems = 0, kCtlTicket = 1, kCtlDirect = 2, kCtlSlots = 3, kCtlPrepDone = 4, kCtlWords = 8 };
 
 // Per-axis sample geometry of one RoI (torchvision roi_align_kernel: pre_calc_for_bilinear_interpolate).
 struct AxisGeom {
@@ -238,7 +238,7 @@ __device__ void roi_direct_one(const float* __restrict__ feat, const float* __re
     }
 }
 
-// Grid-stride over the list of RoIs routed to the direct path (built by roi_scan).
+// Grid-stride over the list of RoIs routed to the direct path (built by roi_prep).
 __global__ void __launch_bounds__(kRoiThreads)
 roi_direct_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
                   const int* __restrict__ direct_list, const int* __restrict__ ctl,
@@ -279,8 +279,9 @@ __device__ __forceinline__ void axis_table(const AxisGeom& g, int size, int lane
 #pragma unroll
             for (int q = 0; q < RR_POOL; ++q)
                 if (q == p) { lo[q] = min(lo[q], l0 - g.lo); hi[q] = max(hi[q], h0 - g.lo); }
-        } else {
-            l0 = h0 = -1;
+        } else {                                   // out of range: below the map -1, above it INT_MAX, so that `low`
+            const float v = g.start + p * g.bin + (float)(i + .5f) * g.bin / (float)g.grid;   // stays non-decreasing
+            l0 = h0 = (v < -1.0f) ? -1 : 0x7fffffff;
         }
         tb.low[t] = l0; tb.high[t] = h0; tb.wl[t] = wl;
     }
@@ -293,12 +294,20 @@ __device__ __forceinline__ void axis_table(const AxisGeom& g, int size, int lane
     __syncwarp();
 }
 
-// weight bin p puts on pixel pix: the table's samples of that bin, in sample order (== axis_weight)
+// weight bin p puts on pixel pix: the table's samples of that bin, in sample order (== axis_weight).  Sample positions
+// are monotone, so the samples that touch pix (low == pix, or low == pix - 1 through `high`) are a contiguous run: found
+// by bisection instead of walking all `grid` samples (the walk made roi_prep issue bound: 36 us at config 2).
 __device__ __forceinline__ float table_weight(const AxisTable& tb, int grid, int p, int pix) {
     float acc = 0.f;
     const int t0 = p * grid;
-    for (int i = 0; i < grid; ++i) {
+    int a = 0, b = grid;                           // first sample with low >= pix - 1
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (tb.low[t0 + mid] < pix - 1) a = mid + 1; else b = mid;
+    }
+    for (int i = a; i < grid; ++i) {
         const int l0 = tb.low[t0 + i], h0 = tb.high[t0 + i];
+        if (l0 > pix) break;
         const float wl = tb.wl[t0 + i];
         if (l0 == pix) acc += 1.f - wl;
         if (h0 == pix && l0 >= 0) acc += wl;
@@ -306,74 +315,6 @@ __device__ __forceinline__ float table_weight(const AxisTable& tb, int grid, int
     return acc;
 }
 
-__global__ void __launch_bounds__(256)
-roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_dev, int n_cap,
-                int B, int C, int H, int W, int force_direct, TileDims td,
-                RoiPrep* __restrict__ prep, int* __restrict__ meta, float* __restrict__ cnt_arr, float* __restrict__ wx,
-                float4* __restrict__ wy4, int* __restrict__ tile_count) {
-    RR_PDL_PROLOGUE();
-    __shared__ AxisTable s_tab[8][2];
-    const int lane = lane_id();
-    const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
-    if (n >= live) return;
-    AxisTable& tx = s_tab[warp_id()][0];
-    AxisTable& ty = s_tab[warp_id()][1];
-    const float* r = rois + (size_t)n * 5;
-    RoiPrep rp;
-    rp.img = (int)r[0];
-    rp.flags = kFlagZero;
-    rp.x_lo = rp.nx = rp.y_lo = rp.ny = 0;
-    rp.tx0 = rp.ty0 = rp.ntx = rp.nty = 0;
-    rp.slot_base = 0;
-    rp.count = 1.f;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) { rp.cx_lo[p] = rp.cy_lo[p] = 127; rp.cx_hi[p] = rp.cy_hi[p] = -1; }
-    int m = 0;
-    if (rp.img >= 0 && rp.img < B) {
-        const AxisGeom gx = axis_geom(r[1], r[3], W), gy = axis_geom(r[2], r[4], H);
-        if (gx.n > 0 && gy.n > 0) {
-            rp.x_lo = gx.lo; rp.nx = gx.n; rp.y_lo = gy.lo; rp.ny = gy.n;
-            rp.count = (float)max(gx.grid * gy.grid, 1);
-            if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0 ||
-                RR_POOL * gx.grid > kMaxSamples || RR_POOL * gy.grid > kMaxSamples) {
-                rp.flags = kFlagDirect;
-                m = -1;
-            } else {
-                rp.flags = kFlagTile;
-                rp.tx0 = gx.lo / kTW; rp.ntx = (gx.lo + gx.n - 1) / kTW - rp.tx0 + 1;
-                rp.ty0 = gy.lo / kTH; rp.nty = (gy.lo + gy.n - 1) / kTH - rp.ty0 + 1;
-                axis_table(gx, W, lane, tx, rp.cx_lo, rp.cx_hi);
-                axis_table(gy, H, lane, ty, rp.cy_lo, rp.cy_hi);
-                float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
-                float4* wyn = wy4 + (size_t)n * kMaxWinT;
-                const int kmax = max(gx.n, gy.n);
-                for (int k = lane; k < kmax; k += 32) {
-                    float b[RR_POOL];
-#pragma unroll
-                    for (int p = 0; p < RR_POOL; ++p) {
-                        const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? table_weight(tx, gx.grid, p, gx.lo + k) : 0.f;
-                        b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? table_weight(ty, gy.grid, p, gy.lo + k) : 0.f;
-                        if (k < gx.n) wxn[p * kMaxWinT + k] = a;
-                    }
-                    if (k < gy.n) wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
-                }
-                m = rp.ntx * rp.nty;
-                if (lane < m) {
-                    const int tyi = rp.ty0 + lane / rp.ntx, txi = rp.tx0 + lane % rp.ntx;
-                    atomicAdd(tile_count + rp.img * td.tiles_per_img + tyi * td.ntx + txi, 1);
-                }
-            }
-        }
-    }
-    if (lane == 0) { prep[n] = rp; meta[n] = m; cnt_arr[n] = rp.count; }
-}
-
-// --------------------------------------------------------------------------------------------
-// TILE path, step 2 (one CTA): exclusive scans -> partial-slot base per RoI (slot[n]; -1 = direct
-// path, which also takes the RoIs that do not fit the slot budget), list offset per tile, work
-// items (tile, list start, piece count), the direct list.
-// --------------------------------------------------------------------------------------------
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
     const int lane = lane_id(), warp = warp_id(), nwarp = blockDim.x >> 5;
     int inc = v;
@@ -400,75 +341,128 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
     return s_warp[warp] + inc - v;
 }
 
-constexpr int kScanThreads = 1024;
-constexpr int kScanPer = 16;                       // elements per thread and round (4 x int4, coalesced per warp)
-
-__global__ void __launch_bounds__(kScanThreads)
-roi_scan_kernel(const int* __restrict__ meta, const int* __restrict__ n_rois_dev, int n_cap,
-                int n_tiles, int slot_cap, const int* __restrict__ tile_count,
-                int* __restrict__ slot, int* __restrict__ tile_off, int4* __restrict__ items,
-                int* __restrict__ direct_list, int* __restrict__ ctl) {
+__global__ void __launch_bounds__(256)
+roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_dev, int n_cap,
+                int B, int C, int H, int W, int force_direct, TileDims td, int n_tiles, int slot_cap,
+                RoiPrep* __restrict__ prep, int* __restrict__ meta, int* __restrict__ slot, float* __restrict__ cnt_arr,
+                float* __restrict__ wx, float4* __restrict__ wy4, int* __restrict__ tile_count,
+                int* __restrict__ tile_off, int4* __restrict__ items, int* __restrict__ direct_list, int* __restrict__ ctl) {
     RR_PDL_PROLOGUE();
+    __shared__ AxisTable s_tab[8][2];
     __shared__ int s_warp[33];
-    __shared__ int s_direct;
-    const int tid = threadIdx.x;
+    __shared__ int s_last, s_m[8], s_off[8], s_base;
+    const int lane = lane_id();
+    const int n = blockIdx.x * (blockDim.x >> 5) + warp_id();
     const int live = n_rois_dev ? min(*n_rois_dev, n_cap) : n_cap;
-    if (tid == 0) s_direct = 0;
-    __syncthreads();
-    // ---- partial-slot bases in RoI order (deterministic); meta/slot are padded to a multiple of 4 ----
-    int carry = 0;
-    for (int base0 = 0; base0 < live; base0 += kScanThreads * kScanPer) {
-        const int i0 = base0 + tid * kScanPer;
-        int v[kScanPer];
+    AxisTable& tx = s_tab[warp_id()][0];
+    AxisTable& ty = s_tab[warp_id()][1];
+    RoiPrep rp;
+    AxisGeom gx, gy;
+    gx.n = gy.n = 0; gx.grid = gy.grid = 1; gx.lo = gy.lo = 0; gx.start = gy.start = gx.bin = gy.bin = 0.f;
+    int m_warp = 0;
+    if (n < live) {
+        const float* r = rois + (size_t)n * 5;
+        rp.img = (int)r[0];
+        rp.flags = kFlagZero;
+        rp.x_lo = rp.nx = rp.y_lo = rp.ny = 0;
+        rp.tx0 = rp.ty0 = rp.ntx = rp.nty = 0;
+        rp.slot_base = 0;
+        rp.count = 1.f;
 #pragma unroll
-        for (int q = 0; q < kScanPer / 4; ++q) {
-            int4 t = make_int4(0, 0, 0, 0);
-            if (i0 + 4 * q < live) t = *reinterpret_cast<const int4*>(meta + i0 + 4 * q);
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-        int sum = 0;
-#pragma unroll
-        for (int q = 0; q < kScanPer; ++q) sum += (i0 + q < live && v[q] > 0) ? v[q] : 0;
-        int total;
-        int run = carry + block_exclusive_scan(sum, s_warp, total);
-        carry += total;
-#pragma unroll
-        for (int q = 0; q < kScanPer; ++q) {
-            const int i = i0 + q;
-            if (i < live) {
-                int sb;
-                if (v[q] < 0) sb = -1;
-                else if (v[q] == 0) sb = 0;
-                else { sb = (run + v[q] <= slot_cap) ? run : -1; run += v[q]; }
-                if (sb < 0) direct_list[atomicAdd(&s_direct, 1)] = i;
-                v[q] = sb;
+        for (int p = 0; p < 4; ++p) { rp.cx_lo[p] = rp.cy_lo[p] = 127; rp.cx_hi[p] = rp.cy_hi[p] = -1; }
+        int m = 0;
+        if (rp.img >= 0 && rp.img < B) {
+            gx = axis_geom(r[1], r[3], W); gy = axis_geom(r[2], r[4], H);
+            if (gx.n > 0 && gy.n > 0) {
+                rp.x_lo = gx.lo; rp.nx = gx.n; rp.y_lo = gy.lo; rp.ny = gy.n;
+                rp.count = (float)max(gx.grid * gy.grid, 1);
+                if (force_direct || gx.n > kMaxWinT || gy.n > kMaxWinT || (C % kTC) != 0 ||
+                    RR_POOL * gx.grid > kMaxSamples || RR_POOL * gy.grid > kMaxSamples) {
+                    rp.flags = kFlagDirect;
+                    m = -1;
+                } else {
+                    rp.flags = kFlagTile;
+                    rp.tx0 = gx.lo / kTW; rp.ntx = (gx.lo + gx.n - 1) / kTW - rp.tx0 + 1;
+                    rp.ty0 = gy.lo / kTH; rp.nty = (gy.lo + gy.n - 1) / kTH - rp.ty0 + 1;
+                    m = rp.ntx * rp.nty;
+                }
             }
         }
-#pragma unroll
-        for (int q = 0; q < kScanPer / 4; ++q)
-            if (i0 + 4 * q < live)
-                *reinterpret_cast<int4*>(slot + i0 + 4 * q) = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        m_warp = m;
     }
-    // ---- tile list offsets and work items ----
+    // partial slots (one per tile piece) and the direct list: handed out with ONE atomic per CTA (8 RoIs).  The slot
+    // NUMBERS therefore change from run to run; the results do not (a RoI's pieces are summed in the order of its own slots).
+    if (lane == 0) s_m[warp_id()] = m_warp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int q = 0; q < 8; ++q) { const int v = s_m[q]; s_off[q] = tot; tot += v > 0 ? v : 0; }
+        s_base = tot ? atomicAdd(ctl + kCtlSlots, tot) : 0;
+    }
+    __syncthreads();
+    if (n < live) {
+        const int m = m_warp;
+        int sb = 0;
+        if (lane == 0) {
+            if (m > 0) {
+                sb = s_base + s_off[warp_id()];
+                if (sb + m > slot_cap) { sb = -1; }                    // slot budget exhausted: direct path
+            } else if (m < 0) {
+                sb = -1;
+            }
+            if (sb < 0) direct_list[atomicAdd(ctl + kCtlDirect, 1)] = n;
+        }
+        sb = __shfl_sync(0xffffffffu, sb, 0);
+        if (m > 0 && sb >= 0) {
+            axis_table(gx, W, lane, tx, rp.cx_lo, rp.cx_hi);
+            axis_table(gy, H, lane, ty, rp.cy_lo, rp.cy_hi);
+            float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
+            float4* wyn = wy4 + (size_t)n * kMaxWinT;
+            const int kmax = max(gx.n, gy.n);
+            for (int k = lane; k < kmax; k += 32) {
+                float b[RR_POOL];
+#pragma unroll
+                for (int p = 0; p < RR_POOL; ++p) {
+                    const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? table_weight(tx, gx.grid, p, gx.lo + k) : 0.f;
+                    b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? table_weight(ty, gy.grid, p, gy.lo + k) : 0.f;
+                    if (k < gx.n) wxn[p * kMaxWinT + k] = a;
+                }
+                if (k < gy.n) wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
+            }
+            if (lane < m) {
+                const int tyi = rp.ty0 + lane / rp.ntx, txi = rp.tx0 + lane % rp.ntx;
+                atomicAdd(tile_count + rp.img * td.tiles_per_img + tyi * td.ntx + txi, 1);
+            }
+        }
+        if (lane == 0) { prep[n] = rp; meta[n] = m; slot[n] = sb; cnt_arr[n] = rp.count; }
+    }
+    // ---- the last CTA to finish lays out the tile lists: list offset per tile and the work items (tile, list start,
+    //      piece count), in tile order (this used to be a separate one-CTA kernel) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ctl + kCtlPrepDone, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     {
-        const int nt = blockDim.x;
+        const int tid = threadIdx.x, nt = blockDim.x;
         const int per = (n_tiles + nt - 1) / nt;
         const int t0 = min(tid * per, n_tiles), t1 = min(t0 + per, n_tiles);
         int sum = 0, chunks = 0;
-        for (int t = t0; t < t1; ++t) { int c = tile_count[t]; sum += c; chunks += (c + kChunk - 1) / kChunk; }
+        for (int t = t0; t < t1; ++t) { const int c = __ldcg(tile_count + t); sum += c; chunks += (c + kChunk - 1) / kChunk; }
         int total, n_items;
         int off = block_exclusive_scan(sum, s_warp, total);
         int ioff = block_exclusive_scan(chunks, s_warp, n_items);
         for (int t = t0; t < t1; ++t) {
-            const int c = tile_count[t];
+            const int c = __ldcg(tile_count + t);
             tile_off[t] = off;
             for (int k = 0; k < c; k += kChunk) items[ioff++] = make_int4(t, off + k, min(kChunk, c - k), 0);
             off += c;
         }
         if (tid == 0) { tile_off[n_tiles] = total; ctl[kCtlItems] = n_items; ctl[kCtlTicket] = 0; }
     }
-    __syncthreads();
-    if (tid == 0) ctl[kCtlDirect] = s_direct;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1115,11 +1109,9 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
     if (rc) return rc;
     const int force_direct = algo == 1;
     launch_pdl(roi_prep_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
-                                                    w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
+               w.n_tiles, w.slot_cap, w.prep, w.meta, w.slot, w.cnt, w.wx, w.wy4, w.tile_count, w.tile_off, w.items,
+               w.direct_list, w.ctl);
     RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
-    launch_pdl(roi_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
-                                                w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
-    RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
         launch_pdl(roi_fill_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);
@@ -1358,11 +1350,9 @@ int roi_align_backward_launch(const float* feat, const float* rois, const int32_
         RR_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)B * C * H * W, st), rc);
     if (rc) return rc;
     launch_pdl(roi_prep_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, rois, n_rois_dev, n_cap, B, C, H, W, force_direct, w.td,
-                                                    w.prep, w.meta, w.cnt, w.wx, w.wy4, w.tile_count);
+               w.n_tiles, w.slot_cap, w.prep, w.meta, w.slot, w.cnt, w.wx, w.wy4, w.tile_count, w.tile_off, w.items,
+               w.direct_list, w.ctl);
     RR_LAUNCHED_K(rc, "roi_prep_kernel", st);
-    launch_pdl(roi_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, w.meta, n_rois_dev, n_cap, w.n_tiles, w.slot_cap, w.tile_count,
-                                                w.slot, w.tile_off, w.items, w.direct_list, w.ctl);
-    RR_LAUNCHED_K(rc, "roi_scan_kernel", st);
     if (!force_direct && C % kTC == 0) {
         launch_pdl(roi_fill_kernel, dim3((n_cap + 7) / 8), dim3(256), 0, st, w.prep, w.slot, w.wx, w.wy4, n_rois_dev, n_cap, w.td,
                                                         w.tile_off, w.tile_fill, w.list, w.list_wx, w.list_wy);

@@ -470,6 +470,14 @@ def set_pdl(enabled):
     check(_lib.lib().rr_set_pdl(int(bool(enabled))), "rr_set_pdl")
 
 
+OPT_PDL, OPT_SELECT_SINGLE_CTA = 1, 2
+
+
+def set_option(option, value):
+    """rr_set_option: OPT_PDL, OPT_SELECT_SINGLE_CTA (the decode's selection by one CTA per image instead of a cluster)."""
+    check(_lib.lib().rr_set_option(int(option), int(value)), "rr_set_option")
+
+
 def set_sm_reserve(n_sms):
     """SMs (0..147) the persistent kernels leave free for the short kernels of another batch on another stream.
     Per calling host thread; grid sizes are fixed at launch / graph capture time."""

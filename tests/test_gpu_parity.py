@@ -80,6 +80,24 @@ def test_decode_ties_and_fallback(ops, oracle_mod, case):
     np.testing.assert_array_equal(npy(dets)[..., [0, 1, 2, 3, 5]], o_dets[..., [0, 1, 2, 3, 5]])
 
 
+@pytest.mark.parametrize("B,H,W,K", [(2, 64, 96, 700), (1, 272, 480, 5000), (3, 40, 40, 1600)])
+def test_decode_cluster_selection_matches_single_cta(ops, oracle_mod, B, H, W, K):
+    """The cluster selection (8 CTAs per image: sorted runs exchanged through distributed shared memory, rank by
+    bisection) and the one-CTA-per-image selection write identical rows; K = H*W hits the exact fall-back in both."""
+    x = synth.eval_inputs(B, H, W, K, seed=B * 7 + K)
+    hm, wh, off = dev(x["hm"]), dev(x["wh"]), dev(x["off"])
+    d_c, i_c = ops.decode_topk(hm, wh, off, K)
+    ops.set_option(ops.OPT_SELECT_SINGLE_CTA, 1)
+    try:
+        d_s, i_s = ops.decode_topk(hm, wh, off, K)
+    finally:
+        ops.set_option(ops.OPT_SELECT_SINGLE_CTA, 0)
+    np.testing.assert_array_equal(npy(i_c), npy(i_s))
+    np.testing.assert_array_equal(npy(d_c), npy(d_s))
+    o_dets, o_inds, _ = oracle_mod.decode(x["hm"].numpy(), x["wh"].numpy(), x["off"].numpy(), K)
+    np.testing.assert_array_equal(npy(i_c), o_inds)
+
+
 def test_decode_pool3(ops, oracle_mod):
     B, C, H, W, K = 2, 10, 64, 80, 120
     hm = synth.heatmap_logits(B, C, H, W, K, 8)
