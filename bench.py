@@ -864,6 +864,34 @@ def run_product(args):
             stage_ms[n] += evs[j].elapsed_time(evs[j + 1])
     stage_ms = {n: v / n_ev for n, v in stage_ms.items()}
 
+    # ---- variant: the features arrive already ReLU-ed.  In the model they do: forward_stage1 builds relu(pre_feat[-1]) for
+    # the stage-1 heads (models/rrnet.py:144) and the host mirror hands that tensor to the path (EvalPath feat_is_relu), so
+    # RoIAlign skips its own ReLU.  The headline numbers above keep the fused ReLU (N(0,1) features). ----
+    variant = None
+    if not args.no_aux and world == 1:
+        try:
+            feat_r = torch.relu(d["feat"])
+            pv = ops.EvalPath(B, C, H, W, K, folded, device=dev, roi_algo=args.roi_algo, head_algo=args.head_algo, feat_is_relu=True)
+            gv = pv.capture(d["hm"], d["wh"], d["off"], feat_r)
+            v_beg, v_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            v_beg.record()
+            for _ in range(args.steps):
+                gv.replay()
+            v_end.record()
+            torch.cuda.synchronize()
+            v_ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            pv.forward(d["hm"], d["wh"], d["off"], feat_r, stage_events=v_ev)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(pv.s2, path.s2) and torch.equal(pv.counts, path.counts))
+            ms_v = v_beg.elapsed_time(v_end) / args.steps
+            variant = {"feat_is_relu": {"single_batch_ms_per_step": ms_v, "value": B / (ms_v / 1e3), "unit": UNIT,
+                                        "roi_align_stage_ms": v_ev[2].elapsed_time(v_ev[3]), "same_result": same}}
+            del feat_r, pv, gv
+            torch.cuda.empty_cache()
+        except Exception as e:
+            variant = {"feat_is_relu": {"error": repr(e)[:200]}}
+
     # ---- e2e: pinned host inputs -> H2D -> path -> D2H of the result, every step ----
     res_host = torch.empty(B * K, 6, dtype=torch.float32).pin_memory()
     cnt_host = torch.empty(B + 1, dtype=torch.int32).pin_memory()
@@ -993,7 +1021,7 @@ def run_product(args):
                     "steps": e2e_steps},
             "single_batch": single, "roofline": roofline, "rooflines": {"stages": stage_rows, "kernels": kernel_rows},
             "stages_ms": stage_ms, "kernels": extra_roof, "cpu_baseline": cpu_info,
-            "reference_cuda": ref_cuda, "aux": aux, "nms_baselines": nms_base}
+            "reference_cuda": ref_cuda, "aux": aux, "nms_baselines": nms_base, "variants": variant}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

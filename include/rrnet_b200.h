@@ -219,7 +219,9 @@ int rr_generate_bbox(const float* bxyxy, const float* reg, const float* scores, 
  * RRNetOperator.generate_bbox for every image.  All launches go to `stream`, no host sync.
  * Outputs have capacity B*K rows; counts [B+1] as in rr_stage1_nms.
  * roi_feat may be NULL (the workspace then holds it).  roi_algo: bit 0 as in rr_roi_align (1 = direct
- * gather), bit 1 selects the head kernel (0 = tcgen05, 2 = fp32 FFMA), bit 2 (4) = rr_roi_align's algo 2.
+ * gather), bit 1 selects the head kernel (0 = tcgen05, 2 = fp32 FFMA), bit 2 (4) = rr_roi_align's algo 2,
+ * bit 3 (8) = `feat` is ALREADY relu(pre_feat[-1]) - the tensor forward_stage1 builds for the stage-1 heads
+ * (models/rrnet.py:144) - so RoIAlign does not apply the ReLU again (same results, fewer instructions).
  * stage_events: NULL, or 6 cudaEvent_t handles (as void*) recorded on `stream` before decode and
  * after decode, stage-1 NMS, RoIAlign, head and generate_bbox (a per-stage timing hook; recording
  * an event does not synchronise).

@@ -109,8 +109,10 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
         return RR_E_BADARG;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return RR_E_BADARG;
     if (feat_ch != RR_HEAD_CH) return RR_E_RANGE;               // the head is 256-channel (fasterrcnn_detector.py:9)
-    if ((pool != 0 && pool != 3 && pool != RR_DECODE_PRECOLLECTED) || roi_algo < 0 || roi_algo > 7 || (roi_algo & 5) == 5) return RR_E_BADARG;
+    if ((pool != 0 && pool != 3 && pool != RR_DECODE_PRECOLLECTED) || roi_algo < 0 || roi_algo > 15 || (roi_algo & 5) == 5) return RR_E_BADARG;
     const int head_algo = (roi_algo >> 1) & 1;       // bit 1: fp32 FFMA head instead of the tcgen05 one
+    const int relu = (roi_algo & 8) ? 0 : 1;         // bit 3: `feat` already went through the ReLU (models/rrnet.py:144 makes that
+                                                     // tensor for the stage-1 heads anyway): RoIAlign skips its own
     roi_algo = (roi_algo & 1) ? 1 : ((roi_algo & 4) ? 2 : 0);   // bit 0: direct-gather RoIAlign, bit 2: tile path staged by loads (no TMA)
     if (C > RR_MAX_CLASSES || K > RR_MAX_TOPK || (long long)K > (long long)H * W) return RR_E_RANGE;
     if ((long long)C * H * W >= (1LL << 31)) return RR_E_RANGE;
@@ -135,7 +137,7 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     // roi_feat requested: materialise it (combine) and feed the head from it; otherwise the head sums the
     // tile-path partial slots itself and only direct-path RoIs go through the buffer
     const int fused = roi_feat == nullptr && roi_algo != 1;
-    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, 1, roi_algo, fused ? 0 : 1, rf, w.roi, st);
+    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, relu, roi_algo, fused ? 0 : 1, rf, w.roi, st);
     if (rc) return rc;
     mark(3);
     if (fused) {

@@ -714,9 +714,13 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 // The 22 consumer warps take (piece, bin column) units from a shared counter and move on to the
 // next ticket on their own (no CTA-wide barrier).
 // --------------------------------------------------------------------------------------------
+#ifndef RR_T2_MERGED
+#define RR_T2_MERGED 0       // 1: a unit is a whole piece (three bin columns in one pass).  Measured on the B200 (config 2):
+#endif                       // 0.581 ms against 0.458 ms for (piece, bin column) units - see unit_rows_m
 #ifndef RR_T2_THREADS
-#define RR_T2_THREADS 736    // 22 consumer warps + the producer.  Measured (RoIAlign stage, ms): 416: 0.557, 480: 0.538,
+#define RR_T2_THREADS (RR_T2_MERGED ? 640 : 736)    // consumer warps + the producer (merged units: 19 warps, 102 registers).  Measured (RoIAlign stage, ms): 416: 0.557, 480: 0.538,
 #endif                       // 544: 0.524, 608: 0.518, 672: 0.513, 736: 0.512, 800 (spills): 0.534, 1024 (64 registers): 0.533
+// RR_T2_MERGED 1: a unit is a whole piece (three bin columns in one pass); 0: (piece, bin column) units
 #ifndef RR_T2_UNROLL
 #define RR_T2_UNROLL 2       // rows per iteration of the unit loop (3 and 4 were not faster at 544 - 672 threads)
 #endif
@@ -785,6 +789,51 @@ __device__ __forceinline__ void unit_rows_q(const float* __restrict__ rowp, cons
         a0 = fmaf(wy.x, s, a0);
         a1 = fmaf(wy.y, s, a1);
         a2 = fmaf(wy.z, s, a2);
+    }
+}
+
+// MERGED units (-DRR_T2_MERGED=1, NOT the default): a unit is a whole piece - all three bin columns in one pass over the piece's
+// aligned chunks.  Every 16-byte chunk of the tile is then read ONCE per piece (the bin columns of a narrow piece share
+// chunks; per piece row 3.7 chunk reads instead of 5.0) and the row weights once instead of three times: -35 % shared-
+// memory wavefronts per piece row, the kernel's limiter.  Price: every chunk is multiplied into all three bin columns
+// (weights outside a bin's range are zero) and the weights of a pass take 6 registers per chunk.
+// Result: slower (0.581 ms against 0.458 ms).  A third as many units per ticket (~25 pieces for 19 warps) wrecks the
+// balance inside a ticket, 96 registers cost three warps, and the kernel is not bound by wavefronts alone: taking the
+// ReLU out of it (-27 % instructions, feat_is_relu) only gains 3 %.  It is a latency chain per unit (LDS -> FMNMX ->
+// FFMA2 -> row reduction) on 22 warps that no single pipe saturates (LSU 71 %, issue 62 %).  Kept for the record.
+template <int NQ, bool kRelu>
+__device__ __forceinline__ void unit_rows_m(const float* __restrict__ rowp, const int (&off)[3],
+                                            const float4* __restrict__ s_wy, int nrows, const ulonglong2 (&w)[3][3],
+                                            float (&a)[3][3]) {
+    const float* p[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) p[j] = rowp + off[j];
+#pragma unroll kT2Unroll
+    for (int y = 0; y < nrows; ++y) {
+        unsigned long long s01[3] = {0ull, 0ull, 0ull}, s23[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            float4 v = *reinterpret_cast<const float4*>(p[j]);
+            p[j] += kTC * kTW;
+            if (kRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            const unsigned long long v01 = t2_pack(v.x, v.y), v23 = t2_pack(v.z, v.w);
+#pragma unroll
+            for (int pw = 0; pw < 3; ++pw) {
+                s01[pw] = t2_fma2(w[pw][j].x, v01, s01[pw]);
+                s23[pw] = t2_fma2(w[pw][j].y, v23, s23[pw]);
+            }
+        }
+        const float4 wy = s_wy[y];                 // warp-uniform address: broadcast, once for the three bin columns
+#pragma unroll
+        for (int pw = 0; pw < 3; ++pw) {
+            float sx, sy, sz, sw;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(s01[pw]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(sz), "=f"(sw) : "l"(s23[pw]));
+            const float sv = (sx + sz) + (sy + sw);
+            a[0][pw] = fmaf(wy.x, sv, a[0][pw]);
+            a[1][pw] = fmaf(wy.y, sv, a[1][pw]);
+            a[2][pw] = fmaf(wy.z, sv, a[2][pw]);
+        }
     }
 }
 
@@ -877,7 +926,7 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
             if (new_tables) {                      // order the units by size class (rows x chunks), largest first
-                const int n_units = n_pieces * RR_POOL;
+                const int n_units = RR_T2_MERGED ? n_pieces : n_pieces * RR_POOL;
                 int cls[RR_POOL], cnt[kT2Passes];
 #pragma unroll
                 for (int k = 0; k < kT2Passes; ++k) cnt[k] = 0;
@@ -886,12 +935,25 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                     const int u = r * 32 + lane;
                     cls[r] = kT2Passes;
                     if (u < n_units) {
+#if RR_T2_MERGED
+                        const int4 d0 = desc[2 * u], d1 = desc[2 * u + 1];
+                        int qlo = 8, qhi = -1;
+                        const int colsv[RR_POOL] = {d0.w, d1.x, d1.y};
+#pragma unroll
+                        for (int pw = 0; pw < RR_POOL; ++pw) {
+                            const int c0 = colsv[pw] & 0xff, nc = (colsv[pw] >> 8) & 0xff;
+                            if (nc > 0) { qlo = min(qlo, c0 >> 2); qhi = max(qhi, (c0 + nc - 1) >> 2); }
+                        }
+                        const int size = ((d0.z >> 8) & 0xff) * max(qhi - qlo + 1, 0);
+                        cls[r] = size >= 96 ? 0 : (size >= 48 ? 1 : (size >= 20 ? 2 : 3));
+#else
                         const int piece = u / RR_POOL, pw = u - piece * RR_POOL;
                         const int4 d0 = desc[2 * piece], d1 = desc[2 * piece + 1];
                         const int cols = pw == 0 ? d0.w : (pw == 1 ? d1.x : d1.y);
                         const int c0 = cols & 0xff, ncols = (cols >> 8) & 0xff;
                         const int size = ((d0.z >> 8) & 0xff) * (ncols > 0 ? ((c0 + ncols - 1) >> 2) - (c0 >> 2) + 1 : 0);
                         cls[r] = size >= 48 ? 0 : (size >= 24 ? 1 : (size >= 10 ? 2 : 3));
+#endif
                     }
 #pragma unroll
                     for (int k = 0; k < kT2Passes; ++k) cnt[k] += __popc(__ballot_sync(0xffffffffu, cls[r] == k));
@@ -927,6 +989,76 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
         const float* tile = reinterpret_cast<const float*>(base + b * kT2TileBytes);
         const int4* s_desc = reinterpret_cast<const int4*>(base + 2 * kT2TileBytes + b * kT2TableBytes);
         const float4* s_wy = reinterpret_cast<const float4*>(s_desc + 2 * kChunk);
+#if RR_T2_MERGED
+        const int n_units = n_pieces;
+        const float* wxp = list_wx + (size_t)list0 * RR_POOL * kTW + lane;     // piece u, bin column pw: wxp[(u * 3 + pw) * kTW]
+        auto next_unit = [&]() {                           // pieces are handed out largest first (ordered by the producer)
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next[b], 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            return u < n_units ? (int)s_order[b][u] : n_units;
+        };
+        int u = next_unit();
+        float wxv[RR_POOL] = {0.f, 0.f, 0.f};
+        if (u < n_units) {
+#pragma unroll
+            for (int pw = 0; pw < RR_POOL; ++pw) wxv[pw] = __ldg(wxp + (u * RR_POOL + pw) * kTW);
+        }
+        while (u < n_units) {
+            const int piece = u;
+            float wal[RR_POOL];
+            const int4 d0 = s_desc[2 * piece], d1 = s_desc[2 * piece + 1];
+            const int colsv[RR_POOL] = {d0.w, d1.x, d1.y};
+            const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
+            int qlo = 8, qhi = -1;
+            // the three bin columns' weights re-indexed by tile column (0 outside the bin's range)
+#pragma unroll
+            for (int pw = 0; pw < RR_POOL; ++pw) {
+                const int c0 = colsv[pw] & 0xff, nc = (colsv[pw] >> 8) & 0xff;
+                wal[pw] = __shfl_sync(0xffffffffu, wxv[pw], (lane - c0) & 31);
+                if (lane < c0 || lane >= c0 + nc) wal[pw] = 0.f;
+                if (nc > 0) { qlo = min(qlo, c0 >> 2); qhi = max(qhi, (c0 + nc - 1) >> 2); }
+            }
+            u = next_unit();                               // next piece and its column weights, under this piece's rows
+            if (u < n_units) {
+#pragma unroll
+                for (int pw = 0; pw < RR_POOL; ++pw) wxv[pw] = __ldg(wxp + (u * RR_POOL + pw) * kTW);
+            }
+            float a[3][3];
+#pragma unroll
+            for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+                for (int pw = 0; pw < 3; ++pw) a[ph][pw] = 0.f;
+            const float* rowp = tile + (r0 * kTC + lane) * kTW;
+            const float4* wyp = s_wy + piece * kTH;
+            for (int q = qlo; q <= qhi; q += 3) {
+                ulonglong2 w[3][3];
+                int off[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int qq = (q + j) & 7;
+                    off[j] = (qq ^ k7) << 2;
+#pragma unroll
+                    for (int pw = 0; pw < RR_POOL; ++pw) {         // a chunk's four weights of a bin column: warp-uniform after the shuffles
+                        const float w0 = __shfl_sync(0xffffffffu, wal[pw], 4 * qq), w1 = __shfl_sync(0xffffffffu, wal[pw], 4 * qq + 1);
+                        const float w2 = __shfl_sync(0xffffffffu, wal[pw], 4 * qq + 2), w3 = __shfl_sync(0xffffffffu, wal[pw], 4 * qq + 3);
+                        w[pw][j].x = t2_pack(w0, w1);
+                        w[pw][j].y = t2_pack(w2, w3);
+                    }
+                }
+                switch (min(qhi - q + 1, 3)) {
+                    case 1: unit_rows_m<1, kRelu>(rowp, off, wyp, nrows, w, a); break;
+                    case 2: unit_rows_m<2, kRelu>(rowp, off, wyp, nrows, w, a); break;
+                    default: unit_rows_m<3, kRelu>(rowp, off, wyp, nrows, w, a); break;
+                }
+            }
+            float* po = partial + (size_t)d0.y * (RR_POOL * RR_POOL) * C + g * kTC + lane;
+#pragma unroll
+            for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+                for (int pw = 0; pw < 3; ++pw) po[(size_t)(ph * RR_POOL + pw) * C] = a[ph][pw];
+        }
+#else
         const int n_units = n_pieces * RR_POOL;
         const float* wxp = list_wx + (size_t)list0 * RR_POOL * kTW + lane;     // unit u: wxp[u * kTW]
         // Units are handed out largest first (the producer warp has ordered them by size class): the buffer can
@@ -982,6 +1114,7 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
             po[(size_t)RR_POOL * C] = a1;
             po[(size_t)2 * RR_POOL * C] = a2;
         }
+#endif
         __syncwarp();
         if (lane == 0) t2_bar_arrive(&s_empty[b]);
     }

@@ -51,16 +51,20 @@ class RRNet(nn.Module):
         tail = self._hm_tail() if (fused and self.fuse_hm_tail) else None
         hms, whs, offsets = self.forward_stage1(pre_feat, skip_last_hm=tail is not None)
         if fused:
-            # decode -> per-class NMS -> RoIAlign(+ReLU) -> head in one C-ABI call, one host sync for N
+            # decode -> per-class NMS -> RoIAlign -> head in one C-ABI call, one host sync for N.  RoIAlign reads
+            # relu(pre_feat[-1]); forward_stage1 has just built that very tensor for the stage-1 heads (:144), so it is
+            # passed on and the kernel skips its own ReLU
             path = self._eval_path((feat.size(0), self.num_classes, feat.size(2), feat.size(3)), k, feat.device)
+            feat = self._relu_last
             if tail is not None:
                 # the heat-map head's last 1x1 conv is fused with the decode's pass over the logits: the
                 # map is written once for the caller (`hms`) and never read back
                 body, last = tail
-                t = body(torch.relu(pre_feat[self.num_stacks - 1]))
+                t = body(self._relu_last)
                 hms.append(path.forward_from_tail(t, last.weight, last.bias, whs[-1], offsets[-1], feat).clone())
             else:
                 path.forward(hms[-1], whs[-1], offsets[-1], feat)
+            self.__dict__.pop('_relu_last', None)               # do not keep the 1 GB activation alive between calls
             r = path.results()
             # the path's buffers are reused by the next forward of the same shape: hand out copies (a few hundred KB)
             return hms, whs, offsets, r["reg"].clone(), r["bxyxy"].clone(), r["scores"].clone(), r["clses"].clone()
@@ -109,7 +113,7 @@ class RRNet(nn.Module):
         folded = self.head_detector.folded()
         if path is None:
             B, C, H, W = hm_shape
-            path = ops.EvalPath(B, C, H, W, k, folded, device=device)
+            path = ops.EvalPath(B, C, H, W, k, folded, device=device, feat_is_relu=True)
             while len(cache) >= self._EVAL_PATH_SLOTS:
                 cache.pop(next(iter(cache)))
         path.folded = folded
@@ -191,6 +195,8 @@ class RRNet(nn.Module):
         hms, whs, offsets = [], [], []
         for i in range(self.num_stacks):
             feat = torch.relu(feats[i])
+            if i == self.num_stacks - 1:
+                self.__dict__['_relu_last'] = feat              # reused by the fused eval path (plain attribute, not a buffer)
             if not (skip_last_hm and i == self.num_stacks - 1):
                 hms.append(self.hm(feat, i))
             whs.append(self.wh(feat, i))

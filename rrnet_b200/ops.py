@@ -296,12 +296,13 @@ class EvalPath:
     RoIAlign+ReLU -> head -> generate_bbox in one C-ABI call (rr_eval_forward).  CUDA-graph capturable."""
 
     def __init__(self, B, C, H, W, K, head_folded, feat_ch=256, pool=0, nms_thr=0.7, scale=4.0, device=None,
-                 keep_roi_feat=False, roi_algo=0, head_algo=0):
+                 keep_roi_feat=False, roi_algo=0, head_algo=0, feat_is_relu=False):
         L = _lib.lib()
         dev = torch.device(device if device is not None else "cuda")
         self.shape = (B, C, H, W, K, feat_ch)
         self.pool, self.nms_thr, self.scale = int(pool), float(nms_thr), float(scale)
-        self.roi_algo = int(roi_algo) | (int(head_algo) << 1)     # bit 0: direct RoIAlign, bit 2 (roi_algo=4): load-staged tiles, bit 1: FFMA head
+        # bit 0: direct RoIAlign, bit 2 (roi_algo=4): load-staged tiles, bit 1: FFMA head, bit 3: feat is already relu(feat)
+        self.roi_algo = int(roi_algo) | (int(head_algo) << 1) | (8 if feat_is_relu else 0)
         self.folded = _f32(head_folded, "head_folded")
         n = B * K
         f32 = dict(dtype=torch.float32, device=dev)
