@@ -21,13 +21,21 @@ constexpr int kOffBr = kOffWr + 4 * 256;
 constexpr int kFoldedF32 = kOffBr + 4;
 static_assert(kFoldedF32 % 4 == 0, "the tensor-core image that follows must stay 16-byte aligned");
 
-// ... followed by the tensor-core image: 34 weight tiles of 64 rows x 32 tf32 (K-major, 128-byte swizzle, exactly
-// the shared-memory image a tcgen05.mma B operand wants), each as a (hi, lo) pair for the 3xTF32 split:
+// ... followed by the tensor-core image: weight tiles of 64 rows x 128 bytes (K-major, 128-byte swizzle, exactly the
+// shared-memory image a tcgen05.mma B operand wants), each as a (hi, lo) pair for the three-product split.
+// RR_HEAD_F16 (default): fp16 elements, 64 K values per row, 17 steps
+//     steps  0.. 3  conv1, K chunk kc            B[o][k] = W1[64kc+k][o]
+//     steps  4..12  conv2, tap                   B[o][k] = W2[k][tap][o]
+//     steps 13..16  conv3, N quarter q           B[n][k] = W3[k][64q+n]
+// else: tf32 elements, 32 K values per row, 34 steps
 //     steps  0.. 7  conv1, K chunk kc            B[o][k] = W1[32kc+k][o]
 //     steps  8..25  conv2, (tap, K chunk)        B[o][k] = W2[32kc+k][tap][o]
 //     steps 26..33  conv3, (N quarter q, chunk)  B[n][k] = W3[32kc+k][64q+n]
-constexpr int kTcSteps = 34;
-constexpr int kTcTileFloats = 64 * 32;                 // one 8 KB tile
+#ifndef RR_HEAD_F16
+#define RR_HEAD_F16 1
+#endif
+constexpr int kTcSteps = RR_HEAD_F16 ? 17 : 34;
+constexpr int kTcTileFloats = 64 * 32;                 // one 8 KB tile (64 rows x 128 bytes)
 constexpr int kTcStepFloats = 2 * kTcTileFloats;       // hi | lo
 constexpr int kOffTc = kFoldedF32;
 constexpr int kFoldedFloats = kFoldedF32 + kTcSteps * kTcStepFloats;

@@ -54,6 +54,8 @@
 // The regressor is applied per row before the pooling (both are linear): reg = (sum_p Wr.relu(y_p)) / 9 + br.
 #include "rr_head.cuh"
 
+#include <cuda_fp16.h>
+
 namespace rr {
 
 constexpr int kTcRois = 8;                       // RoIs per tile
@@ -74,18 +76,38 @@ constexpr int kTcBSlot = 2 * kTcBTile;           // B_hi | B_lo = 16 KB = one st
 constexpr int kRing1 = 1;                        // slots of ring 1 (conv1 weights): the conv1 stream is paced by the x loaders, not by its weights
 constexpr int kXRing = 8;                        // tiles of loader -> output-epilogue hand-off state (s_xdone, s_sb)
 constexpr int kRing2 = 4;                        // slots of ring 2 (conv2 / conv3 weights)
+#if RR_HEAD_F16
+// fp16 operands (kind::f16): a 128-byte row holds 64 K values instead of 32, so every GEMM takes half as many MMAs for
+// the same operand bytes - and the MMA rate here is set by the operand bytes (48 cycles per instruction either way).
+// hi = fp16(v), lo = fp16(v - hi): 22 mantissa bits like the tf32 pair; |x|, |t|, |w| must stay below 65 504.
+constexpr int kSteps1 = 4, kSteps2 = 13;         // weight steps of stream 1 (conv1: 4 K chunks of 64) and stream 2 (9 taps + 4 quarters)
+#else
 constexpr int kSteps1 = 8, kSteps2 = 26;         // weight steps of stream 1 (conv1) and stream 2 (conv2, conv3)
+#endif
 constexpr int kMargin = 8;                       // zero rows above and below the 128 tile rows of a t1 / t2 plane
 constexpr int kPlaneBytes = (128 + 2 * kMargin) * 128;
+#if RR_HEAD_F16
+constexpr int kT2PlaneBytes = 128 * 128;         // t2 (conv3's A operand) lives in shared memory too: no shifted reads, no margins
+constexpr int kTBytes = 2 * kPlaneBytes + 2 * kT2PlaneBytes;     // t1 planes (hi | lo) + t2 planes (hi | lo): 68 KB
+#else
 constexpr int kTBytes = 4 * kPlaneBytes;         // t planes (hi | lo) x (kc 0 | 1): 72 KB
+#endif
 static_assert(kTcBSlot == kTcStepFloats * 4, "a ring slot is one step of the folded image");
+static_assert((kSteps1 / 2) % 2 == 0 && kSteps1 % 2 == 0, "stage / ring-1 phase parities assume an even number of uses per tile");
 static_assert(kSteps1 + kSteps2 == kTcSteps, "the two streams cover the folded image");
 constexpr int kTcSmem = kTBytes + kAStages * kTcAStage + (kRing1 + kRing2) * kTcBSlot + 1024;   // + slack for the 1024-byte alignment
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColD12 = 0, kColD3 = 128;    // conv1 / conv2 accumulator (+64 for odd tiles), conv3 accumulator (256 columns)
 constexpr uint32_t kColT2 = 384;                 // t2 as conv3's A operand: 64 columns tf32 hi, 64 columns lo
+#if RR_HEAD_F16
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+//                          D = f32      A = f16      B = f16       N = 64               M = 128      (both K-major)
+#define RR_MMA_KIND "kind::f16"
+#else
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 //                          D = f32      A = tf32     B = tf32      N = 64               M = 128      (both K-major)
+#define RR_MMA_KIND "kind::tf32"
+#endif
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -97,13 +119,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate,
                                           uint32_t idesc = kIdesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 "tcgen05.mma.cta_group::1." RR_MMA_KIND " [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 // A operand in tensor memory: A[m][k] = lane m, column a_tmem + k (32-bit tf32 words)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 "tcgen05.mma.cta_group::1." RR_MMA_KIND " [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
@@ -176,7 +198,44 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
     hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
     lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
 }
-// ---- weight image: (hi, lo) tf32 tiles in the swizzled shared-memory layout, made once per fold ----
+// fp16 pair of a value: hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+// four values -> 8 bytes of hi and 8 bytes of lo (consecutive K)
+__device__ __forceinline__ void split4_h(float4 v, uint2& hi, uint2& lo) {
+    __half h[4], l[4];
+    split_h(v.x, h[0], l[0]); split_h(v.y, h[1], l[1]); split_h(v.z, h[2], l[2]); split_h(v.w, h[3], l[3]);
+    hi.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    hi.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    lo.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    lo.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+}
+// ---- weight image: (hi, lo) tiles in the swizzled shared-memory layout, made once per fold ----
+#if RR_HEAD_F16
+__global__ void head_fold_tc_kernel(float* __restrict__ f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one (step, n, k) element: 64 x 64 per tile
+    if (i >= kTcSteps * 64 * 64) return;
+    const int step = i / 4096, e = i - step * 4096;
+    const int n = e >> 6, k = e & 63;                               // tile row (output channel), K index inside the chunk
+    float w;
+    if (step < 4) {
+        w = f[kOffW1 + (64 * step + k) * 64 + n];
+    } else if (step < 13) {
+        w = f[kOffW2 + (k * 9 + (step - 4)) * 64 + n];
+    } else {
+        w = f[kOffW3 + k * 256 + 64 * (step - 13) + n];
+    }
+    __half hi, lo;
+    split_h(w, hi, lo);
+    const int pos = n * 64 + ((((k >> 3) ^ (n & 7))) << 3) + (k & 7);          // in halfs: 16-byte chunks of 8 K values, swizzled
+    __half* dst = reinterpret_cast<__half*>(f + kOffTc + step * kTcStepFloats);
+    dst[pos] = hi;
+    dst[2 * kTcTileFloats + pos] = lo;                                          // the lo tile follows 8 KB later
+}
+constexpr int kFoldThreads = kTcSteps * 64 * 64;
+#else
 __global__ void head_fold_tc_kernel(float* __restrict__ f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kTcSteps * kTcTileFloats) return;
@@ -199,9 +258,12 @@ __global__ void head_fold_tc_kernel(float* __restrict__ f) {
     dst[kTcTileFloats + pos] = lo;
 }
 
+constexpr int kFoldThreads = kTcSteps * kTcTileFloats;
+#endif
+
 int head_fold_tc_launch(float* folded, cudaStream_t st) {
     int rc = 0;
-    head_fold_tc_kernel<<<(kTcSteps * kTcTileFloats + 255) / 256, 256, 0, st>>>(folded);
+    head_fold_tc_kernel<<<(kFoldThreads + 255) / 256, 256, 0, st>>>(folded);
     RR_LAUNCHED_K(rc, "head_fold_tc_kernel", st);
     return rc;
 }
@@ -333,7 +395,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     if (++slot2 == kRing2) { slot2 = 0; ++use2; }
                 }
                 if (c1 < total1 && (c1 == 0 || bar_test(&s_free_b1[0], (uint32_t)((c1 - 1) & 1)))) {
-                    load_b(&s_full_b1[0], ring1, c1 & 7);
+                    load_b(&s_full_b1[0], ring1, c1 % kSteps1);
                     ++c1;
                 }
             }
@@ -374,9 +436,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 if (j >= 2) bar_wait(&s_d12free[j & 1], (uint32_t)(((j >> 1) - 1) & 1));   // tile j - 2 has left that accumulator
                 const uint32_t d = tmem + kColD12 + 64u * (uint32_t)(j & 1);
 #pragma unroll
-                for (int s1 = 0; s1 < kSteps1; ++s1) {          // stage / ring-1 slot s1 & 1, its use 4 j + (s1 >> 1)
-                    TC_TIMED(w_a, bar_wait(&s_full_a[s1 & 1], (uint32_t)((s1 >> 1) & 1)));     // (4 j is even)
-                    TC_TIMED(w_b1, bar_wait(&s_full_b1[0], (uint32_t)(s1 & 1)));                // its use is 8 j + s1
+                for (int s1 = 0; s1 < kSteps1; ++s1) {          // stage s1 & 1, its use (kSteps1 / 2) j + (s1 >> 1); kSteps1 / 2 is even
+                    TC_TIMED(w_a, bar_wait(&s_full_a[s1 & 1], (uint32_t)((s1 >> 1) & 1)));
+                    TC_TIMED(w_b1, bar_wait(&s_full_b1[0], (uint32_t)(s1 & 1)));                // ring-1 use kSteps1 j + s1, kSteps1 is even
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
                         const uint32_t sa = sA + (uint32_t)((s1 & 1) * kTcAStage);
@@ -392,8 +454,43 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
 #endif
             return;
         }
-        uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % 3, its use c2 / 3
+        uint32_t c2 = 0;                                        // stream-2 steps issued (all tiles): ring slot c2 % kRing2, its use c2 / kRing2
         long long w_b2 = 0, w_t = 0, w_c1 = 0;                   // trace build: ns blocked on ring 2 / on t1, t2
+#if RR_HEAD_F16
+        const uint32_t sT2 = sT + 2u * (uint32_t)kPlaneBytes;   // t2 planes (hi | lo) behind the t1 planes
+        for (int it = 0; it < n_my; ++it) {
+            const uint32_t d12_cur = tmem + kColD12 + 64u * (uint32_t)(it & 1);
+            uint32_t slot2 = c2 % kRing2, par2 = (c2 / kRing2) & 1u;
+#pragma unroll
+            for (int s2 = 0; s2 < kSteps2; ++s2) {              // one step = one tap of conv2 (K = 64) or one N quarter of conv3
+                if (s2 == 0) TC_TIMED(w_t, bar_wait(&s_t1ready, (uint32_t)(it & 1)));           // t1 in place
+                if (s2 == 9) {
+                    TC_TIMED(w_t, bar_wait(&s_t2ready, (uint32_t)(it & 1)));                    // t2 in place
+                    if (it > 0) bar_wait(&s_d3free, (uint32_t)((it - 1) & 1));  // the previous tile has left conv3's accumulator
+                }
+                const uint32_t slot_a = slot2, par_a = par2;
+                if (++slot2 == kRing2) { slot2 = 0; par2 ^= 1u; }
+                TC_TIMED(w_b2, bar_wait(&s_full_b2[slot_a], par_a));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                int shift = 0;
+                if (s2 < 9) shift = 4 * (s2 / 3 - 1) + (s2 % 3 - 1);
+                const uint32_t sa_hi = sT + (uint32_t)((kMargin + shift) * 128);
+                if (elect_one()) {
+                    if (s2 < 9) {                               // conv2: A = t1 tiles in shared memory, shifted by the tap
+                        issue12(sa_hi, sa_hi + kPlaneBytes, sB2 + slot_a * (uint32_t)kTcBSlot, d12_cur, s2 == 0);
+                    } else {                                    // conv3: A = t2 tiles in shared memory, one N quarter per step
+                        issue12(sT2, sT2 + kT2PlaneBytes, sB2 + slot_a * (uint32_t)kTcBSlot,
+                                tmem + kColD3 + 64u * (uint32_t)(s2 - 9), true);
+                    }
+                    umma_commit(&s_free_b2[slot_a]);
+                    if (s2 == 8) umma_commit(&s_phase[1]);
+                    if (s2 == 10) umma_commit(&s_phase[2]);
+                    if (s2 == 12) umma_commit(&s_phase[3]);
+                }
+            }
+            c2 += kSteps2;
+        }
+#else
         for (int it = 0; it < n_my; ++it) {
             const uint32_t d12_cur = tmem + kColD12 + 64u * (uint32_t)(it & 1);
             uint32_t slot2 = c2 % kRing2, par2 = (c2 / kRing2) & 1u;
@@ -433,6 +530,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             }
             c2 += kSteps2;
         }
+#endif
 #ifdef RR_HEAD_TC_TRACE
         if (lane == 0) { TC_TRACE_VAL(22, w_b2); TC_TRACE_VAL(23, w_t); TC_TRACE_VAL(24, w_c1); }
 #endif
@@ -447,12 +545,23 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     if (warp >= kEpiWarps && warp < kWarpIssuer1) {
         const int ltid = tid - kEpiThreads;
         int it_row[kTcItems], it_p[kTcItems], it_ch[kTcItems], xoff[kTcItems];
+#if RR_HEAD_F16
+        int it_m7[kTcItems];
+#endif
 #pragma unroll
         for (int q = 0; q < kTcItems; ++q) {
             const int i = ltid + q * kLoaders, r72 = i >> 3, ch = i & 7;
             const int rl = r72 / 9, p = r72 - rl * 9, m = kRoiRows * rl + 4 + 4 * (p / 3) + p % 3;
             it_row[q] = rl; it_p[q] = p; it_ch[q] = ch;
+#if RR_HEAD_F16
+            // fp16 stage rows hold 64 K values: the item's four channels of the 32-channel chunk kc are half of the
+            // 16-byte chunk 4 (kc & 1) + (ch >> 1) of row m; xoff is the offset for an even kc, odd chunks flip bit 2 of
+            // the chunk index before the swizzle (see the store)
+            xoff[q] = m * 128;
+            it_m7[q] = m & 7;
+#else
             xoff[q] = m * 128 + ((ch ^ (m & 7)) << 4);
+#endif
         }
         uint32_t cw = 0;                                        // conv1 chunks staged so far (all tiles)
         long long w_fa = 0;                                     // trace build: ns blocked on a free stage
@@ -525,6 +634,29 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     }
                 }
                 if (kc + 1 < 8) load_x_chunk(kc + 1);           // in flight while this chunk is split and stored
+#if RR_HEAD_F16
+                // a stage holds TWO 32-channel chunks (K = 64): wait for it before the first, publish it after the second
+                const uint32_t fill = cw >> 1, st = fill & 1u, use = fill >> 1;
+                if ((cw & 1u) == 0 && use > 0) TC_TIMED(w_fa, bar_wait_warp(&s_free_a[st], (use - 1) & 1u));
+                uint8_t* a_hi = stages + st * kTcAStage;
+                uint8_t* a_lo = a_hi + kTcATile;
+#pragma unroll
+                for (int q = 0; q < kTcItems; ++q) {
+                    uint2 hi, lo;
+                    split4_h(v[q], hi, lo);
+                    const int chunk = (4 * (int)(cw & 1u) + (it_ch[q] >> 1)) ^ it_m7[q];
+                    const int o = xoff[q] + (chunk << 4) + ((it_ch[q] & 1) << 3);
+                    *reinterpret_cast<uint2*>(a_hi + o) = hi;
+                    *reinterpret_cast<uint2*>(a_lo + o) = lo;
+                    if (xscr[q]) *reinterpret_cast<float4*>(xscr[q] + 32 * kc) = v[q];
+                }
+                if (cw & 1u) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(&s_full_a[st]);
+                }
+                ++cw;
+#else
                 const uint32_t st = cw & 1u, use = cw >> 1;
                 if (use > 0) TC_TIMED(w_fa, bar_wait_warp(&s_free_a[st], (use - 1) & 1u));
                 uint8_t* a_hi = stages + st * kTcAStage;
@@ -541,6 +673,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                 __syncwarp();
                 if (lane == 0) bar_arrive(&s_full_a[st]);
                 ++cw;
+#endif
             }
             __threadfence_block();                              // the fp32 copy and s_sb, before the epilogue warps are told
             __syncwarp();
@@ -564,6 +697,39 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
         //     descriptors; pad rows are written as zeros).  The two column halves are the K chunks of conv2.
         // E2: t2 = relu(conv2 + b2) -> (hi, lo) tf32 in tensor memory, conv3's A operand: the shared-memory tiles
         //     are free for t1 of the next tile while conv3 runs.
+#if RR_HEAD_F16
+        // t = relu(D + b) as fp16 (hi, lo) rows of 64 K values in shared memory: t1 into the margin-padded planes that
+        // conv2 reads through shifted descriptors (pad rows written as zeros), t2 into its own planes (conv3's A operand)
+        auto epilogue_t = [&](uint32_t d12, const float* bias, bool to_t1) {
+            uint8_t* p_hi = to_t1 ? base + (kMargin + em) * 128 : base + 2 * kPlaneBytes + em * 128;
+            uint8_t* p_lo = p_hi + (to_t1 ? kPlaneBytes : kT2PlaneBytes);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tmem_ld32(d12 + ((uint32_t)(32 * eq) << 16) + (uint32_t)(32 * h), v);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                   // 16-byte chunk 4 h + c = channels 32 h + 8 c .. + 7
+                    float4 o0, o1;
+                    const float* bb = bias + 32 * h + 8 * c;
+                    const bool on = pixel_row || !to_t1;
+                    o0.x = on ? fmaxf(v[8 * c] + bb[0], 0.f) : 0.f;     o0.y = on ? fmaxf(v[8 * c + 1] + bb[1], 0.f) : 0.f;
+                    o0.z = on ? fmaxf(v[8 * c + 2] + bb[2], 0.f) : 0.f; o0.w = on ? fmaxf(v[8 * c + 3] + bb[3], 0.f) : 0.f;
+                    o1.x = on ? fmaxf(v[8 * c + 4] + bb[4], 0.f) : 0.f; o1.y = on ? fmaxf(v[8 * c + 5] + bb[5], 0.f) : 0.f;
+                    o1.z = on ? fmaxf(v[8 * c + 6] + bb[6], 0.f) : 0.f; o1.w = on ? fmaxf(v[8 * c + 7] + bb[7], 0.f) : 0.f;
+                    uint2 h0, l0, h1, l1;
+                    split4_h(o0, h0, l0);
+                    split4_h(o1, h1, l1);
+                    const int off = ((4 * h + c) ^ (em & 7)) << 4;
+                    *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                    *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(to_t1 ? &s_t1ready : &s_t2ready);
+        };
+#else
         auto epilogue_t = [&](uint32_t d12, const float* bias, bool to_smem) {
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -603,6 +769,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
             __syncwarp();
             if (lane == 0) bar_arrive(to_smem ? &s_t1ready : &s_t2ready);
         };
+#endif
         TC_TRACE(2);
 #ifdef RR_HEAD_TC_TRACE
         long long lap_ = tc_now(), w_p0 = 0, w_e1 = 0, w_x = 0, w_p1 = 0, w_e2 = 0, w_e3 = 0;

@@ -32,7 +32,7 @@ def test_binding_table_matches_header():
     assert L.rr_version() >= 100
     assert b"workspace" in L.rr_error_string(-2)
     # size queries are pure host code
-    assert L.rr_head_folded_floats() == (256 * 64 + 64 + 9 * 64 * 64 + 64 + 64 * 256 + 256 + 4 * 256 + 4) + 34 * 2 * 64 * 32
+    assert L.rr_head_folded_floats() == (256 * 64 + 64 + 9 * 64 * 64 + 64 + 64 * 256 + 256 + 4 * 256 + 4) + 17 * 2 * 64 * 32      # tensor-core image: 17 steps of (hi | lo) 64 x 128-byte fp16 tiles
     assert L.rr_decode_workspace_bytes(8, 10, 272, 480, 1500) >= 8 * 16384 * 8
     assert L.rr_eval_workspace_bytes(8, 10, 272, 480, 1500, 256) > 8 * 1500 * 256 * 9 * 4
 
