@@ -647,6 +647,10 @@ def kernel_rooflines(path, d, peak, n_rois, algo_read, B, C, H, W, K, Cf, reps=5
         "decode_sample_kernel": (B * 32768 * 4, "latency", "32 K sampled logits per image"),
         "decode_collect_kernel": (B * C * H * W * 4, "hbm", "heat-map logits read once: B*C*H*W*4"),
         "decode_select_kernel": (B * K * (8 + 16 + 32), "latency", "candidates + wh/offset gathers + rows out; one CTA per image"),
+        "decode_select_cluster_kernel": (B * K * (2 * 8 + 16 + 32), "latency", "~2K candidates of 8 bytes per image + wh/offset gathers + rows out; a cluster of 8 CTAs per image"),
+        "tail_sample_kernel": (0, "latency", "sampled pixel lines of the head activations"),
+        "tail_thresh_kernel": (0, "latency", "threshold from 1024 folded sample maxima per image"),
+        "tail_conv_collect_kernel": (B * Cf * H * W * 4 + B * C * H * W * 4, "hbm", "head activations read once + logits written once"),
         "stage1_partition_kernel": (B * K * (24 + 28), "latency", "rows in, class-sorted rows out; one CTA per image"),
         "nms_mask_kernel": (B * K * 20, "alu", "sorted boxes in; IoU tiles (fp32 ALU bound, SURVEY 8d)"),
         "nms_scan_kernel": (B * K * 8, "latency", "greedy scan per (image,class) segment: serial chain"),
