@@ -64,9 +64,12 @@ int         rr_set_sm_reserve(int n_sms);
 int         rr_set_pdl(int enabled);
 /* Process-wide switches between equivalent implementations (same results), for measurements:
  *   RR_OPT_PDL                as rr_set_pdl
- *   RR_OPT_SELECT_SINGLE_CTA  1 = the decode's top-K selection by ONE CTA per image instead of a cluster of 8 */
+ *   RR_OPT_SELECT_SINGLE_CTA  1 = the decode's top-K selection by ONE CTA per image instead of a cluster of 8
+ *   RR_OPT_COMBINE_IN_TILE_KERNEL  1 = in rr_eval_forward the RoIAlign tile kernel combines a RoI's partial slots itself as soon
+ *                             as its last piece is done (deterministic, bit-identical; default 0: the head sums the slots) */
 #define RR_OPT_PDL 1
 #define RR_OPT_SELECT_SINGLE_CTA 2
+#define RR_OPT_COMBINE_IN_TILE_KERNEL 3
 int         rr_set_option(int option, int value);
 int         rr_kernel_trace_begin(void* const* events, const char** names, int capacity, void* stream);
 int         rr_kernel_trace_end(void);

@@ -9,6 +9,7 @@ namespace rr {
 std::atomic<uint64_t> g_launches{0};
 thread_local int g_sm_reserve = 0;
 extern int g_select_single_cta;   // rr_decode.cu
+int g_combine_in_tile = 0;        // RR_OPT_COMBINE_IN_TILE_KERNEL: the RoIAlign tile kernel combines a RoI's slots itself (measured slower in total)
 int g_pdl_enabled = 0;          // measured on the B200: no gain for one batch at a time (0.771 ms either way), -7 % with two batches in flight
 thread_local KernelTrace g_ktrace = {nullptr, nullptr, 0, 0};
 
@@ -19,10 +20,10 @@ size_t decode_ws_bytes(int B);
 int stage1_nms_launch(const float*, int, int, int, double, float*, float*, float*, int32_t*, void*, cudaStream_t);
 size_t stage1_nms_ws_bytes(int B, int K, int C);
 int roi_align_launch(const float*, const float*, const int32_t*, int, int, int, int, int, int, int, int, float*, void*,
-                     cudaStream_t);
+                     cudaStream_t, int*);
 void roi_align_ws_views(void*, int, int, int, int, int, const float**, const int**, const int**, const float**);
 int head_forward_launch_partial(float*, const float*, const int*, const int*, const float*, const int32_t*, int,
-                                const float*, float*, int, cudaStream_t);
+                                const float*, float*, int, int, cudaStream_t);
 size_t roi_align_ws_bytes(int n_cap, int B, int C, int H, int W);
 int head_forward_launch(const float*, const int32_t*, int, const float*, float*, int, cudaStream_t);
 int generate_bbox_launch(const float*, const float*, const float*, const float*, const int32_t*, int, float,
@@ -63,6 +64,7 @@ RR_API int rr_set_option(int option, int value) {
     switch (option) {
         case RR_OPT_PDL: g_pdl_enabled = value ? 1 : 0; return 0;
         case RR_OPT_SELECT_SINGLE_CTA: g_select_single_cta = value ? 1 : 0; return 0;
+        case RR_OPT_COMBINE_IN_TILE_KERNEL: g_combine_in_tile = value ? 1 : 0; return 0;
         default: return RR_E_BADARG;
     }
 }
@@ -137,13 +139,17 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     // roi_feat requested: materialise it (combine) and feed the head from it; otherwise the head sums the
     // tile-path partial slots itself and only direct-path RoIs go through the buffer
     const int fused = roi_feat == nullptr && roi_algo != 1;
-    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, relu, roi_algo, fused ? 0 : 1, rf, w.roi, st);
+    // fused: the head sums the RoIAlign partial slots (rows_mode = 0, default), or - RR_OPT_COMBINE_IN_TILE_KERNEL - the tile
+    // kernel combines a RoI's slots itself and leaves the RoI's [9][256] row in rf (rows_mode = 1; needs the TMA kernel)
+    int rows_mode = 0;
+    rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, relu, roi_algo,
+                          fused ? (g_combine_in_tile ? 2 : 0) : 1, rf, w.roi, st, &rows_mode);
     if (rc) return rc;
     mark(3);
     if (fused) {
         const float* partial; const int* slot; const int* pieces; const float* count;
         roi_align_ws_views(w.roi, n_cap, B, feat_ch, H, W, &partial, &slot, &pieces, &count);
-        rc = head_forward_launch_partial(rf, partial, slot, pieces, count, n_dev, n_cap, head_folded, out_reg, head_algo, st);
+        rc = head_forward_launch_partial(rf, partial, slot, pieces, count, n_dev, n_cap, head_folded, out_reg, head_algo, rows_mode, st);
     } else {
         rc = head_forward_launch(rf, n_dev, n_cap, head_folded, out_reg, head_algo, st);
     }

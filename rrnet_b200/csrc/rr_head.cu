@@ -116,7 +116,10 @@ head_forward_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     const bool on = n < live;
     int sb = -1, pieces = 0;
     float cnt = 1.f;
-    if (on && src.partial) { sb = src.slot[n]; pieces = src.pieces[n]; cnt = src.count[n]; }
+    if (on && src.partial) {
+        sb = src.slot[n]; pieces = src.pieces[n]; cnt = src.count[n];
+        if (src.combined && sb >= 0) { sb = n; pieces = pieces > 0 ? 1 : 0; cnt = 1.f; }       // one finished row per RoI
+    }
 
     stage_weights(s_w, f + kOffW1, kC1 * 64, tid);                      // chunk 0
     float xv[kPix];
@@ -286,7 +289,7 @@ int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, cons
 // algo: 0 = tcgen05 tensor cores (3xTF32), 1 = fp32 FFMA
 int head_forward_launch(const float* roi_feat, const int32_t* n_rois_dev, int n_cap, const float* folded,
                         float* reg, int algo, cudaStream_t st) {
-    HeadSrc src = {roi_feat, nullptr, nullptr, nullptr, nullptr, nullptr};
+    HeadSrc src = {roi_feat, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
                      : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }
@@ -296,8 +299,8 @@ int head_forward_launch(const float* roi_feat, const int32_t* n_rois_dev, int n_
 // (combine == 0), so the tensor-core head keeps its residual copy of x there
 int head_forward_launch_partial(float* roi_feat, const float* partial, const int* slot, const int* pieces,
                                 const float* count, const int32_t* n_rois_dev, int n_cap, const float* folded,
-                                float* reg, int algo, cudaStream_t st) {
-    HeadSrc src = {roi_feat, partial, slot, pieces, count, roi_feat};
+                                float* reg, int algo, int combined, cudaStream_t st) {
+    HeadSrc src = {roi_feat, combined ? roi_feat : partial, slot, pieces, count, roi_feat, combined};
     return algo == 1 ? head_ffma_launch_src(src, n_rois_dev, n_cap, folded, reg, st)
                      : head_tc_launch_src(src, n_rois_dev, n_cap, folded, reg, st);
 }

@@ -583,13 +583,17 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     const int n = roi0 + rl;
                     int sb = -1, pcs = 0;
                     float cnt = 1.f;
-                    if (src.partial) { sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n); }
+                    if (src.partial) {
+                        sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n);
+                        if (src.combined && sb >= 0) { sb = n; pcs = pcs > 0 ? 1 : 0; cnt = 1.f; }     // one finished row per RoI
+                    }
                     if (sb < 0) {                               // finished feature [256][9] (direct RoIAlign path / plain API)
                         xpc[q] = -1;
                         xptr[q] = src.roi_feat + (size_t)n * 2304 + p + 36 * ch;
                     } else {                                    // partial slots [pieces][9][256], to be summed and scaled
                         xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
-                        xscr[q] = src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
+                        // combined: the row IS the copy - except for a RoI without pieces (all-zero output), whose row nobody wrote
+                        xscr[q] = (src.combined && pcs > 0) ? nullptr : src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
                         xpc[q] = pcs;
                         xinv[q] = 1.0f / cnt;
                     }

@@ -471,7 +471,7 @@ def set_pdl(enabled):
     check(_lib.lib().rr_set_pdl(int(bool(enabled))), "rr_set_pdl")
 
 
-OPT_PDL, OPT_SELECT_SINGLE_CTA = 1, 2
+OPT_PDL, OPT_SELECT_SINGLE_CTA, OPT_COMBINE_IN_TILE_KERNEL = 1, 2, 3
 
 
 def set_option(option, value):

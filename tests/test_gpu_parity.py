@@ -607,6 +607,31 @@ def test_eval_path_config4_shards(ops, oracle_mod, world, rank):
     _check_shard_against_oracle(ops, oracle_mod, B, 1500, synth.SEED_C4 + rank, roi_stride=1 if world == 8 else 7)
 
 
+def test_eval_path_combine_in_tile_kernel_is_bit_identical(ops):
+    """RR_OPT_COMBINE_IN_TILE_KERNEL: the RoIAlign tile kernel sums a RoI's partial slots itself when its last piece is done
+    (arrival counters, combine jobs) and hands the head one row per RoI.  Same order of summation as the head's own sum of
+    the slots, so every output is bit-identical - also on a workspace full of garbage (a RoI without pieces has no row)."""
+    B, C, H, W, K = 4, 10, 136, 240, 900
+    x = {k: dev(v) for k, v in synth.eval_inputs(B, H, W, K, 4242).items()}
+    folded = ops.head_fold({k: v.cuda() for k, v in synth.head_params(3).items()})
+    ref = ops.EvalPath(B, C, H, W, K, folded)
+    ref.forward(x["hm"], x["wh"], x["off"], x["feat"])
+    r = ref.results()
+    ops.set_option(ops.OPT_COMBINE_IN_TILE_KERNEL, 1)
+    try:
+        for fill in (0, 0x7f):
+            p = ops.EvalPath(B, C, H, W, K, folded)
+            p.ws.fill_(fill)
+            for _ in range(2):                      # a second call on the used workspace
+                p.forward(x["hm"], x["wh"], x["off"], x["feat"])
+            got = p.results()
+            assert got["n"] == r["n"] and got["n"] > 500
+            for key in ("bxyxy", "reg", "s1", "s2"):
+                np.testing.assert_array_equal(npy(got[key]), npy(r[key]))
+    finally:
+        ops.set_option(ops.OPT_COMBINE_IN_TILE_KERNEL, 0)
+
+
 def test_eval_path_config5_full_batch(ops, oracle_mod):
     """Config 5 at its full size: B=16, K=5000 proposals per image (~75 k RoIs) through the whole path."""
     r = _check_shard_against_oracle(ops, oracle_mod, 16, 5000, synth.SEED_C5, roi_stride=5)
