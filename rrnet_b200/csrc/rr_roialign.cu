@@ -717,8 +717,23 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 #ifndef RR_T2_MERGED
 #define RR_T2_MERGED 0       // 1: a unit is a whole piece (three bin columns in one pass).  Measured on the B200 (config 2):
 #endif                       // 0.581 ms against 0.458 ms for (piece, bin column) units - see unit_rows_m
+// RR_T2_TMEM 1 (NOT the default - measured slower): the first kT2TmRows rows of every tile are ALSO copied into tensor
+// memory (64 x tcgen05.cp.32x128b.warpx4 straight from the swizzled tile: 32 channels -> 32 lanes, replicated into the four
+// lane quarters so that any warp can read them; 512 columns = 2 tile buffers x 8 rows x 32 pixels, no MMA is ever issued) and
+// the units take those rows with tcgen05.ld.32x32b.x4 - the same four pixels of the lane's channel an LDS.128 returns -
+// instead of through the load/store unit, whose shared-memory wavefronts bound this kernel.  tools/tmem_tile_probe.cu on
+// the B200: the layout works as designed (0 mismatches) and the two read paths do add up (LDS.128 alone 128 B/clk/SM,
+// tcgen05.ld alone up to 222, both at once 120 + 134).  But (1) a tcgen05.cp costs ~75 cycles whatever its shape (32x128b
+// 512 bytes, 128x256b 4 KB: ~130), i.e. 5 200 cycles per ticket for 8 rows, and while copies run LDS.128 drops to ~50
+// B/clk/SM - the copies take more from the LSU than the tensor-memory reads give back; (2) LDTM wants its address in a
+// uniform register: every base address costs WARPSYNC + R2UR, rows must be compile-time offsets (pairs of rows per block).
+// Kernel time at config 2, bit-identical results: 0.463 ms without, 0.525 with; copies but no tensor-memory reads 0.497,
+// reads but no copies 0.489, neither (just the extra code and barriers) 0.477.  Kept for the record.
+#ifndef RR_T2_TMEM
+#define RR_T2_TMEM 0
+#endif
 #ifndef RR_T2_THREADS
-#define RR_T2_THREADS (RR_T2_MERGED ? 640 : 736)    // consumer warps + the producer (merged units: 19 warps, 102 registers).  Measured (RoIAlign stage, ms): 416: 0.557, 480: 0.538,
+#define RR_T2_THREADS (RR_T2_MERGED ? 640 : (RR_T2_TMEM ? 768 : 736))    // consumer warps + the producer (+ the tensor-memory copier) (merged units: 19 warps, 102 registers).  Measured (RoIAlign stage, ms): 416: 0.557, 480: 0.538,
 #endif                       // 544: 0.524, 608: 0.518, 672: 0.513, 736: 0.512, 800 (spills): 0.534, 1024 (64 registers): 0.533
 // RR_T2_MERGED 1: a unit is a whole piece (three bin columns in one pass); 0: (piece, bin column) units
 #ifndef RR_T2_UNROLL
@@ -726,7 +741,16 @@ roi_tile_kernel(const float* __restrict__ feat, const int4* __restrict__ list,
 #endif
 constexpr int kT2Threads = RR_T2_THREADS;
 constexpr int kT2Unroll = RR_T2_UNROLL;
-constexpr int kT2Consumers = kT2Threads / 32 - 1;
+constexpr int kT2Consumers = kT2Threads / 32 - 1 - (RR_T2_TMEM ? 1 : 0);
+#ifndef RR_T2_TM_ROWS
+#define RR_T2_TM_ROWS 8
+#endif
+#ifndef RR_T2_TM_MIN_PIECES
+#define RR_T2_TM_MIN_PIECES 0            // tickets with fewer pieces are evaluated from shared memory only (no copy)
+#endif
+constexpr int kT2TmRows = RR_T2_TM_ROWS; // tile rows mirrored in tensor memory (8 x 32 pixels = 256 columns per tile buffer)
+constexpr int kT2TmCols = 512;
+static_assert(2 * kT2TmRows * kTW <= kT2TmCols && kT2TmRows <= kTH, "two tile buffers' rows fit the 512 columns");
 constexpr int kT2Passes = 4;             // unit size classes, handed out largest first
 constexpr int kT2TileBytes = kTC * kTH * kTW * (int)sizeof(float);            // 98304 = one TMA box
 constexpr int kT2TableBytes = kChunk * 2 * 16 + kChunk * kTH * 16;            // descriptors + row weights
@@ -789,6 +813,66 @@ __device__ __forceinline__ void unit_rows_q(const float* __restrict__ rowp, cons
         a0 = fmaf(wy.x, s, a0);
         a1 = fmaf(wy.y, s, a1);
         a2 = fmaf(wy.z, s, a2);
+    }
+}
+
+// ---- tensor-memory side of a unit (RR_T2_TMEM) ----
+__device__ __forceinline__ void t2_ldtm4(uint32_t taddr, uint32_t (&r)[4]) {      // lane <- its TMEM lane, 4 consecutive columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void t2_ldtm_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers of a tcgen05.ld must not be read before the wait: tie their uses to a point after it
+__device__ __forceinline__ void t2_pin(uint32_t (&r)[4]) { asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])); }
+// shared-memory matrix descriptor of 32 rows x 16 bytes inside a K-major SWIZZLE_128B tile (8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t t2_sw128_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+template <int NQ, bool kRelu>
+__device__ __forceinline__ void unit_row_t(const uint32_t (&r)[3][4], const float4 wy, const ulonglong2 (&w)[3],
+                                           float& a0, float& a1, float& a2) {
+    unsigned long long s01 = 0ull, s23 = 0ull;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        float4 v = make_float4(__uint_as_float(r[j][0]), __uint_as_float(r[j][1]), __uint_as_float(r[j][2]), __uint_as_float(r[j][3]));
+        if (kRelu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        s01 = t2_fma2(w[j].x, t2_pack(v.x, v.y), s01);
+        s23 = t2_fma2(w[j].y, t2_pack(v.z, v.w), s23);
+    }
+    float sx, sy, sz, sw;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(s01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sz), "=f"(sw) : "l"(s23));
+    const float s = (sx + sz) + (sy + sw);
+    a0 = fmaf(wy.x, s, a0);
+    a1 = fmaf(wy.y, s, a1);
+    a2 = fmaf(wy.z, s, a2);
+}
+
+// rows of one unit that live in tensor memory: the arithmetic of unit_rows_q, the pixels from tcgen05.ld.  ta = the
+// warp's lane quarter | column of (the unit's first row, its first chunk of this group).  LDTM takes its address from a
+// UNIFORM register plus an immediate: with a dynamic row / chunk offset every load costs a WARPSYNC + R2UR of its own
+// (measured: 0.70 ms for the kernel instead of 0.46), so the (at most kT2TmRows) rows and the chunks of the group are
+// compile-time offsets from ONE base.  tcgen05.wait::ld is free (the loads sit on the ordinary scoreboard).
+template <int NQ, bool kRelu>
+__device__ __forceinline__ void unit_rows_t(const uint32_t ta, const float4* __restrict__ s_wy, const int npairs,
+                                            const ulonglong2 (&w)[3], float& a0, float& a1, float& a2) {
+#pragma unroll
+    for (int p = 0; p < kT2TmRows / 2; ++p) {              // rows come in PAIRS (an odd last row is left to the shared-memory loop):
+        if (p < npairs) {                                  // one straight-line block and one base-address move per pair
+            uint32_t ra[3][4], rb[3][4];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) t2_ldtm4(ta + (uint32_t)(2 * p * kTW + 4 * j), ra[j]);
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) t2_ldtm4(ta + (uint32_t)((2 * p + 1) * kTW + 4 * j), rb[j]);
+            const float4 wy0 = s_wy[2 * p], wy1 = s_wy[2 * p + 1];
+            t2_ldtm_wait();
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) { t2_pin(ra[j]); t2_pin(rb[j]); }
+            unit_row_t<NQ, kRelu>(ra, wy0, w, a0, a1, a2);
+            unit_row_t<NQ, kRelu>(rb, wy1, w, a0, a1, a2);
+        }
     }
 }
 
@@ -864,6 +948,11 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
     __shared__ int4 s_jobs[2][kChunk];
     __shared__ int s_njobs[2], s_nextjob[2];
     __shared__ unsigned long long s_jobsready[2];            // the producer has written the jobs that ride with buffer b's ticket
+#if RR_T2_TMEM
+    __shared__ unsigned long long s_tfull[2];                // rows 0..kT2TmRows-1 of buffer b's tile are in tensor memory (tcgen05.commit)
+    __shared__ unsigned long long s_done;                    // every consumer warp is past its last tensor-memory read
+    __shared__ uint32_t s_tmem;
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char* base = s_raw + ((1024u - (t2_saddr(s_raw) & 1023u)) & 1023u);
     if (tid == 0) {
@@ -872,11 +961,70 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_full[b])), "r"(1) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_empty[b])), "r"(kT2Consumers) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_jobsready[b])), "r"(1) : "memory");
+#if RR_T2_TMEM
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_tfull[b])), "r"(1) : "memory");
+#endif
         }
+#if RR_T2_TMEM
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t2_saddr(&s_done)), "r"(kT2Consumers) : "memory");
+#endif
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+#if RR_T2_TMEM
+    if (warp == kT2Consumers + 1) {                          // the copier warp owns the allocation (all 512 columns of the SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t2_saddr(&s_tmem)), "n"(kT2TmCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
     __syncthreads();
+#if RR_T2_TMEM
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    if (warp == kT2Consumers + 1) {
+        // ------------------------------ tensor-memory copier ------------------------------
+        // As soon as a tile has landed (`full`): 64 x tcgen05.cp.32x128b.warpx4 - row y, 16-byte chunk q of the 32
+        // channels -> columns 32 y + 4 q .. + 3 of the buffer's 256-column region, all four lane quarters - and one
+        // commit onto `tfull`.  The region's previous reader (ticket i - 2) is done: the producer only refilled the
+        // buffer after its `empty` phase, which every consumer reaches after its last tcgen05.wait::ld.
+        if (lane == 0) {
+            for (int i = 0;; ++i) {
+                const int b = i & 1;
+                uint32_t ok;
+                for (;;) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(t2_saddr(&s_full[b])), "r"((uint32_t)((i >> 1) & 1)), "r"(1000u) : "memory");
+                    if (ok) break;
+                }
+                const int n_pieces = *reinterpret_cast<volatile int*>(&s_work[b][2]);
+                if (n_pieces < 0) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (n_pieces > 0 && n_pieces >= RR_T2_TM_MIN_PIECES) {
+                    const uint32_t src = t2_saddr(base + b * kT2TileBytes), dst = tmem + (uint32_t)(b * kT2TmRows * kTW);
+#pragma unroll 1
+                    for (int y = 0; y < kT2TmRows; ++y) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;"
+                                         ::"r"(dst + (uint32_t)(y * kTW + 4 * q)), "l"(t2_sw128_desc(src + (uint32_t)(y * kTC * kTW * 4 + 16 * q))) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t2_saddr(&s_tfull[b])) : "memory");
+            }
+            uint32_t ok;
+            for (;;) {                                       // all consumers are through: the columns can go back
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(t2_saddr(&s_done)), "r"(0u), "r"(1000u) : "memory");
+                if (ok) break;
+            }
+        }
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kT2TmCols) : "memory");
+        return;
+    }
+#endif
 
     if (warp == kT2Consumers) {
         // ------------------------------ producer warp ------------------------------
@@ -1027,11 +1175,22 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
 
     // ------------------------------ consumer warps ------------------------------
     const int k7 = lane & 7;
+#if RR_T2_TMEM
+    const uint32_t tq = tmem + ((uint32_t)(32 * (warp & 3)) << 16);       // a warp reaches the lane quarter warp % 4 (all four hold the same rows)
+#endif
     for (int i = 0;; ++i) {
         const int b = i & 1;
         t2_bar_wait_warp(&s_full[b], (uint32_t)((i >> 1) & 1));
         const int n_pieces = s_work[b][2];
         if (n_pieces < 0) break;
+#if RR_T2_TMEM
+        bool tm_ready = false;                             // this warp has seen `tfull` of this ticket
+        auto tm_wait = [&]() {
+            t2_bar_wait_warp(&s_tfull[b], (uint32_t)((i >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tm_ready = true;
+        };
+#endif
         const int g = s_work[b][0], list0 = s_work[b][1];
         const float* tile = reinterpret_cast<const float*>(base + b * kT2TileBytes);
         const int4* s_desc = reinterpret_cast<const int4*>(base + 2 * kT2TileBytes + b * kT2TableBytes);
@@ -1137,10 +1296,19 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
             __syncwarp();
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             if (ncols > 0) {
-                const float* rowp = tile + (r0 * kTC + lane) * kTW;
                 const float4* wyp = s_wy + piece * kTH;
                 const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(s_wal[warp]);
                 const int q1 = (c0 + ncols - 1) >> 2;
+#if RR_T2_TMEM
+                // rows below kT2TmRows come from tensor memory, the rest from the shared-memory tile (same arithmetic,
+                // same order: rows ascending inside a chunk group)
+                const int nt = n_pieces >= RR_T2_TM_MIN_PIECES ? (max(min(nrows, kT2TmRows - r0), 0) & ~1) : 0;     // an even number of rows
+                if (nt > 0 && !tm_ready) tm_wait();
+                const float* rowp = tile + ((r0 + nt) * kTC + lane) * kTW;
+                const uint32_t ta = tq + (uint32_t)(b * kT2TmRows * kTW + r0 * kTW);
+#else
+                const float* rowp = tile + (r0 * kTC + lane) * kTW;
+#endif
                 for (int q = c0 >> 2; q <= q1; q += 3) {
                     ulonglong2 w[3];
                     int off[3];
@@ -1149,11 +1317,29 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                         off[j] = (((q + j) & 7) ^ k7) << 2;
                         w[j] = wq[(q + j) & 7];
                     }
+#if RR_T2_TMEM
+                    const uint32_t tg = ta + (uint32_t)(4 * q);      // the group's chunks q .. q + 2 never wrap (q + j <= q1 <= 7)
+                    switch (min(q1 - q + 1, 3)) {
+                        case 1:
+                            if (nt > 0) unit_rows_t<1, kRelu>(tg, wyp, nt >> 1, w, a0, a1, a2);
+                            unit_rows_q<1, kRelu>(rowp, off, wyp + nt, nrows - nt, w, a0, a1, a2);
+                            break;
+                        case 2:
+                            if (nt > 0) unit_rows_t<2, kRelu>(tg, wyp, nt >> 1, w, a0, a1, a2);
+                            unit_rows_q<2, kRelu>(rowp, off, wyp + nt, nrows - nt, w, a0, a1, a2);
+                            break;
+                        default:
+                            if (nt > 0) unit_rows_t<3, kRelu>(tg, wyp, nt >> 1, w, a0, a1, a2);
+                            unit_rows_q<3, kRelu>(rowp, off, wyp + nt, nrows - nt, w, a0, a1, a2);
+                            break;
+                    }
+#else
                     switch (min(q1 - q + 1, 3)) {
                         case 1: unit_rows_q<1, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
                         case 2: unit_rows_q<2, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
                         default: unit_rows_q<3, kRelu>(rowp, off, wyp, nrows, w, a0, a1, a2); break;
                     }
+#endif
                 }
             }
             float* po = partial + ((size_t)d0.y * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
@@ -1189,9 +1375,21 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                 for (int q = 0; q < kBins; ++q) dst[(size_t)q * C] = acc[q] * inv;
             }
         }
+#if RR_T2_TMEM
+        // Every warp sees `tfull` before it releases the buffer, whether it read tensor memory or not: the copier is then
+        // never more than one phase behind (parity waits stay unambiguous) and is done with the tile before the next TMA
+        // may overwrite it.
+        if (!tm_ready) tm_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
         __syncwarp();
         if (lane == 0) t2_bar_arrive(&s_empty[b]);
     }
+#if RR_T2_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) t2_bar_arrive(&s_done);
+#endif
 }
 
 // The 4-D tensor map of the feature maps, dimensions ordered (x, c, y, image) so that a box lands in shared
