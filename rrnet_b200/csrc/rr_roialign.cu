@@ -418,16 +418,34 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
             axis_table(gy, H, lane, ty, rp.cy_lo, rp.cy_hi);
             float* wxn = wx + (size_t)n * (RR_POOL * kMaxWinT);
             float4* wyn = wy4 + (size_t)n * kMaxWinT;
-            const int kmax = max(gx.n, gy.n);
-            for (int k = lane; k < kmax; k += 32) {
-                float b[RR_POOL];
+            // One (axis, bin, pixel) weight per lane and round, only for the pixels inside the bin's range (a bin covers
+            // about a third of the window): with lanes on pixels and a loop over the three bins of both axes every
+            // round ran six divergent table look-ups, most of them for lanes outside the bin.  Column weights outside a
+            // bin's range are never read (roi_fill masks by the range); row weights outside it must be zero.
+            for (int k = lane; k < gy.n; k += 32) wyn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            int cnt[2 * RR_POOL], total = 0;
 #pragma unroll
-                for (int p = 0; p < RR_POOL; ++p) {
-                    const float a = (k >= rp.cx_lo[p] && k <= rp.cx_hi[p]) ? table_weight(tx, gx.grid, p, gx.lo + k) : 0.f;
-                    b[p] = (k >= rp.cy_lo[p] && k <= rp.cy_hi[p]) ? table_weight(ty, gy.grid, p, gy.lo + k) : 0.f;
-                    if (k < gx.n) wxn[p * kMaxWinT + k] = a;
-                }
-                if (k < gy.n) wyn[k] = make_float4(b[0], b[1], b[2], 0.f);
+            for (int p = 0; p < RR_POOL; ++p) {
+                cnt[p] = max(rp.cx_hi[p] - rp.cx_lo[p] + 1, 0);
+                cnt[RR_POOL + p] = max(rp.cy_hi[p] - rp.cy_lo[p] + 1, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 2 * RR_POOL; ++q) total += cnt[q];
+            for (int t = lane; t < total; t += 32) {
+                int q = 0, r = t, lo = rp.cx_lo[0];
+#pragma unroll
+                for (int j = 0; j < 2 * RR_POOL - 1; ++j)
+                    if (q == j && r >= cnt[j]) {
+                        r -= cnt[j]; q = j + 1;
+                        lo = j + 1 < RR_POOL ? rp.cx_lo[(j + 1) % RR_POOL] : rp.cy_lo[(j + 1) % RR_POOL];
+                    }
+                const bool is_y = q >= RR_POOL;
+                const int p = is_y ? q - RR_POOL : q;
+                const int k = lo + r;
+                const float wgt = table_weight(is_y ? ty : tx, is_y ? gy.grid : gx.grid, p, (is_y ? gy.lo : gx.lo) + k);
+                if (is_y) reinterpret_cast<float*>(wyn + k)[p] = wgt;
+                else wxn[p * kMaxWinT + k] = wgt;
             }
             if (lane < m) {
                 const int tyi = rp.ty0 + lane / rp.ntx, txi = rp.tx0 + lane % rp.ntx;
@@ -470,7 +488,7 @@ roi_prep_kernel(const float* __restrict__ rois, const int* __restrict__ n_rois_d
 // piece owns its slot).  A descriptor is 8 ints:
 //   roi, slot, rows = r0 | nrows<<8 | wy_off<<16, cols[3] = c0 | ncols<<8, pieces of the RoI, its first slot
 // (r0/c0 tile-local start, wy_off offset of the first row inside the RoI window), followed in two side
-// arrays by the piece's slices of the separable weights: list_wx[pos][3][32], list_wy[pos][kTH] (zero padded).
+// arrays by the piece's slices of the separable weights: list_wx[pos][3][32], list_wy[pos][kTH] (valid entries only).
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
@@ -495,33 +513,35 @@ roi_fill_kernel(const RoiPrep* __restrict__ prep, const int* __restrict__ slot,
         const int t = rp.img * td.tiles_per_img + (rp.ty0 + lane / rp.ntx) * td.ntx + rp.tx0 + lane % rp.ntx;
         my_pos = tile_off[t] + atomicAdd(tile_fill + t, 1);
     }
-    for (int j = 0; j < rp.nty; ++j) {
+    // Only the valid rows / columns of a slice are written: every consumer stops at nrows / ncols (or masks by them), so the
+    // entries past them are never used - and the kernel is a chain of dependent latencies, not of bytes: two pieces per
+    // iteration keep the loads of one under the stores of the other.
+#pragma unroll 2
+    for (int pc = 0; pc < m; ++pc) {
+        const int j = pc / rp.ntx, i = pc - j * rp.ntx;
         const int py0 = (rp.ty0 + j) * kTH;
         const int r0 = max(rp.y_lo, py0), r1 = min(rp.y_lo + rp.ny - 1, py0 + kTH - 1);
         const int nrows = r1 - r0 + 1, wyo = r0 - rp.y_lo;
         const int rows = (r0 - py0) | (nrows << 8) | (wyo << 16);
-        for (int i = 0; i < rp.ntx; ++i) {
-            const int px0 = (rp.tx0 + i) * kTW;
-            int cols[RR_POOL], ncol[RR_POOL], wxo[RR_POOL];
+        const int px0 = (rp.tx0 + i) * kTW;
+        int cols[RR_POOL], ncol[RR_POOL], wxo[RR_POOL];
 #pragma unroll
-            for (int p = 0; p < RR_POOL; ++p) {
-                const int c0 = max(rp.x_lo + rp.cx_lo[p], px0), c1 = min(rp.x_lo + rp.cx_hi[p], px0 + kTW - 1);
-                ncol[p] = max(c1 - c0 + 1, 0);
-                wxo[p] = c0 - rp.x_lo;
-                cols[p] = ncol[p] > 0 ? ((c0 - px0) | (ncol[p] << 8)) : 0;
-            }
-            const int pos = __shfl_sync(0xffffffffu, my_pos, j * rp.ntx + i);
-            if (lane == 0) {
-                list[2 * pos] = make_int4(n, sb + j * rp.ntx + i, rows, cols[0]);
-                list[2 * pos + 1] = make_int4(cols[1], cols[2], m, sb);       // .z pieces of the RoI, .w its first slot
-            }
-            // the piece's slices of the separable weights, zero padded, in list order
-            if (lane < kTH)
-                list_wy[(size_t)pos * kTH + lane] = lane < nrows ? wyn[wyo + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int p = 0; p < RR_POOL; ++p)
-                list_wx[((size_t)pos * RR_POOL + p) * kTW + lane] = lane < ncol[p] ? wxn[p * kMaxWinT + wxo[p] + lane] : 0.f;
+        for (int p = 0; p < RR_POOL; ++p) {
+            const int c0 = max(rp.x_lo + rp.cx_lo[p], px0), c1 = min(rp.x_lo + rp.cx_hi[p], px0 + kTW - 1);
+            ncol[p] = max(c1 - c0 + 1, 0);
+            wxo[p] = c0 - rp.x_lo;
+            cols[p] = ncol[p] > 0 ? ((c0 - px0) | (ncol[p] << 8)) : 0;
         }
+        const int pos = __shfl_sync(0xffffffffu, my_pos, pc);
+        if (lane == 0) {
+            list[2 * pos] = make_int4(n, sb + pc, rows, cols[0]);
+            list[2 * pos + 1] = make_int4(cols[1], cols[2], m, sb);       // .z pieces of the RoI, .w its first slot
+        }
+        // the piece's slices of the separable weights, in list order
+        if (lane < nrows) list_wy[(size_t)pos * kTH + lane] = wyn[wyo + lane];
+#pragma unroll
+        for (int p = 0; p < RR_POOL; ++p)
+            if (lane < ncol[p]) list_wx[((size_t)pos * RR_POOL + p) * kTW + lane] = wxn[p * kMaxWinT + wxo[p] + lane];
     }
 }
 
