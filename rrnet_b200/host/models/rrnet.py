@@ -69,17 +69,20 @@ class RRNet(nn.Module):
             # the path's buffers are reused by the next forward of the same shape: hand out copies (a few hundred KB)
             return hms, whs, offsets, r["reg"].clone(), r["bxyxy"].clone(), r["scores"].clone(), r["clses"].clone()
         bboxs = self.transform_bbox(hms[-1], whs[-1], offsets[-1], k)     # (bs, k, 6)
-        bxyxys, scores, clses = [], [], []
-        for b_idx in range(bboxs.size(0)):
-            bbox = self.nms(bboxs[b_idx])
-            xyxy = bbox[:, :4]
-            scores.append(bbox[:, 4])
-            clses.append(bbox[:, 5])
-            batch_idx = torch.ones((xyxy.size(0), 1), device=xyxy.device) * b_idx
-            bxyxys.append(torch.cat((batch_idx, xyxy), dim=1))
-        bxyxys = torch.cat(bxyxys, dim=0)
-        scores = torch.cat(scores, dim=0)
-        clses = torch.cat(clses, dim=0)
+        if self.nms_type != 'soft_nms' and self.nms_per_class:
+            bxyxys, scores, clses = self._nms_batch(bboxs)                # all images at once, one host sync
+        else:
+            bxyxys, scores, clses = [], [], []
+            for b_idx in range(bboxs.size(0)):
+                bbox = self.nms(bboxs[b_idx])
+                xyxy = bbox[:, :4]
+                scores.append(bbox[:, 4])
+                clses.append(bbox[:, 5])
+                batch_idx = torch.ones((xyxy.size(0), 1), device=xyxy.device) * b_idx
+                bxyxys.append(torch.cat((batch_idx, xyxy), dim=1))
+            bxyxys = torch.cat(bxyxys, dim=0)
+            scores = torch.cat(scores, dim=0)
+            clses = torch.cat(clses, dim=0)
         roi_feat = _RoIAlignReLU.apply(feat, bxyxys)
         stage2_reg = self.forward_stage2(roi_feat)
         return hms, whs, offsets, stage2_reg, bxyxys, scores, clses
@@ -119,6 +122,36 @@ class RRNet(nn.Module):
         path.folded = folded
         cache[key] = path                      # re-inserted last = most recently used
         return path
+
+    def _nms_batch(self, bboxs):
+        """The per-image loop of the reference's forward (models/rrnet.py:37-49) + its per-class hard NMS (:56-80) for the
+        whole batch: bboxs [B,K,6] -> bxyxys [N,5] (image index, box), scores [N], clses [N]; images ascending, classes
+        ascending inside an image, scores descending inside a class - the reference's concatenation order.  One launch and
+        one host sync (for N) instead of a Python loop with two syncs per image.  When bboxs carries gradients (training:
+        criterion back-propagates through the kept boxes, rrnet_operator.py:82-83) the kept rows are gathered from bboxs by
+        index, so autograd keeps working."""
+        B, K = bboxs.size(0), bboxs.size(1)
+        device = bboxs.device
+        if not (bboxs.requires_grad and torch.is_grad_enabled()):
+            bx, sc, cl, counts = ops.stage1_nms(bboxs.detach().contiguous(), self.num_classes, 0.7)
+            n = int(counts[B].item())
+            return bx[:n], sc[:n], cl[:n]
+        d = bboxs.detach().reshape(B * K, 6)
+        img = torch.arange(B, device=device).repeat_interleave(K)
+        key = img * self.num_classes + d[:, 5].long()                     # one segment per (image, class)
+        order = torch.sort(key, stable=True).indices                      # stable: score order inside a segment survives
+        _, counts = torch.unique_consecutive(key[order], return_counts=True)
+        seg = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=device)
+        seg[1:] = torch.cumsum(counts, 0).int()
+        ds = d[order]
+        keep_idx, keep_cnt = ops.nms_batched(ds[:, :4].contiguous(), ds[:, 4].contiguous(), seg, 0.7)
+        # a segment's kept rows sit at the start of its own range of keep_idx
+        start = seg[:-1].long().repeat_interleave(counts, output_size=B * K)
+        kept = torch.arange(B * K, device=device) - start < keep_cnt.long().repeat_interleave(counts, output_size=B * K)
+        rows = order[keep_idx[:B * K][kept].long()]                        # the one host sync: N is data dependent
+        sel = bboxs.reshape(B * K, 6)[rows]
+        bxyxys = torch.cat(((rows // K).to(sel.dtype)[:, None], sel[:, :4]), dim=1)
+        return bxyxys, sel[:, 4], sel[:, 5]
 
     # ------------------------------------------------------------------ models/rrnet.py:56-80
     def nms(self, bbox):

@@ -173,7 +173,16 @@ def test_forward_generate_bbox_ext_nms_golden(host):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     np.testing.assert_array_equal(npy(outs2[4]), g["bxyxy"])
+    np.testing.assert_array_equal(npy(outs2[6]), g["clses"])
     assert rel_err(npy(outs2[3]), g["s2_reg"], floor=1.0) < TOL
+    # the batched NMS of the unfused forward without gradients (rr_stage1_nms) and with them (segmented rr_nms_batched +
+    # index gather) return the same rows in the reference's order
+    with torch.no_grad():
+        bb = net.transform_bbox(x["hm"], x["wh"], x["off"], K)
+        bx, sc, cl = net._nms_batch(bb)
+    np.testing.assert_array_equal(npy(bx), g["bxyxy"])
+    np.testing.assert_array_equal(npy(cl), g["clses"])
+    assert rel_err(npy(sc), g["scores"]) < TOL
 
 
 def test_nms_method_matches_oracle(host, oracle_mod):
