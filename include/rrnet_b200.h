@@ -66,7 +66,10 @@ int         rr_set_pdl(int enabled);
  *   RR_OPT_PDL                as rr_set_pdl
  *   RR_OPT_SELECT_SINGLE_CTA  1 = the decode's top-K selection by ONE CTA per image instead of a cluster of 8
  *   RR_OPT_COMBINE_IN_TILE_KERNEL  1 = in rr_eval_forward the RoIAlign tile kernel combines a RoI's partial slots itself as soon
- *                             as its last piece is done (deterministic, bit-identical; default 0: the head sums the slots) */
+ *                             as its last piece is done (deterministic, bit-identical; default 0: the head sums the slots);
+ *                             2 = no slots at all: the tile kernel's units add their bins into the RoI's zeroed row with float
+ *                             reductions (red.global.add.f32).  NOT bit-reproducible for RoIs cut into three or more pieces
+ *                             (the order of the additions is the hardware's); within 1e-6 of the default */
 #define RR_OPT_PDL 1
 #define RR_OPT_SELECT_SINGLE_CTA 2
 #define RR_OPT_COMBINE_IN_TILE_KERNEL 3

@@ -64,7 +64,7 @@ RR_API int rr_set_option(int option, int value) {
     switch (option) {
         case RR_OPT_PDL: g_pdl_enabled = value ? 1 : 0; return 0;
         case RR_OPT_SELECT_SINGLE_CTA: g_select_single_cta = value ? 1 : 0; return 0;
-        case RR_OPT_COMBINE_IN_TILE_KERNEL: g_combine_in_tile = value ? 1 : 0; return 0;
+        case RR_OPT_COMBINE_IN_TILE_KERNEL: g_combine_in_tile = value == 2 ? 2 : (value ? 1 : 0); return 0;
         default: return RR_E_BADARG;
     }
 }
@@ -143,7 +143,7 @@ RR_API int rr_eval_forward(const float* hm, const float* wh, const float* off, c
     // kernel combines a RoI's slots itself and leaves the RoI's [9][256] row in rf (rows_mode = 1; needs the TMA kernel)
     int rows_mode = 0;
     rc = roi_align_launch(feat, out_bxyxy, n_dev, n_cap, B, feat_ch, H, W, relu, roi_algo,
-                          fused ? (g_combine_in_tile ? 2 : 0) : 1, rf, w.roi, st, &rows_mode);
+                          fused ? (g_combine_in_tile == 2 ? 3 : (g_combine_in_tile ? 2 : 0)) : 1, rf, w.roi, st, &rows_mode);
     if (rc) return rc;
     mark(3);
     if (fused) {

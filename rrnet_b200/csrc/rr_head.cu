@@ -118,7 +118,7 @@ head_forward_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
     float cnt = 1.f;
     if (on && src.partial) {
         sb = src.slot[n]; pieces = src.pieces[n]; cnt = src.count[n];
-        if (src.combined && sb >= 0) { sb = n; pieces = pieces > 0 ? 1 : 0; cnt = 1.f; }       // one finished row per RoI
+        if (src.combined && sb >= 0) { sb = n; pieces = pieces > 0 ? 1 : 0; if (src.combined == 1) cnt = 1.f; }       // one row per RoI (2: still to be scaled)
     }
 
     stage_weights(s_w, f + kOffW1, kC1 * 64, tid);                      // chunk 0

@@ -50,7 +50,8 @@ struct HeadSrc {
     const float* count;        // [n_cap] divisor
     float* scratch;            // [n_cap,9,256] workspace for the tensor-core head's residual copy of x (tile-path RoIs), with partial
     int combined;              // 1: `partial` holds one finished, already scaled [9][256] row per tile-path RoI AT ROW n (the
-                               // tile kernel combined the slots itself): one piece per RoI, no scaling, no residual copy
+                               // tile kernel combined the slots itself): one piece per RoI, no scaling, no residual copy;
+                               // 2: the same row holds the UNSCALED sum (atomic accumulation): scaled by 1/count, copy written in place
 };
 
 int head_ffma_launch_src(HeadSrc src, const int32_t* n_rois_dev, int n_cap, const float* folded, float* reg, cudaStream_t st);

@@ -585,7 +585,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     float cnt = 1.f;
                     if (src.partial) {
                         sb = __ldg(src.slot + n); pcs = __ldg(src.pieces + n); cnt = __ldg(src.count + n);
-                        if (src.combined && sb >= 0) { sb = n; pcs = pcs > 0 ? 1 : 0; cnt = 1.f; }     // one finished row per RoI
+                        if (src.combined && sb >= 0) { sb = n; pcs = pcs > 0 ? 1 : 0; if (src.combined == 1) cnt = 1.f; }     // one row per RoI (2: still to be scaled)
                     }
                     if (sb < 0) {                               // finished feature [256][9] (direct RoIAlign path / plain API)
                         xpc[q] = -1;
@@ -593,7 +593,7 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     } else {                                    // partial slots [pieces][9][256], to be summed and scaled
                         xptr[q] = src.partial + (size_t)sb * 2304 + p * 256 + 4 * ch;
                         // combined: the row IS the copy - except for a RoI without pieces (all-zero output), whose row nobody wrote
-                        xscr[q] = (src.combined && pcs > 0) ? nullptr : src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;
+                        xscr[q] = (src.combined == 1 && pcs > 0) ? nullptr : src.scratch + (size_t)n * 2304 + p * 256 + 4 * ch;      // 2: scaled in place
                         xpc[q] = pcs;
                         xinv[q] = 1.0f / cnt;
                     }
@@ -612,7 +612,11 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     } else {
 #pragma unroll
                         for (int j = 0; j < kTcSlotsInReg; ++j)
+#ifdef RR_HEAD_PROBE_ONE_SLOT                                      // timing-only experiment (tools/head_trace.py): wrong results
+                            if (j < min(xpc[q], 1))
+#else
                             if (j < xpc[q])
+#endif
                                 xp[q][j] = __ldg(reinterpret_cast<const float4*>(xptr[q] + (size_t)j * 2304 + 32 * kc));
                     }
                 }
@@ -652,7 +656,9 @@ head_tc_kernel(HeadSrc src, const int* __restrict__ n_rois_dev, int n_cap,
                     const int o = xoff[q] + (chunk << 4) + ((it_ch[q] & 1) << 3);
                     *reinterpret_cast<uint2*>(a_hi + o) = hi;
                     *reinterpret_cast<uint2*>(a_lo + o) = lo;
+#ifndef RR_HEAD_PROBE_NO_SCRATCH
                     if (xscr[q]) *reinterpret_cast<float4*>(xscr[q] + 32 * kc) = v[q];
+#endif
                 }
                 if (cw & 1u) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA

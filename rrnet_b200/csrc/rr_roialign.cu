@@ -954,7 +954,8 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
                     const int4* __restrict__ items, const int* __restrict__ tile_off,
                     const int* __restrict__ tile_fill, int* __restrict__ ctl,
                     int C, TileDims td, float* __restrict__ partial,
-                    int* __restrict__ arrived, const float* __restrict__ cnt_arr, float* __restrict__ combined) {
+                    int* __restrict__ arrived, const float* __restrict__ cnt_arr, float* __restrict__ combined,
+                    float* __restrict__ atomic_rows) {
     RR_PDL_PROLOGUE();
     extern __shared__ unsigned char s_raw[];
     __shared__ int s_work[2][4];                   // g, list start, pieces (-1: no more tickets)
@@ -1368,10 +1369,20 @@ roi_tile_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __rest
 #endif
                 }
             }
-            float* po = partial + ((size_t)d0.y * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
-            po[0] = a0;
-            po[(size_t)RR_POOL * C] = a1;
-            po[(size_t)2 * RR_POOL * C] = a2;
+            if (atomic_rows) {
+                // RR_OPT_COMBINE_IN_TILE_KERNEL = 2: no slots - the unit ADDS its three bins into the RoI's own (zeroed) [9][C]
+                // row with fire-and-forget float reductions.  The order of a RoI's pieces is whatever the hardware makes it:
+                // bit-reproducible for RoIs of one or two pieces only (a + b is commutative), last-bit differences otherwise.
+                float* po = atomic_rows + ((size_t)d0.x * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(po), "f"(a0) : "memory");
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(po + (size_t)RR_POOL * C), "f"(a1) : "memory");
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(po + (size_t)2 * RR_POOL * C), "f"(a2) : "memory");
+            } else {
+                float* po = partial + ((size_t)d0.y * (RR_POOL * RR_POOL) + pw) * C + g * kTC + lane;
+                po[0] = a0;
+                po[(size_t)RR_POOL * C] = a1;
+                po[(size_t)2 * RR_POOL * C] = a2;
+            }
         }
 #endif
         if (combined) {
@@ -1535,6 +1546,8 @@ void roi_align_ws_views(void* ws, int n_cap, int B, int C, int H, int W, const f
 
 // combine == 0: leave the tile-path RoIs as partial slots (out only receives the direct-path RoIs)
 // combine == 1: roi_combine_kernel materialises out [n,C,3,3]
+// combine == 3: the TMA tile kernel's units add their bins straight into the RoI's zeroed [9][C] ROW in out with float
+//               reductions (no slots; unscaled sums; *rows_mode = 2, or 0 when the call fell back to plain slots)
 // combine == 2: the TMA tile kernel combines a RoI's slots itself as soon as its last piece is done and writes the RoI's
 //               [9][C] ROW into out (same buffer, other layout; direct-path RoIs still get [C][3][3]); *rows_mode tells the
 //               caller whether that happened (1) or the call fell back to plain slots (0: no TMA, load-staged tiles)
@@ -1564,16 +1577,19 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
         }
         CUtensorMap tm;
         if (algo != 2 && make_tile_tmap(feat, B, C, H, W, &tm)) {      // TMA-staged tiles (needs 16-byte rows)
+            if (combine == 3)                                           // the rows the units add into start from zero
+                RR_CUDA(cudaMemsetAsync(out, 0, (size_t)n_cap * C * RR_POOL * RR_POOL * sizeof(float), st), rc);
             if (relu)
                 launch_pdl(roi_tile_tma_kernel<true>, dim3(sms_for_persistent()), dim3(kT2Threads), kT2Smem, st, 
                     tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial,
-                    w.arrived, w.cnt, combine == 2 ? out : (float*)nullptr);
+                    w.arrived, w.cnt, combine == 2 ? out : (float*)nullptr, combine == 3 ? out : (float*)nullptr);
             else
                 launch_pdl(roi_tile_tma_kernel<false>, dim3(sms_for_persistent()), dim3(kT2Threads), kT2Smem, st, 
                     tm, w.list, w.list_wx, w.list_wy, w.items, w.tile_off, w.tile_fill, w.ctl, C, w.td, w.partial,
-                    w.arrived, w.cnt, combine == 2 ? out : (float*)nullptr);
+                    w.arrived, w.cnt, combine == 2 ? out : (float*)nullptr, combine == 3 ? out : (float*)nullptr);
             RR_LAUNCHED_K(rc, "roi_tile_tma_kernel", st);
             if (combine == 2 && rows_mode) *rows_mode = 1;
+            if (combine == 3 && rows_mode) *rows_mode = 2;
         } else {                                                        // tiles staged through the load/store path
             launch_pdl(roi_tile_kernel, dim3(2 * sms_for_persistent()), dim3(kTileThreads), kTileSmem, st, feat, w.list, w.list_wx, w.list_wy, w.items,
                                                                       w.tile_off, w.tile_fill, w.ctl, C, H, W, relu,
@@ -1601,11 +1617,18 @@ int roi_align_launch(const float* feat, const float* rois, const int32_t* n_rois
 // scatters 4 atomicAdds per sample); the pieces of a tile are summed in ascending RoI order: bit-reproducible.  The ReLU mask is applied in the coalesced write-out.  RoIs of the direct path
 // (windows over 64 pixels) are added afterwards by a per-RoI kernel with atomicAdd.
 // --------------------------------------------------------------------------------------------
+#ifndef RR_BWD_VEC
+#define RR_BWD_VEC 1
+#endif
+// One CTA of 24 warps (= the 24 tile rows) per (tile, channel group).  Measured alternatives (config 2, kernel time): two CTAs
+// of 12 rows each so that two fit an SM (the write-out scratch then overlays the piece tables, which needs a block barrier
+// before the write-out) 1.71 ms, three of 8 rows 2.72 ms, one CTA with that barrier 1.61 ms - against 1.49 ms: the warps of a
+// CTA finish their piece loops at different times and the early ones' write-out already runs under the others' loops.
 constexpr int kBwdThreads = 32 * kTH;                 // 24 warps = 24 tile rows
 constexpr int kBwdWxFloats = kChunk * RR_POOL * kTW;  // weights placed at tile columns
 constexpr int kBwdGFloats = kChunk * kTC * RR_POOL * RR_POOL;
 constexpr int kBwdMaxSort = 2048;                      // pieces of one tile that are brought into RoI order (more: list order)
-constexpr int kBwdSmemFloats = kChunk * 2 * 4 + kChunk * kTH * 4 + kBwdWxFloats + kBwdGFloats + kChunk + kTH * kTC * 33 + 2 * kBwdMaxSort;
+constexpr int kBwdSmemFloats = kChunk * 2 * 4 + kChunk * kTH * 4 + kBwdWxFloats + kBwdGFloats + 2 * kChunk + kTH * kTC * 33 + 2 * kBwdMaxSort;
 constexpr int kBwdSmem = kBwdSmemFloats * (int)sizeof(float);
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -1619,7 +1642,8 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
     float* s_wx = reinterpret_cast<float*>(s_wy + kChunk * kTH);      // [piece][pw][tile column]
     float* s_g = s_wx + kBwdWxFloats;                                // [piece][channel][9]
     float* s_inv = s_g + kBwdGFloats;
-    float* s_t = s_inv + kChunk;                                     // [row][channel][33]
+    int* s_rng = reinterpret_cast<int*>(s_inv + kChunk);             // per piece: first | last tile column with a weight
+    float* s_t = s_inv + 2 * kChunk;                                 // [row][channel][33]
     int* s_ids = reinterpret_cast<int*>(s_t + kTH * kTC * 33);       // RoI index of every piece of the tile
     int* s_perm = s_ids + kBwdMaxSort;                               // pieces in ascending RoI order
     const int tid = threadIdx.x, lane = tid & 31, y = tid >> 5;
@@ -1631,9 +1655,17 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
     const int px0 = tx * kTW, py0 = ty * kTH;
     if (n_p == 0) {                                                  // no RoI touches the tile: its gradient is zero.  Every
         const int gy = py0 + y, gx = px0 + lane;                     // element of the map is written by exactly one CTA, so
-        if (gy < H && gx < W)                                        // the map needs no memset (1.07 GB at config 2)
+        if (gy >= H) return;                                         // the map needs no memset (1.07 GB at config 2)
+        if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(grad_feat) & 15) == 0) {
+            const int x4 = lane & 7;
+            if (px0 + 4 * x4 < W)
+                for (int c = lane >> 3; c < kTC; c += 4)
+                    *reinterpret_cast<float4*>(grad_feat + (((size_t)img * C + (size_t)g * kTC + c) * H + gy) * W + px0 + 4 * x4) =
+                        make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (gx < W) {
             for (int c = 0; c < kTC; ++c)
                 grad_feat[(((size_t)img * C + (size_t)g * kTC + c) * H + gy) * W + gx] = 0.f;
+        }
         return;
     }
     float acc[kTW];
@@ -1675,12 +1707,23 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
             const int roi = s_desc[2 * p].x;
             s_g[i] = __ldg(grad_out + ((size_t)roi * C + (size_t)g * kTC) * 9 + e);
         }
-        if (tid < cnt) s_inv[tid] = 1.0f / __ldg(cnt_arr + s_desc[2 * tid].x);
+        if (tid < cnt) {
+            const int4 d0 = s_desc[2 * tid], d1 = s_desc[2 * tid + 1];
+            s_inv[tid] = 1.0f / __ldg(cnt_arr + d0.x);
+            int cmin = kTW, cmax = -1;
+            const int colsv[RR_POOL] = {d0.w, d1.x, d1.y};
+#pragma unroll
+            for (int pw = 0; pw < RR_POOL; ++pw) {
+                const int c0 = colsv[pw] & 0xff, nc = (colsv[pw] >> 8) & 0xff;
+                if (nc > 0) { cmin = min(cmin, c0); cmax = max(cmax, c0 + nc - 1); }
+            }
+            s_rng[tid] = cmin | ((cmax + 1) << 8) | ((d0.z & 0xffff) << 16);      // cmax + 1: 0 for a piece without columns; r0 | nrows << 8 on top
+        }
         __syncthreads();
 
         for (int p = 0; p < cnt; ++p) {
-            const int4 d0 = s_desc[2 * p], d1 = s_desc[2 * p + 1];
-            const int r0 = d0.z & 0xff, nrows = (d0.z >> 8) & 0xff;
+            const unsigned rng = (unsigned)s_rng[p];                 // one broadcast word per (row, piece): most pairs stop here
+            const int r0 = (rng >> 16) & 0xff, nrows = rng >> 24;
             if ((unsigned)(y - r0) >= (unsigned)nrows) continue;     // warp-uniform: this piece does not cover row y
             const float4 wy = s_wy[p * kTH + (y - r0)];
             const float inv = s_inv[p];
@@ -1689,13 +1732,7 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
 #pragma unroll
             for (int pw = 0; pw < RR_POOL; ++pw)
                 s3[pw] = fmaf(wy.x, gp[pw], fmaf(wy.y, gp[3 + pw], wy.z * gp[6 + pw])) * inv;
-            int cmin = kTW, cmax = -1;
-            const int colsv[RR_POOL] = {d0.w, d1.x, d1.y};
-#pragma unroll
-            for (int pw = 0; pw < RR_POOL; ++pw) {
-                const int c0 = colsv[pw] & 0xff, nc = (colsv[pw] >> 8) & 0xff;
-                if (nc > 0) { cmin = min(cmin, c0); cmax = max(cmax, c0 + nc - 1); }
-            }
+            const int cmin = rng & 0xff, cmax = (int)((rng >> 8) & 0xff) - 1;
             const float4* w0 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 0) * kTW);
             const float4* w1 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 1) * kTW);
             const float4* w2 = reinterpret_cast<const float4*>(s_wx + (p * RR_POOL + 2) * kTW);
@@ -1717,7 +1754,35 @@ roi_tile_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ gr
     for (int x = 0; x < kTW; ++x) st[lane * 33 + x] = acc[x];
     __syncwarp();
     const int gy = py0 + y, gx = px0 + lane;
-    if (gy < H && gx < W) {
+    if (gy >= H) return;
+    if (RR_BWD_VEC && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(grad_feat)) & 15) == 0) {
+        // four pixels per lane: eight lanes cover the 128-byte row of one channel, a warp four channels per round.  The
+        // four scalar reads of the [c][33] scratch are conflict free (bank = c + 4 x4 + j over 4 channels x 8 chunks).
+        const int x4 = lane & 7, cq = lane >> 3;
+        if (px0 + 4 * x4 < W) {                                        // W % 4 == 0: a chunk is inside the map or outside it
+            float4 f[kTC / 4];                                         // all eight mask loads in flight before the first store
+            const size_t idx0 = (((size_t)img * C + (size_t)g * kTC + cq) * H + gy) * W + px0 + 4 * x4;
+            const size_t cstep = (size_t)4 * H * W;
+            if (relu) {
+#pragma unroll
+                for (int k = 0; k < kTC / 4; ++k) f[k] = __ldg(reinterpret_cast<const float4*>(feat + idx0 + k * cstep));
+            }
+#pragma unroll
+            for (int k = 0; k < kTC / 4; ++k) {
+                const float* sp = st + (cq + 4 * k) * 33 + 4 * x4;
+                float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                if (relu) {
+                    if (!(f[k].x > 0.f)) v.x = 0.f;
+                    if (!(f[k].y > 0.f)) v.y = 0.f;
+                    if (!(f[k].z > 0.f)) v.z = 0.f;
+                    if (!(f[k].w > 0.f)) v.w = 0.f;
+                }
+                *reinterpret_cast<float4*>(grad_feat + idx0 + k * cstep) = v;
+            }
+        }
+        return;
+    }
+    if (gx < W) {
         for (int c = 0; c < kTC; ++c) {
             const size_t idx = (((size_t)img * C + (size_t)g * kTC + c) * H + gy) * W + gx;
             float v = st[c * 33 + lane];

@@ -13,7 +13,8 @@ from rrnet_b200 import build as B  # noqa: E402
 TRACE_LIB = os.path.join(ROOT, "tools", "librrnet_trace.so")
 
 
-VARIANTS = {"": []}
+VARIANTS = {"": [], "oneslot": ["-DRR_HEAD_PROBE_ONE_SLOT"], "noscr": ["-DRR_HEAD_PROBE_NO_SCRATCH"],
+            "oneslot_noscr": ["-DRR_HEAD_PROBE_ONE_SLOT", "-DRR_HEAD_PROBE_NO_SCRATCH"]}      # timing-only: wrong results by design
 
 
 def lib_path(variant):
