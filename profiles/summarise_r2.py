@@ -58,7 +58,7 @@ def main():
     lines = ["# Round 2, final state - one B200 (`tools/r2_measure.sh`, summarised by `profiles/summarise_r2.py`)", ""]
     # ---- bench lines
     for name in ("r2_final_bench", "r2_final_bench_c3", "r2_final_bench_c5", "r2_final_bench_reference", "r2_bench_n2", "r2_bench_c4_n2",
-                 "r2_bench_n8", "r2_bench_c4_n8"):
+                 "r2_bench_n4", "r2_bench_n8", "r2_bench_c4_n8"):
         src = os.path.join(OUT, name + ".json")
         if os.path.exists(src):
             txt = [l for l in open(src).read().splitlines() if l.startswith("{")]
@@ -99,7 +99,7 @@ def main():
         for r in d["rooflines"]["kernels"]:
             lines.append("| %s | %.1f | %.1f MB | %.0f | %.3f | %.3f |" % (r["kernel"], r["ms"] * 1e3, r["bytes"] / 1e6, r["achieved"], r["frac"], r["frac_nominal_8tbs"]))
         lines.append("")
-    for name in ("r2_bench_n2", "r2_bench_c4_n2", "r2_bench_n8", "r2_bench_c4_n8"):
+    for name in ("r2_bench_n2", "r2_bench_c4_n2", "r2_bench_n4", "r2_bench_n8", "r2_bench_c4_n8"):
         p = os.path.join(HERE, name + ".json")
         if os.path.exists(p):
             d = json.load(open(p))
